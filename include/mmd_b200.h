@@ -1,0 +1,136 @@
+/* mmd_b200.h -- C ABI of the B200-native constrained-HMC hot path.
+ *
+ * Drop-in boundary for the path that the reference drives through
+ * sde/mici_extensions.py (ConditionedDiffusionConstrainedSystem :208-1259, the projection solvers
+ * :1323-1476, SwitchPartitionTransition :1262-1282) and Mici's ConstrainedLeapfrogIntegrator
+ * (call site scripts/utils.py:284-290).  The reference has no FFI of its own (it is pure Python on
+ * JAX); each entry point below names the reference function it replaces.  All chains of a handle
+ * share one model configuration and are processed as one batch.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures; `double*` arguments are HOST pointers unless
+ *     the name ends in `_dev`;
+ *   - host arrays use the reference's per-chain layout: q, p, vct: [n_chains][dim_q] row-major with
+ *     q = [u | v_0 | v_seq(T*S, dim_v) | n(T, dim_y)] (mici_extensions.py:476-484);
+ *     x_obs_seq: [n_chains][T][dim_x]; constraint vectors: [n_chains][n_c(partition)];
+ *   - return value 0 = ok, <0 = API / CUDA error (text via mmd_last_error_string); numerical
+ *     failures are per-chain status bits, never errors across the ABI:
+ *       1 not converged, 2 diverged / NaN   -> mici.errors.ConvergenceError (:1393-1402)
+ *       4 non-reversible step               -> mici.errors.NonReversibleStepError
+ *       8 non-finite Hamiltonian            -> mici.errors.HamiltonianDivergenceError
+ *   - calls are asynchronous on the handle's CUDA stream; getters synchronise.  One handle per host
+ *     thread / GPU (thread-compatible, not thread-safe).
+ */
+#ifndef MMD_B200_H
+#define MMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mmd_handle_s* mmd_handle;
+
+enum { MMD_MODEL_FHN = 0, MMD_MODEL_SIR = 1 };
+enum { MMD_NOISE_NONE = 0, MMD_NOISE_FIXED = 1, MMD_NOISE_PARAM = 2 };
+enum { MMD_SOLVER_QUASI_NEWTON = 0, MMD_SOLVER_NEWTON = 1 };
+
+typedef struct {
+  int model;               /* MMD_MODEL_*  (sde/example_models/{fhn,sir}.py) */
+  int num_obs;             /* T   y_seq.shape[0] */
+  int num_steps_per_obs;   /* S */
+  int num_obs_per_subseq;  /* R; <= 0 or == T: no blocking (mici_extensions.py:321-324) */
+  int dim_u;               /* dim_z, +1 when the observation noise scale is inferred */
+  int noise;               /* MMD_NOISE_*  (generate_sigma None / number / callable, :353-358) */
+  double sigma_fixed;      /* used when noise == MMD_NOISE_FIXED */
+  int gaussian_splitting;  /* use_gaussian_splitting (:303) */
+  double obs_interval;
+  const double* y_seq;     /* host [T * dim_y] */
+  int n_chains;
+  int device;              /* CUDA device ordinal */
+} mmd_config;
+
+/* ConditionedDiffusionConstrainedSystem.__init__ (:211-377) for a batch of chains. */
+int mmd_create(const mmd_config* cfg, mmd_handle* out);
+int mmd_destroy(mmd_handle h);
+const char* mmd_last_error_string(void);
+
+int mmd_dim_q(mmd_handle h);
+int mmd_num_partition(mmd_handle h);                 /* system.num_partition (:362) */
+int mmd_num_constraints(mmd_handle h, int partition); /* len(constr(...)) */
+int mmd_num_blocks(mmd_handle h, int partition);
+int mmd_n_chains(mmd_handle h);
+
+/* ---- resident chain state (ConditionedDiffusionHamiltonianState :1285-1320) ------------------ */
+/* Upload positions / momenta / conditioned states; p may be NULL (left unchanged).  Invalidates
+ * the cached linearisation like a Mici ChainState variable assignment does. */
+int mmd_set_state(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition);
+int mmd_get_state(mmd_handle h, double* q, double* p, double* x_obs_seq);
+int mmd_set_momentum(mmd_handle h, const double* p);
+/* Same with device pointers in the library's structure-of-arrays layout [rows][ld] (zero-copy
+ * path for DLPack producers); ld = mmd_leading_dim(h). */
+int mmd_leading_dim(mmd_handle h);
+int mmd_set_state_soa_dev(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_obs_seq_dev,
+                          int partition);
+int mmd_get_partition(mmd_handle h);
+
+/* ---- system ops on the resident state ----------------------------------------------------------- */
+/* jacob_constr_blocks + chol_gram_blocks + log_det_sqrt_gram (+ grad_log_det_sqrt_gram when
+ * with_grad): one evaluation fills every cached quantity (:1151-1184). */
+int mmd_linearize(mmd_handle h, int with_grad);
+/* constr (:473-519, :1151-1155) -> c_out [n_chains][n_c] */
+int mmd_constr(mmd_handle h, double* c_out);
+/* log_det_sqrt_gram (:1169-1171) -> [n_chains] ; grad_log_det_sqrt_gram (:1173-1184) -> [n_chains][dim_q] */
+int mmd_log_det_sqrt_gram(mmd_handle h, double* out);
+int mmd_grad_log_det_sqrt_gram(mmd_handle h, double* out);
+/* h = h1 + h2 (:1186-1202) -> [n_chains] */
+int mmd_hamiltonian(mmd_handle h, double* out);
+/* project_onto_cotangent_space (:1252-1254) applied to the resident momentum */
+int mmd_project_momentum(mmd_handle h);
+/* normal_space_component (:1243-1250) of host vectors vct [n_chains][dim_q] at the resident position */
+int mmd_normal_space_component(mmd_handle h, const double* vct, double* out);
+/* update_x_obs_seq / generate_x_obs_seq (:384-397, :1240-1241) from the resident position */
+int mmd_update_x_obs_seq(mmd_handle h);
+/* SwitchPartitionTransition.sample (:1279-1282) */
+int mmd_switch_partition(mmd_handle h);
+/* sample_momentum (:1256-1259): Philox-4x32-10 standard normals, then cotangent projection */
+int mmd_sample_momentum(mmd_handle h, uint64_t seed, uint64_t offset);
+
+/* Compressed factors behind jacob_constr_blocks / chol_gram_blocks, for tests and for rebuilding
+ * the reference's dense blocks on the host.  name in {"K","Psib","A","L","DinvA","LC"}; out is
+ * [rows][n_chains] (structure of arrays, chain fastest); returns rows via *rows_out when out==NULL. */
+int mmd_get_factor(mmd_handle h, const char* name, double* out, int* rows_out);
+
+/* ---- integrator ----------------------------------------------------------------------------- */
+typedef struct {
+  int solver;              /* MMD_SOLVER_* */
+  double constraint_tol;   /* projection_solver_kwargs (scripts/utils.py:278-282) */
+  double position_tol;
+  double divergence_tol;
+  int max_iters;
+  double reverse_check_tol; /* ConstrainedLeapfrogIntegrator(reverse_check_tol=...) */
+} mmd_integrator_opts;
+void mmd_default_integrator_opts(mmd_integrator_opts* o);
+
+/* One ConstrainedLeapfrogIntegrator.step (n_inner_step = 1) of size `dt` (signed = dir * step_size)
+ * for every chain.  Chains whose step fails keep their state; their status bits say why. */
+int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts);
+/* per-chain status / diagnostics of the last step (any pointer may be NULL) */
+int mmd_get_step_info(mmd_handle h, int* status, int* iters_fwd, int* iters_rev, double* rev_dist);
+/* jitted_solve_projection_onto_manifold_quasi_newton (:1323-1402) on host inputs: projects
+ * q [n][dim_q] using the linearisation at the resident position; returns projected q and mu. */
+int mmd_project_quasi_newton(mmd_handle h, const double* q_in, double dt, const mmd_integrator_opts* opts,
+                             double* q_out, int* status, int* iters);
+
+/* number of kernel launches issued since creation (bench.py's gpu_launches) and event timing on the
+ * handle's stream */
+long long mmd_launch_count(mmd_handle h);
+int mmd_timer_start(mmd_handle h);
+int mmd_timer_stop_ms(mmd_handle h, float* ms);
+int mmd_synchronize(mmd_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMD_B200_H */

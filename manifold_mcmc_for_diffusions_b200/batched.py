@@ -1,0 +1,195 @@
+"""Batched (many-chain) host interface to the CUDA constrained-HMC path.
+
+``BatchedChains`` mirrors, for a batch of chains held resident in HBM, the per-state methods of the
+reference's ``ConditionedDiffusionConstrainedSystem`` (``sde/mici_extensions.py:1151-1259``) and one
+``ConstrainedLeapfrogIntegrator.step``.  Array arguments are NumPy float64 in the reference's
+per-chain layout (``q`` is ``[n_chains, dim_q]``); they are passed to C zero-copy.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import MmdConfig, MmdIntegratorOpts, check, lib
+
+MODEL_IDS = {"fhn": 0, "sir": 1}
+STATUS_NOT_CONVERGED, STATUS_DIVERGED, STATUS_NON_REVERSIBLE, STATUS_NON_FINITE = 1, 2, 4, 8
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class BatchedChains:
+    def __init__(
+        self,
+        model,
+        obs_interval,
+        num_steps_per_obs,
+        num_obs_per_subseq,
+        y_seq,
+        dim_u,
+        n_chains,
+        noise=0,
+        sigma_fixed=0.0,
+        use_gaussian_splitting=False,
+        device=0,
+    ):
+        self._L = lib()
+        self._y = _c(np.asarray(y_seq).reshape(-1))
+        cfg = MmdConfig(
+            MODEL_IDS[model],
+            int(np.asarray(y_seq).shape[0]),
+            int(num_steps_per_obs),
+            int(num_obs_per_subseq) if num_obs_per_subseq else 0,
+            int(dim_u),
+            int(noise),
+            float(sigma_fixed),
+            int(bool(use_gaussian_splitting)),
+            float(obs_interval),
+            _dp(self._y),
+            int(n_chains),
+            int(device),
+        )
+        self._h = C.c_void_p()
+        check(self._L.mmd_create(C.byref(cfg), C.byref(self._h)))
+        self.n_chains = int(n_chains)
+        self.dim_q = self._L.mmd_dim_q(self._h)
+        self.num_partition = self._L.mmd_num_partition(self._h)
+        self.num_obs = cfg.num_obs
+        self.opts = MmdIntegratorOpts()
+        self._L.mmd_default_integrator_opts(C.byref(self.opts))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.mmd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state -------------------------------------------------------------------------
+    @property
+    def partition(self):
+        return self._L.mmd_get_partition(self._h)
+
+    def num_constraints(self, partition=None):
+        return self._L.mmd_num_constraints(self._h, self.partition if partition is None else partition)
+
+    def set_state(self, q, x_obs_seq, partition=0, p=None):
+        q = _c(q)
+        x = _c(x_obs_seq)
+        assert q.shape == (self.n_chains, self.dim_q), q.shape
+        assert x.shape[0] == self.n_chains and x.size == self.n_chains * x.shape[1] * x.shape[2]
+        pp = None if p is None else _c(p)
+        check(self._L.mmd_set_state(self._h, _dp(q), None if pp is None else _dp(pp), _dp(x), int(partition)))
+        self._dim_x = x.shape[2]
+
+    def set_momentum(self, p):
+        check(self._L.mmd_set_momentum(self._h, _dp(_c(p))))
+
+    def get_state(self):
+        q = np.empty((self.n_chains, self.dim_q))
+        p = np.empty((self.n_chains, self.dim_q))
+        x = np.empty((self.n_chains, self.num_obs, self._dim_x))
+        check(self._L.mmd_get_state(self._h, _dp(q), _dp(p), _dp(x)))
+        return q, p, x
+
+    # ---- system ops --------------------------------------------------------------------
+    def linearize(self, with_grad=True):
+        check(self._L.mmd_linearize(self._h, int(with_grad)))
+
+    def constr(self):
+        out = np.empty((self.n_chains, self.num_constraints()))
+        check(self._L.mmd_constr(self._h, _dp(out)))
+        return out
+
+    def log_det_sqrt_gram(self):
+        out = np.empty(self.n_chains)
+        check(self._L.mmd_log_det_sqrt_gram(self._h, _dp(out)))
+        return out
+
+    def grad_log_det_sqrt_gram(self):
+        out = np.empty((self.n_chains, self.dim_q))
+        check(self._L.mmd_grad_log_det_sqrt_gram(self._h, _dp(out)))
+        return out
+
+    def hamiltonian(self):
+        out = np.empty(self.n_chains)
+        check(self._L.mmd_hamiltonian(self._h, _dp(out)))
+        return out
+
+    def project_momentum(self):
+        check(self._L.mmd_project_momentum(self._h))
+
+    def normal_space_component(self, vct):
+        vct = _c(vct)
+        out = np.empty_like(vct)
+        check(self._L.mmd_normal_space_component(self._h, _dp(vct), _dp(out)))
+        return out
+
+    def update_x_obs_seq(self):
+        check(self._L.mmd_update_x_obs_seq(self._h))
+
+    def switch_partition(self):
+        check(self._L.mmd_switch_partition(self._h))
+
+    def sample_momentum(self, seed, offset=0):
+        check(self._L.mmd_sample_momentum(self._h, int(seed), int(offset)))
+
+    def get_factor(self, name):
+        rows = C.c_int()
+        check(self._L.mmd_get_factor(self._h, name.encode(), None, C.byref(rows)))
+        out = np.empty((rows.value, self.n_chains))
+        check(self._L.mmd_get_factor(self._h, name.encode(), _dp(out), C.byref(rows)))
+        return out
+
+    # ---- integrator --------------------------------------------------------------------
+    def leapfrog_step(self, dt):
+        check(self._L.mmd_leapfrog_step(self._h, float(dt), C.byref(self.opts)))
+
+    def step_info(self):
+        st = np.empty(self.n_chains, dtype=np.int32)
+        i0 = np.empty(self.n_chains, dtype=np.int32)
+        i1 = np.empty(self.n_chains, dtype=np.int32)
+        rv = np.empty(self.n_chains)
+        check(self._L.mmd_get_step_info(self._h, _ip(st), _ip(i0), _ip(i1), _dp(rv)))
+        return {"status": st, "iters_fwd": i0, "iters_rev": i1, "rev_dist": rv}
+
+    def project_quasi_newton(self, q_in, dt=1.0):
+        q_in = _c(q_in)
+        out = np.empty_like(q_in)
+        st = np.empty(self.n_chains, dtype=np.int32)
+        it = np.empty(self.n_chains, dtype=np.int32)
+        check(
+            self._L.mmd_project_quasi_newton(
+                self._h, _dp(q_in), float(dt), C.byref(self.opts), _dp(out), _ip(st), _ip(it)
+            )
+        )
+        return out, st, it
+
+    # ---- instrumentation ----------------------------------------------------------------
+    def launch_count(self):
+        return int(self._L.mmd_launch_count(self._h))
+
+    def timer_start(self):
+        check(self._L.mmd_timer_start(self._h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        check(self._L.mmd_timer_stop_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def synchronize(self):
+        check(self._L.mmd_synchronize(self._h))

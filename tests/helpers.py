@@ -1,0 +1,52 @@
+"""Shared problem builders for the parity tests (oracle side + seeded inputs)."""
+
+import numpy as np
+import torch
+
+from oracle import torch_oracle as O
+from oracle.models import fhn, fhn_simulate_y_seq_numpy
+
+Z_TRUE = np.array([0.3, 0.1, 1.5, 0.8])  # fhn_model_noiseless_obs_chmc_experiment.py:41-46
+X0_TRUE = np.array([-0.5, 0.2])
+OBS_INTERVAL = 0.2
+SEED = 20200710
+
+
+def make_fhn_problem(T, S, R, n_chains, nd=1000, seed=SEED):
+    """Simulated data + oracle system + linear-interpolation initial states for `n_chains` chains
+    (restates fhn_model_noiseless_obs_chmc_experiment.py:84-134 with `nd` fine steps per obs)."""
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((T * nd, 2))
+    y = fhn_simulate_y_seq_numpy(Z_TRUE, X0_TRUE, v, OBS_INTERVAL / nd, nd)
+    system = O.OracleSystem(
+        OBS_INTERVAL, S, R, y, 4, 2, 2, fhn.forward_func, fhn.generate_x_0, fhn.generate_z, fhn.obs_func,
+        None, False, dim_v_0=2,
+    )
+
+    def gen_init(rng_):
+        return np.concatenate((y, rng_.standard_normal(y.shape) * 0.5), -1)
+
+    qs, xs = [], []
+    for c in range(n_chains):
+        crng = np.random.default_rng([seed, c])
+        u = crng.standard_normal(4) * 0.5
+        v0 = crng.standard_normal(2)
+        q, xo = O.find_initial_state_by_linear_interpolation(system, crng, gen_init, u=u, v_0=v0)
+        qs.append(q.numpy())
+        xs.append(xo.numpy())
+    return dict(T=T, S=S, R=R, y=y, system=system, q=np.stack(qs), xobs=np.stack(xs))
+
+
+def make_batched(prob, n_chains=None):
+    from manifold_mcmc_for_diffusions_b200 import BatchedChains
+
+    n = prob["q"].shape[0] if n_chains is None else n_chains
+    return BatchedChains("fhn", OBS_INTERVAL, prob["S"], prob["R"], prob["y"], 4, n)
+
+
+def oracle_momentum(prob, q, xobs, part, seed):
+    """Projected momentum for one chain from a seeded normal draw (both sides get the same draw)."""
+    rng = np.random.default_rng(seed)
+    p = torch.tensor(rng.standard_normal(q.shape[0]))
+    pt = prob["system"].point(q, xobs, part)
+    return prob["system"].project_onto_cotangent_space(p, pt).numpy(), pt
