@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Headline benchmark: constrained-HMC leapfrog steps/s over all chains, FHN noiseless T=100, S=25, R=5.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one ConstrainedLeapfrogIntegrator.step (both projection solves, reversibility check,
+grad log-det) for every chain of the rank (default 4096 chains per GPU, weak scaling).  Momentum
+refresh (Philox, on device), the Metropolis accept and the partition switch happen every
+`--traj-len` steps INSIDE the timed region; only successful chain-steps are counted.
+Prints ONE JSON line (see DESIGN.md "Measurement").
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T, S, R = 100, 25, 5
+OBS_INTERVAL = 0.2
+SEED = 20200710
+METRIC = "chmc_leapfrog_steps_per_s"
+UNIT = "chain-steps/s"
+WORKLOAD = "FHN noiseless-obs CHMC, T=100 obs x S=25 steps/obs, R=5, quasi-Newton projection, float64"
+
+
+def load_y():
+    return np.load(os.path.join(ROOT, "tests", "golden", "fhn_yseq_T100.npy"))
+
+
+def init_inputs(n, rank):
+    """Synthetic initial states: the reference recipe (fhn_model_noiseless_obs_chmc_experiment.py:
+    120-134) with a per-rank generator."""
+    y = load_y()
+    rng = np.random.default_rng([SEED, rank])
+    u = rng.standard_normal((n, 4))
+    v0 = rng.standard_normal((n, 2))
+    xo = np.concatenate((np.broadcast_to(y, (n, T, 1)), 0.5 * rng.standard_normal((n, T, 1))), -1)
+    return y, u, v0, xo
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip().split(",")
+                self.samples.append((float(out[0]), float(out[1])))
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons)}
+
+
+# work model (SURVEY.md 8d / DESIGN.md): bytes one quasi-Newton sweep must read per chain
+def qn_sweep_bytes_per_chain():
+    n_steps = T * S
+    # per step: work position v_t (2 doubles) + compressed Jacobian K_t (4 doubles)
+    return 8 * (n_steps * (2 + 4))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from manifold_mcmc_for_diffusions_b200 import BatchedChains
+
+    n = args.chains
+    y, u, v0, xo = init_inputs(n, rank)
+    bc = BatchedChains("fhn", OBS_INTERVAL, S, R, y, 4, n, device=local_rank)
+    bc.init_linear_interpolation(u, v0, xo, 0)
+    L = args.traj_len
+    # untimed burn-in towards the typical set (the linear-interpolation states are far in the tails)
+    for it in range(args.burnin):
+        bc.hmc_transition(args.burnin_dt, L, SEED + rank, it)
+    bc.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        bc.synchronize()
+
+    it_counter = [args.burnin]
+
+    def do_steps(k):
+        for s in range(k):
+            if s % L == 0:
+                bc.transition_begin(SEED + rank, it_counter[0])
+            bc.transition_step(args.dt)
+            if s % L == L - 1:
+                bc.transition_end(SEED + rank, it_counter[0], True)
+                it_counter[0] += 1
+        if k % L != 0:
+            bc.transition_end(SEED + rank, it_counter[0], True)
+            it_counter[0] += 1
+
+    do_steps(args.warmup)
+    bc.successful_steps(reset=True)
+    launches0 = bc.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    bc.profile_enable(True, 64 * args.steps + 64)
+    barrier()
+    bc.timer_start()
+    do_steps(args.steps)
+    ms = bc.timer_stop_ms()
+    barrier()
+    sampler.stop_flag = True
+    bc.profile_enable(False)
+    launches = bc.launch_count() - launches0
+    ok = bc.successful_steps()
+    st = bc.transition_stats()
+    info = bc.step_info()
+    n_qn, ms_qn = bc.profile_summary(2)
+    n_pt, ms_pt = bc.profile_summary(0)
+    n_pj, ms_pj = bc.profile_summary(1)
+
+    # ---- end to end through the public API with host buffers (pinned), every step ----
+    e2e_steps = min(args.steps, args.e2e_steps)
+    q_h, p_h, x_h = bc.get_state()
+    pin = [torch.from_numpy(a).pin_memory() for a in (q_h, p_h, x_h)]
+    qn_, pn_, xn_ = [t.numpy() for t in pin]
+    part = bc.partition
+    barrier()
+    t0 = time.perf_counter()
+    ok_e2e = 0
+    for s in range(e2e_steps):
+        bc.set_state(qn_, xn_, part, p=pn_)      # H2D of this step's inputs
+        bc.leapfrog_step(args.dt)
+        inf = bc.step_info()                      # D2H of the step's result (status, iterations, reverse dist)
+        ok_e2e += int((inf["status"] == 0).sum())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = int(qn_.nbytes + pn_.nbytes + xn_.nbytes)
+    d2h = int(n * (4 + 4 + 4 + 8))
+
+    vals = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    tot = torch.tensor([float(ok), float(ok_e2e), float(launches)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = vals.tolist()
+    ok_tot, ok_e2e_tot, launches_tot = tot.tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        # roofline of the dominant kernel (k_qn): algorithmic bytes = sweeps x bytes per sweep
+        iters_mean = float(info["iters_fwd"].mean() + info["iters_rev"].mean()) / 2.0
+        sweeps_per_launch = iters_mean + 1.0  # + the finalisation pass over K
+        alg_bytes = n * qn_sweep_bytes_per_chain() * sweeps_per_launch
+        qn_ms = ms_qn / max(n_qn, 1)
+        achieved = alg_bytes / (qn_ms * 1e-3) / 1e9 if qn_ms > 0 else 0.0
+        out = {
+            "metric": METRIC,
+            "value": ok_tot / (ms_max * 1e-3),
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD,
+                "chains_per_gpu": n,
+                "step_size": args.dt,
+                "traj_len": L,
+                "burnin_transitions": args.burnin,
+                "l2": "per-step working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2)"
+                % (n * 450e3 / 1e9),
+                "step_success_frac": ok_tot / (n * world * args.steps),
+                "accept_stat_last": float(st["accept_stat"].mean()),
+                "qn_iters_mean": iters_mean,
+            },
+            "roofline": {
+                "bound": "hbm",
+                "kernel": "k_qn (on-device quasi-Newton projection)",
+                "achieved": achieved,
+                "peak": hbm_peak,
+                "unit": "GB/s",
+                "frac": achieved / hbm_peak,
+                "traffic": None,
+                "peak_source": peak_src,
+                "kernel_ms": {"k_qn": qn_ms, "k_point": ms_pt / max(n_pt, 1), "k_project": ms_pj / max(n_pj, 1)},
+                "share_of_step": {
+                    "k_qn": ms_qn / ms, "k_point": ms_pt / ms, "k_project": ms_pj / ms,
+                },
+            },
+            "e2e": {
+                "value": ok_e2e_tot / (e2e_ms_max * 1e-3),
+                "unit": UNIT,
+                "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps,
+            },
+            "gpu_launches": int(launches_tot),
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(out))
+    bc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (port of the reference path) on the host cores, bounded sample
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    chain, n_steps, dt = args
+    import torch
+
+    torch.set_num_threads(1)
+    from oracle import torch_oracle as O
+    from oracle.models import fhn
+
+    y = load_y()
+    sysm = O.OracleSystem(
+        OBS_INTERVAL, S, R, y, 4, 2, 2, fhn.forward_func, fhn.generate_x_0, fhn.generate_z, fhn.obs_func,
+        None, False, dim_v_0=2,
+    )
+    rng = np.random.default_rng([SEED, 10_000 + chain])
+
+    def gen_init(rng_):
+        return np.concatenate((y, rng_.standard_normal(y.shape) * 0.5), -1)
+
+    q, xo = O.find_initial_state_by_linear_interpolation(
+        sysm, rng, gen_init, u=0.3 * rng.standard_normal(4), v_0=rng.standard_normal(2)
+    )
+    pt = sysm.point(q, xo, 0)
+    p = sysm.project_onto_cotangent_space(torch.tensor(rng.standard_normal(q.shape[0])), pt)
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(n_steps):
+        try:
+            q, p, pt, _ = O.leapfrog_step(sysm, q, p, xo, 0, dt, pt=pt)
+            done += 1
+        except (O.ConvergenceError, O.NonReversibleStepError):
+            break
+    return done, time.perf_counter() - t0
+
+
+def cpu_baseline(seconds_hint=20.0, steps_per_chain=1, dt=0.02):
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(c, steps_per_chain, dt) for c in range(cores)])
+    wall = time.perf_counter() - t0
+    done = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return {
+        "value": done / busy if busy > 0 else 0.0,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{cores} chains x {steps_per_chain} leapfrog step(s), one process per core, torch.func float64 "
+                  f"oracle (oracle/torch_oracle.py), timed region {busy:.1f}s of {wall:.1f}s wall",
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cb = cpu_baseline(steps_per_chain=max(1, args.steps // 8) if args.steps >= 8 else 1)
+    out = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": cb["value"],
+        "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": None,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=4096, help="chains per GPU")
+    ap.add_argument("--dt", type=float, default=0.1)
+    ap.add_argument("--traj-len", type=int, default=8)
+    ap.add_argument("--burnin", type=int, default=150)
+    ap.add_argument("--burnin-dt", type=float, default=0.05)
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

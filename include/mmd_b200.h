@@ -116,6 +116,19 @@ void mmd_default_integrator_opts(mmd_integrator_opts* o);
 /* One ConstrainedLeapfrogIntegrator.step (n_inner_step = 1) of size `dt` (signed = dir * step_size)
  * for every chain.  Chains whose step fails keep their state; their status bits say why. */
 int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts);
+/* One full Markov transition for every chain, entirely on device: IndependentMomentumTransition
+ * (Philox draw keyed by (seed, iter) + cotangent projection), `n_leapfrog` constrained leapfrog
+ * steps of size dt, Metropolis accept on the Hamiltonian error (integrator errors reject), then
+ * optionally SwitchPartitionTransition (scripts/utils.py:292-301; static instead of dynamic
+ * trajectory length). */
+int mmd_hmc_transition(mmd_handle h, double dt, int n_leapfrog, uint64_t seed, uint64_t iter,
+                       const mmd_integrator_opts* opts, int switch_partition);
+/* The same transition in three calls so a driver can interleave its own work between steps. */
+int mmd_transition_begin(mmd_handle h, uint64_t seed, uint64_t iter);
+int mmd_transition_step(mmd_handle h, double dt, const mmd_integrator_opts* opts);
+int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_partition);
+/* accepted flag, accept_stat = min(1, exp(h0 - h1)), integrator status of the last transition */
+int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, int* status);
 /* per-chain status / diagnostics of the last step (any pointer may be NULL) */
 int mmd_get_step_info(mmd_handle h, int* status, int* iters_fwd, int* iters_rev, double* rev_dist);
 /* jitted_solve_projection_onto_manifold_quasi_newton (:1323-1402) on host inputs: projects
@@ -123,9 +136,20 @@ int mmd_get_step_info(mmd_handle h, int* status, int* iters_fwd, int* iters_rev,
 int mmd_project_quasi_newton(mmd_handle h, const double* q_in, double dt, const mmd_integrator_opts* opts,
                              double* q_out, int* status, int* iters);
 
+/* find_initial_state_by_linear_interpolation (:1479-1547) for every chain: u [n][dim_u],
+ * v_0 [n][dim_v_0], x_obs_seq [n][T][dim_x] (host); fills the resident position and x_obs_seq. */
+int mmd_init_linear_interpolation(mmd_handle h, const double* u, const double* v_0, const double* x_obs_seq,
+                                  int partition);
+
 /* number of kernel launches issued since creation (bench.py's gpu_launches) and event timing on the
  * handle's stream */
 long long mmd_launch_count(mmd_handle h);
+/* total successful chain leapfrog steps since creation / last reset (device-side counter) */
+long long mmd_successful_steps(mmd_handle h, int reset);
+/* per-kernel CUDA-event timing on the handle's stream: kernel ids 0 linearise (k_point), 1 momentum
+ * projection (k_project), 2 quasi-Newton projection (k_qn) */
+int mmd_profile_enable(mmd_handle h, int on, int max_launches);
+int mmd_profile_summary(mmd_handle h, int kernel_id, int* count, double* total_ms);
 int mmd_timer_start(mmd_handle h);
 int mmd_timer_stop_ms(mmd_handle h, float* ms);
 int mmd_synchronize(mmd_handle h);

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmd_b200.so")
+LIB_PATH = os.environ.get("MMD_B200_LIB", os.path.join(_HERE, "libmmd_b200.so"))  # override: tuning builds
 
 
 class MmdError(RuntimeError):
@@ -82,6 +82,18 @@ SIGNATURES = {
         C.c_int,
         [_H, _dp, C.c_double, C.POINTER(MmdIntegratorOpts), _dp, _ip, _ip],
     ),
+    "mmd_init_linear_interpolation": (C.c_int, [_H, _dp, _dp, _dp, C.c_int]),
+    "mmd_hmc_transition": (
+        C.c_int,
+        [_H, C.c_double, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(MmdIntegratorOpts), C.c_int],
+    ),
+    "mmd_get_transition_stats": (C.c_int, [_H, _ip, _dp, _ip]),
+    "mmd_transition_begin": (C.c_int, [_H, C.c_uint64, C.c_uint64]),
+    "mmd_transition_step": (C.c_int, [_H, C.c_double, C.POINTER(MmdIntegratorOpts)]),
+    "mmd_transition_end": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int]),
+    "mmd_successful_steps": (C.c_longlong, [_H, C.c_int]),
+    "mmd_profile_enable": (C.c_int, [_H, C.c_int, C.c_int]),
+    "mmd_profile_summary": (C.c_int, [_H, C.c_int, _ip, _dp]),
     "mmd_launch_count": (C.c_longlong, [_H]),
     "mmd_timer_start": (C.c_int, [_H]),
     "mmd_timer_stop_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),

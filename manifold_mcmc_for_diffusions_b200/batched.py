@@ -96,6 +96,12 @@ class BatchedChains:
         check(self._L.mmd_set_state(self._h, _dp(q), None if pp is None else _dp(pp), _dp(x), int(partition)))
         self._dim_x = x.shape[2]
 
+    def init_linear_interpolation(self, u, v_0, x_obs_seq, partition=0):
+        """Batched `find_initial_state_by_linear_interpolation` (mici_extensions.py:1479-1547)."""
+        u, v_0, x = _c(u), _c(v_0), _c(x_obs_seq)
+        self._dim_x = x.shape[2]
+        check(self._L.mmd_init_linear_interpolation(self._h, _dp(u), _dp(v_0), _dp(x), int(partition)))
+
     def set_momentum(self, p):
         check(self._L.mmd_set_momentum(self._h, _dp(_c(p))))
 
@@ -158,6 +164,42 @@ class BatchedChains:
     # ---- integrator --------------------------------------------------------------------
     def leapfrog_step(self, dt):
         check(self._L.mmd_leapfrog_step(self._h, float(dt), C.byref(self.opts)))
+
+    def hmc_transition(self, dt, n_leapfrog, seed, it, switch_partition=True):
+        """Momentum refresh + static constrained trajectory + Metropolis accept (+ partition switch)."""
+        check(
+            self._L.mmd_hmc_transition(
+                self._h, float(dt), int(n_leapfrog), int(seed), int(it), C.byref(self.opts), int(switch_partition)
+            )
+        )
+
+    def transition_begin(self, seed, it):
+        check(self._L.mmd_transition_begin(self._h, int(seed), int(it)))
+
+    def transition_step(self, dt):
+        check(self._L.mmd_transition_step(self._h, float(dt), C.byref(self.opts)))
+
+    def transition_end(self, seed, it, switch_partition=True):
+        check(self._L.mmd_transition_end(self._h, int(seed), int(it), int(switch_partition)))
+
+    def successful_steps(self, reset=False):
+        return int(self._L.mmd_successful_steps(self._h, int(reset)))
+
+    def profile_enable(self, on, max_launches=4096):
+        check(self._L.mmd_profile_enable(self._h, int(on), int(max_launches)))
+
+    def profile_summary(self, kernel_id):
+        n = C.c_int()
+        ms = C.c_double()
+        check(self._L.mmd_profile_summary(self._h, int(kernel_id), C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def transition_stats(self):
+        acc = np.empty(self.n_chains, dtype=np.int32)
+        ap = np.empty(self.n_chains)
+        st = np.empty(self.n_chains, dtype=np.int32)
+        check(self._L.mmd_get_transition_stats(self._h, _ip(acc), _dp(ap), _ip(st)))
+        return {"accepted": acc, "accept_stat": ap, "status": st}
 
     def step_info(self):
         st = np.empty(self.n_chains, dtype=np.int32)

@@ -1,0 +1,18 @@
+// Host-side (g++) build of the generated model functors so their arithmetic can be unit-tested
+// on a machine without a GPU (tests/test_model_functor_host.py).  Not part of the product path.
+#include "mmd_model_fhn.cuh"
+#include "mmd_philox.cuh"
+
+extern "C" {
+void fhn_step(const double* z, double sd, const double* x, const double* v, double* xn) { FhnModel::step(z, sd, x, v, xn); }
+void fhn_jac_x(const double* z, double sd, const double* x, const double* v, double* F) { FhnModel::jac_x(z, sd, x, v, F); }
+void fhn_jac_v(const double* z, double sd, const double* x, const double* v, double* B) { FhnModel::jac_v(z, sd, x, v, B); }
+void fhn_jac_z(const double* z, double sd, const double* x, const double* v, double* G) { FhnModel::jac_z(z, sd, x, v, G); }
+void fhn_hess_contract(const double* z, double sd, const double* x, const double* v, const double* Th, double* g) {
+  FhnModel::hess_contract(z, sd, x, v, Th, g);
+}
+void fhn_gen_z(const double* u, double* z, double* dzdu) { FhnModel::gen_z(u, z, dzdu); }
+void philox_normal_pair(unsigned long long seed, unsigned long long offset, unsigned long long idx, double* a, double* b) {
+  mmd::philox_normal_pair(seed, offset, idx, a, b);
+}
+}

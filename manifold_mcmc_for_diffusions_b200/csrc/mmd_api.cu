@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -54,6 +55,10 @@ struct mmd_handle_s {
   double* stage;  // [n_chains * max(dim_q, ...)] AoS staging
   double* stage2;
   double* hbuf;   // [ld]
+  double* h0buf;  // [ld]
+  double* qsave;  // [dim_q][ld]
+  double* accp;   // [ld]
+  int* accepted;  // [ld]
   int partition;
   int ncmax, nbmax;
   int cpb, nslot;
@@ -63,6 +68,12 @@ struct mmd_handle_s {
   long long launches;
   bool lin_valid;
   std::vector<void*> allocs;
+  // optional per-kernel event timing (bench.py's roofline leg)
+  bool prof_on;
+  std::vector<cudaEvent_t> prof_ev;   // pairs
+  std::vector<int> prof_kid;
+  size_t prof_used;
+  long long* n_ok;   // [ld] successful leapfrog steps per chain (device counter)
 };
 
 namespace {
@@ -83,10 +94,31 @@ void partition_shapes(int T, int R, int init, int* nb, int* fin) {
   *nb = 2 + (num_middle > 0 ? num_middle : 0);
 }
 
+enum { KID_POINT = 0, KID_PROJECT = 1, KID_QN = 2, KID_FLOW = 3, KID_OTHER = 4, KID_COUNT = 5 };
+
+struct ProfScope {
+  mmd_handle h;
+  size_t idx;
+  bool on;
+  ProfScope(mmd_handle h_, int kid) : h(h_), idx(0), on(false) {
+    if (h->prof_on && h->prof_used + 2 <= h->prof_ev.size()) {
+      on = true;
+      idx = h->prof_used;
+      h->prof_used += 2;
+      h->prof_kid.push_back(kid);
+      cudaEventRecord(h->prof_ev[idx], h->stream);
+    }
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(h->prof_ev[idx + 1], h->stream);
+  }
+};
+
 template <int CPB, int NSLOT>
 struct K {
   using Mdl = FhnModel;
   static int point(mmd_handle h, int which, int with_grad) {
+    ProfScope ps(h, KID_POINT);
     auto kern = k_point<Mdl, CPB, NRMAX, RMAX, UMAX, CPB * NSLOT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(h->d, h->S, h->W, h->xobs, h->y,
@@ -103,6 +135,7 @@ struct K {
     return 0;
   }
   static int project(mmd_handle h, int lin, int src, int dst, double hh, double qcoef) {
+    ProfScope ps(h, KID_PROJECT);
     auto kern = k_project<Mdl, CPB, NRMAX, UMAX, CPB * NSLOT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(h->d, h->S, h->W, h->partition, lin, src,
@@ -112,6 +145,7 @@ struct K {
     return 0;
   }
   static int qn(mmd_handle h, int mode, double mom_coef, const mmd_integrator_opts* o) {
+    ProfScope ps(h, KID_QN);
     auto kern = k_qn<Mdl, CPB, NRMAX, UMAX, CPB * NSLOT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(
@@ -122,7 +156,7 @@ struct K {
     return 0;
   }
   static int hamiltonian(mmd_handle h, int sel, double* out) {
-    k_hamiltonian<CPB><<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(h->d, h->S, h->W, sel, out);
+    k_hamiltonian<CPB><<<h->d.ld / CPB, CPB * h->nslot, (size_t)h->nslot * CPB * sizeof(double), h->stream>>>(h->d, h->S, h->W, sel, out);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -258,7 +292,8 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   d.ld = (cfg->n_chains + 31) / 32 * 32;
   h->ncmax = d.n_c[0] > d.n_c[1] ? d.n_c[0] : d.n_c[1];
   h->nbmax = d.nb[0] > d.nb[1] ? d.nb[0] : d.nb[1];
-  if (h->nbmax <= 24) { h->cpb = 32; }
+  const char* cpb_env = getenv("MMD_CPB");  // tuning override
+  if (h->nbmax <= 24 && !(cpb_env && atoi(cpb_env) == 8)) { h->cpb = 32; }
   else if (h->nbmax <= 128) { h->cpb = 8; }
   else { delete h; FAIL("too many observation blocks for this build"); }
   h->nslot = h->nbmax;
@@ -267,6 +302,8 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   h->launches = 0;
+  h->prof_on = false;
+  h->prof_used = 0;
   h->lin_valid = false;
   h->partition = 0;
 
@@ -314,6 +351,11 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   rc |= dalloc(h, &h->stage, stage_n);
   rc |= dalloc(h, &h->stage2, (size_t)d.dim_q * ld);
   rc |= dalloc(h, &h->hbuf, ld);
+  rc |= dalloc(h, &h->h0buf, ld);
+  rc |= dalloc(h, &h->qsave, (size_t)d.dim_q * ld);
+  rc |= dalloc(h, &h->accp, ld);
+  rc |= dalloc(h, &h->accepted, ld);
+  rc |= dalloc(h, &h->n_ok, ld);
   if (rc) { mmd_destroy(h); return -2; }
   CK(cudaMemcpyAsync(h->y, cfg->y_seq, (size_t)T * Mdl::Y * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -325,6 +367,7 @@ int mmd_destroy(mmd_handle h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -498,7 +541,7 @@ int mmd_get_factor(mmd_handle h, const char* name, double* out, int* rows_out) {
   return 0;
 }
 
-int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts) {
+static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opts, bool reset_status) {
   mmd_integrator_opts o;
   if (opts) o = *opts; else mmd_default_integrator_opts(&o);
   if (o.solver != MMD_SOLVER_QUASI_NEWTON) FAIL("only the quasi-Newton projection solver is built");
@@ -506,7 +549,7 @@ int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts) 
     int rc0 = mmd_linearize(h, 1);
     if (rc0) return rc0;
   }
-  CK(cudaMemsetAsync(h->W.status, 0, h->d.ld * sizeof(int), h->stream));
+  if (reset_status) CK(cudaMemsetAsync(h->W.status, 0, h->d.ld * sizeof(int), h->stream));
   int rc = 0;
   // A(dt/2): h1_flow + cotangent projection at the current point; result -> p(other)
   rc = DISPATCH(h, project(h, 0, 0, 1, 0.5 * dt, 1.0)); if (rc) return rc;
@@ -521,9 +564,101 @@ int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts) 
   rc = DISPATCH(h, qn(h, 1, 0.0, &o)); if (rc) return rc;
   // A(dt/2)
   rc = DISPATCH(h, project(h, 1, 1, 1, 0.5 * dt, 1.0)); if (rc) return rc;
-  k_commit<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->S, h->W, o.reverse_check_tol);
+  k_commit<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->S, h->W, o.reverse_check_tol, h->n_ok);
   h->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+
+int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts) {
+  return leapfrog_impl(h, dt, opts, true);
+}
+
+int mmd_transition_begin(mmd_handle h, uint64_t seed, uint64_t iter) {
+  int rc = mmd_linearize(h, 1); if (rc) return rc;               // also clears status
+  rc = mmd_sample_momentum(h, seed, 2 * iter); if (rc) return rc;
+  rc = DISPATCH(h, hamiltonian(h, 0, h->h0buf)); if (rc) return rc;
+  if (gather(h, h->S.q, h->S.s_q, 0, h->d.dim_q, h->qsave)) return -2;
+  return 0;
+}
+
+int mmd_transition_step(mmd_handle h, double dt, const mmd_integrator_opts* opts) {
+  return leapfrog_impl(h, dt, opts, false);
+}
+
+int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_partition) {
+  int rc = DISPATCH(h, hamiltonian(h, 0, h->hbuf)); if (rc) return rc;
+  k_decide<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->W, h->h0buf, h->hbuf, seed, 2 * iter + 1,
+                                                              h->accepted, h->accp);
+  h->launches++;
+  k_restore<<<592, 256, 0, h->stream>>>(h->d, h->S, h->accepted, h->qsave);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->lin_valid = false;
+  if (switch_partition) return mmd_switch_partition(h);
+  return 0;
+}
+
+int mmd_hmc_transition(mmd_handle h, double dt, int n_leapfrog, uint64_t seed, uint64_t iter,
+                       const mmd_integrator_opts* opts, int switch_partition) {
+  // IndependentMomentumTransition + static-trajectory integration with Metropolis accept +
+  // SwitchPartitionTransition (scripts/utils.py:292-301 with a static instead of dynamic trajectory)
+  int rc = mmd_transition_begin(h, seed, iter); if (rc) return rc;
+  for (int s = 0; s < n_leapfrog; ++s) {
+    rc = leapfrog_impl(h, dt, opts, false);
+    if (rc) return rc;
+  }
+  return mmd_transition_end(h, seed, iter, switch_partition);
+}
+
+int mmd_profile_enable(mmd_handle h, int on, int max_launches) {
+  if (on) {
+    while ((int)h->prof_ev.size() < 2 * max_launches) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->prof_ev.push_back(e);
+    }
+    h->prof_used = 0;
+    h->prof_kid.clear();
+  }
+  h->prof_on = on != 0;
+  return 0;
+}
+
+int mmd_profile_summary(mmd_handle h, int kid, int* count, double* total_ms) {
+  CK(cudaStreamSynchronize(h->stream));
+  int n = 0;
+  double tot = 0.0;
+  for (size_t i = 0; i < h->prof_kid.size(); ++i) {
+    if (h->prof_kid[i] != kid) continue;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    tot += ms;
+    n++;
+  }
+  if (count) *count = n;
+  if (total_ms) *total_ms = tot;
+  return 0;
+}
+
+long long mmd_successful_steps(mmd_handle h, int reset) {
+  std::vector<long long> host(h->d.ld);
+  if (cudaMemcpyAsync(host.data(), h->n_ok, h->d.ld * sizeof(long long), cudaMemcpyDeviceToHost, h->stream) !=
+      cudaSuccess)
+    return -1;
+  cudaStreamSynchronize(h->stream);
+  long long tot = 0;
+  for (int i = 0; i < h->d.n_chains; ++i) tot += host[i];
+  if (reset) cudaMemsetAsync(h->n_ok, 0, h->d.ld * sizeof(long long), h->stream);
+  return tot;
+}
+
+int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, int* status) {
+  const int n = h->d.n_chains;
+  if (accepted) CK(cudaMemcpyAsync(accepted, h->accepted, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (accept_prob) CK(cudaMemcpyAsync(accept_prob, h->accp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (status) CK(cudaMemcpyAsync(status, h->W.status, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -551,6 +686,26 @@ int mmd_project_quasi_newton(mmd_handle h, const double* q_in, double dt, const 
   if (from_soa(h, h->stage2, q_out, h->d.dim_q)) return -2;
   (void)dt;
   return mmd_get_step_info(h, status, iters, nullptr, nullptr);
+}
+
+int mmd_init_linear_interpolation(mmd_handle h, const double* u, const double* v_0, const double* x_obs_seq,
+                                  int partition) {
+  // find_initial_state_by_linear_interpolation (:1479-1547) for all chains at once
+  if (partition < 0 || partition >= h->d.num_partition) FAIL("bad partition");
+  const Dims& d = h->d;
+  CK(cudaMemsetAsync(h->S.cur, 0, d.ld * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->W.status, 0, d.ld * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->S.q, 0, (size_t)d.dim_q * d.ld * sizeof(double), h->stream));
+  if (to_soa(h, u, h->S.q, d.U)) return -2;
+  if (to_soa(h, v_0, h->S.q + (long long)d.off_v0 * d.ld, h->V0)) return -2;
+  if (to_soa(h, x_obs_seq, h->xobs, d.T * h->X)) return -2;
+  const long long n = (long long)d.T * d.ld;
+  k_init_interp<FhnModel, UMAX><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(d, h->S.q, h->xobs);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->partition = partition;
+  h->lin_valid = false;
+  return 0;
 }
 
 int mmd_timer_start(mmd_handle h) { CK(cudaEventRecord(h->ev0, h->stream)); return 0; }

@@ -17,6 +17,10 @@
 #include "mmd_common.cuh"
 #include <stdint.h>
 
+#ifndef MMD_PREFETCH_STEPS
+#define MMD_PREFETCH_STEPS 5
+#endif
+
 namespace mmd {
 
 // ------------------------------------------------------------------------------------------
@@ -271,7 +275,35 @@ MMD_D void constr_block(const Dims& d, const Blk& B, const double* z, double sig
     double al[X];
     if (WITH_K) ldcol<X>(alph + (long long)(B.o + k) * X * ld, ld, al);
     const double* Kp = WITH_K ? Kc + g0 * X * V * ld : nullptr;
-    for (int t = 0; t < d.S; ++t) {
+    // loads do not depend on the recursion: fetch PF steps' worth of rows first, then run the steps
+    // (register-level software pipelining; the sweep is otherwise bound by global-load latency)
+    constexpr int PF = MMD_PREFETCH_STEPS;
+    int t = 0;
+    for (; t + PF <= d.S; t += PF) {
+      double vb[PF * V], Kb[WITH_K ? PF * X * V : 1];
+#pragma unroll
+      for (int i = 0; i < PF * V; ++i) vb[i] = vp[((long long)t * V + i) * ld];
+      if (WITH_K) {
+#pragma unroll
+        for (int i = 0; i < PF * X * V; ++i) Kb[i] = Kp[((long long)t * X * V + i) * ld];
+      }
+#pragma unroll
+      for (int g = 0; g < PF; ++g) {
+        double v[V], xn[X];
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = vb[g * V + j];
+        if (WITH_K) {
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+#pragma unroll
+            for (int i = 0; i < X; ++i) v[j] = fma(-Kb[g * X * V + i * V + j], al[i], v[j]);
+        }
+        M::step(z, d.sd, x, v, xn);
+#pragma unroll
+        for (int i = 0; i < X; ++i) x[i] = xn[i];
+      }
+    }
+    for (; t < d.S; ++t) {
       double v[V];
       ldcol<V>(vp + (long long)t * V * ld, ld, v);
       if (WITH_K) {

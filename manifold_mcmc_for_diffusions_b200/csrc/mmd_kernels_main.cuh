@@ -1,6 +1,7 @@
 // __global__ kernels of the CHMC hot path.  See mmd_kernels.cuh for the layout and the mapping.
 #pragma once
 #include "mmd_kernels.cuh"
+#include "mmd_philox.cuh"
 
 namespace mmd {
 
@@ -866,7 +867,7 @@ __global__ void k_flow(Dims d, Slots S, Work W, int q_sel, int p_sel, double dt)
 
 // commit / reject: successful chains flip to the new slot; reverse check (Mici
 // ConstrainedLeapfrogIntegrator._step_b: reverse_check_norm(...) > reverse_check_tol)
-__global__ void k_commit(Dims d, Slots S, Work W, double rev_tol) {
+__global__ void k_commit(Dims d, Slots S, Work W, double rev_tol, long long* __restrict__ n_ok) {
   const int chain = blockIdx.x * blockDim.x + threadIdx.x;
   if (chain >= d.n_chains) return;
   int st = W.status[chain];
@@ -874,7 +875,10 @@ __global__ void k_commit(Dims d, Slots S, Work W, double rev_tol) {
     st |= ST_NONREV;
     W.status[chain] = st;
   }
-  if (st == 0) S.cur[chain] = 1 - S.cur[chain];
+  if (st == 0) {
+    S.cur[chain] = 1 - S.cur[chain];
+    n_ok[chain] += 1;
+  }
 }
 
 // Hamiltonian h = h1 + h2 (mici_extensions.py:1186-1202) for the current slot
@@ -947,6 +951,108 @@ __global__ void k_gen_xobs(Dims d, const double* __restrict__ q, double* __restr
       for (int i = 0; i < X; ++i) x[i] = xn[i];
     }
     stcol<X>(xobs + chain + (long long)k * X * ld, ld, x);
+  }
+}
+
+// find_initial_state_by_linear_interpolation (mici_extensions.py:1479-1547), batched: one thread per
+// (chain, observation interval).  Given u, v_0 and the states at observation times, solves per
+// step for the noise vector that makes the discretised path interpolate linearly between them
+// (forward_func is affine in v; d f / d v square and invertible: X == V).
+template <class M, int UMAX>
+__global__ void k_init_interp(Dims d, double* __restrict__ q, const double* __restrict__ xobs) {
+  constexpr int X = M::X, V = M::V, Z = M::Z;
+  static_assert(X == V, "linear-interpolation initialiser needs a square noise Jacobian");
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int chain = (int)(idx % d.ld);
+  const int k = (int)(idx / d.ld);
+  if (k >= d.T || chain >= d.n_chains) return;
+  const long long ld = d.ld;
+  double* qc = q + chain;
+  double u[UMAX], z[Z], dzdu[Z * Z], xa[X], xb[X];
+  for (int j = 0; j < d.U; ++j) u[j] = qc[(long long)j * ld];
+  M::gen_z(u, z, dzdu);
+  if (k == 0) {
+    double v0[M::V0];
+    ldcol<M::V0>(qc + (long long)d.off_v0 * ld, ld, v0);
+    M::gen_x0(z, v0, xa);
+  } else {
+    ldcol<X>(xobs + chain + (long long)(k - 1) * X * ld, ld, xa);
+  }
+  ldcol<X>(xobs + chain + (long long)k * X * ld, ld, xb);
+  double dx[X];
+#pragma unroll
+  for (int i = 0; i < X; ++i) dx[i] = (xb[i] - xa[i]) / d.S;
+  for (int s = 0; s < d.S; ++s) {
+    double x[X], vz[V], m[X], Bm[X * V], rhs[X];
+#pragma unroll
+    for (int i = 0; i < X; ++i) x[i] = xa[i] + s * dx[i];
+#pragma unroll
+    for (int j = 0; j < V; ++j) vz[j] = 0.0;
+    M::step(z, d.sd, x, vz, m);
+    M::jac_v(z, d.sd, x, vz, Bm);
+#pragma unroll
+    for (int i = 0; i < X; ++i) rhs[i] = dx[i] - (m[i] - x[i]);
+    // Gaussian elimination with partial pivoting on the X x X system Bm v = rhs
+    for (int c = 0; c < X; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < X; ++r)
+        if (fabs(Bm[r * V + c]) > fabs(Bm[piv * V + c])) piv = r;
+      if (piv != c) {
+        for (int j = 0; j < V; ++j) { double t = Bm[c * V + j]; Bm[c * V + j] = Bm[piv * V + j]; Bm[piv * V + j] = t; }
+        double t = rhs[c]; rhs[c] = rhs[piv]; rhs[piv] = t;
+      }
+      for (int r = c + 1; r < X; ++r) {
+        const double f = Bm[r * V + c] / Bm[c * V + c];
+        for (int j = c; j < V; ++j) Bm[r * V + j] -= f * Bm[c * V + j];
+        rhs[r] -= f * rhs[c];
+      }
+    }
+    double v[V];
+    for (int r = X - 1; r >= 0; --r) {
+      double t = rhs[r];
+      for (int j = r + 1; j < V; ++j) t -= Bm[r * V + j] * v[j];
+      v[r] = t / Bm[r * V + r];
+    }
+    stcol<V>(qc + ((long long)d.off_v + ((long long)k * d.S + s) * V) * ld, ld, v);
+  }
+  if (d.noisy) qc[((long long)d.off_n + k) * ld] = 0.0;
+}
+
+// Metropolis accept step of a static-trajectory constrained HMC transition, on device.
+// accept iff the trajectory finished without an integrator error, the final Hamiltonian is finite
+// and log(uniform) < h0 - h1 (Mici MetropolisStaticIntegrationTransition semantics; IntegratorError
+// -> reject).  acc_prob is the `accept_stat` statistic min(1, exp(h0 - h1)).
+__global__ void k_decide(Dims d, Work W, const double* __restrict__ h0, const double* __restrict__ h1,
+                         uint64_t seed, uint64_t offset, int* __restrict__ accepted,
+                         double* __restrict__ acc_prob) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= d.n_chains) return;
+  double n0, n1;
+  (void)n1;
+  uint32_t c[4] = {(uint32_t)chain, 0u, (uint32_t)offset, (uint32_t)(offset >> 32)};
+  philox4x32_10(c, (uint32_t)seed ^ 0x5bd1e995u, (uint32_t)(seed >> 32));
+  const double uu = ((double)((((uint64_t)c[1] << 32) | c[0]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const int st = W.status[chain];
+  const double dh = h0[chain] - h1[chain];
+  const bool finite = (dh == dh) && (fabs(h1[chain]) < 1.0e300);
+  double ap = 0.0;
+  int acc = 0;
+  if (st == 0 && finite) {
+    ap = dh >= 0.0 ? 1.0 : exp(dh);
+    acc = log(uu) < dh;
+  } else if (st == 0) {
+    W.status[chain] = ST_NONFINITE;
+  }
+  n0 = ap;
+  accepted[chain] = acc;
+  acc_prob[chain] = n0;
+}
+__global__ void k_restore(Dims d, Slots S, const int* __restrict__ accepted, const double* __restrict__ qsave) {
+  const long long n = (long long)d.dim_q * d.ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int chain = (int)(i % d.ld);
+    if (chain < d.n_chains && !accepted[chain]) S.q[S.cur[chain] * S.s_q + i] = qsave[i];
   }
 }
 

@@ -810,15 +810,17 @@ def find_initial_state_by_linear_interpolation(system, rng, generate_x_obs_seq_i
     def solve_for_v_seq(x_obs_seq, x_0, z):  # :1503-1526
         def solve_inner(x, Δx):
             mean_diff, sqrt_covar_diff = mean_and_sqrt_covar_step_diff(z, x, md["δ"])
-            return torch.linalg.lstsq(sqrt_covar_diff, (Δx - mean_diff).unsqueeze(-1)).solution[:, 0]
+            # np.linalg.lstsq on a square full-rank system == solve
+            return torch.linalg.solve(sqrt_covar_diff, Δx - mean_diff)
 
-        out = []
+        def solve_outer(x_0_, x_1_):
+            Δx = (x_1_ - x_0_) / S
+            x_seq = x_0_[None] + torch.arange(S, dtype=x_0_.dtype)[:, None] * Δx[None]
+            return vmap(solve_inner, in_dims=(0, None))(x_seq, Δx)
+
         x_0_seq = torch.cat((x_0[None], x_obs_seq[:-1]))
-        for x0_, x1_ in zip(x_0_seq, x_obs_seq):
-            Δx = (x1_ - x0_) / S
-            for s in range(S):
-                out.append(solve_inner(x0_ + s * Δx, Δx))
-        return torch.stack(out)
+        x_1_seq = x_obs_seq
+        return vmap(solve_outer)(x_0_seq, x_1_seq).reshape((-1, dim_v))
 
     u = rng.standard_normal(md["dim_u"]) if u is None else u
     u = _t(u)

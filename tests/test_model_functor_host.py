@@ -1,0 +1,90 @@
+"""The generated device functors (step, Jacobians, second-order contraction), compiled for the host
+with g++, against torch autodiff of the oracle's forward_func.  CPU only."""
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.models import fhn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "manifold_mcmc_for_diffusions_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("shim") / "libhostshim.so")
+    subprocess.run(
+        ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", os.path.join(CSRC, "host_model_shim.cpp"),
+         "-I", CSRC, "-o", out],
+        check=True,
+    )
+    return C.CDLL(out)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def test_fhn_functor_matches_autodiff(shim):
+    rng = np.random.default_rng(11)
+    dl = 0.008
+    sd = np.sqrt(dl)
+    for _ in range(10):
+        z = np.array([0.3, 0.1, 1.5, 0.8]) * np.exp(0.3 * rng.standard_normal(4))
+        x = rng.standard_normal(2)
+        v = rng.standard_normal(2)
+        zt, xt, vt = torch.tensor(z), torch.tensor(x), torch.tensor(v)
+        f = lambda z_, x_, v_: fhn.forward_func(z_, x_, v_, dl)  # noqa: E731
+        xn = np.zeros(2)
+        shim.fhn_step(_p(z), C.c_double(sd), _p(x), _p(v), _p(xn))
+        assert np.max(np.abs(xn - f(zt, xt, vt).numpy())) < 1e-14
+        Jz, Jx, Jv = torch.func.jacrev(f, argnums=(0, 1, 2))(zt, xt, vt)
+        F, B, G = np.zeros(4), np.zeros(4), np.zeros(8)
+        shim.fhn_jac_x(_p(z), C.c_double(sd), _p(x), _p(v), _p(F))
+        shim.fhn_jac_v(_p(z), C.c_double(sd), _p(x), _p(v), _p(B))
+        shim.fhn_jac_z(_p(z), C.c_double(sd), _p(x), _p(v), _p(G))
+        assert np.max(np.abs(F.reshape(2, 2) - Jx.numpy())) < 1e-12 * max(1, np.abs(Jx.numpy()).max())
+        assert np.max(np.abs(B.reshape(2, 2) - Jv.numpy())) < 1e-13
+        assert np.max(np.abs(G.reshape(2, 4) - Jz.numpy())) < 1e-12 * max(1, np.abs(Jz.numpy()).max())
+        # second-order contraction g[a] = sum_i sum_b d2 f_i/dy_a dy_b Th[b, i], y = (x, v, z)
+        Th = rng.standard_normal((8, 2))
+
+        def fj(yv):
+            return fhn.forward_func(yv[4:8], yv[0:2], yv[2:4], dl)
+
+        H = torch.func.jacfwd(torch.func.jacrev(fj))(torch.tensor(np.concatenate([x, v, z]))).numpy()  # [i,a,b]
+        ref = np.einsum("iab,bi->a", H, Th)
+        g = np.zeros(8)
+        Thc = np.ascontiguousarray(Th)
+        shim.fhn_hess_contract(_p(z), C.c_double(sd), _p(x), _p(v), _p(Thc), _p(g))
+        assert np.max(np.abs(g - ref)) < 1e-10 * max(1.0, np.abs(ref).max())
+
+
+def test_gen_z(shim):
+    u = np.array([0.1, -0.2, 0.3, 0.4])
+    z, dz = np.zeros(4), np.zeros(16)
+    shim.fhn_gen_z(_p(u), _p(z), _p(dz))
+    assert np.allclose(z, fhn.generate_z(torch.tensor(u)).numpy(), rtol=1e-15)
+    J = torch.func.jacrev(fhn.generate_z)(torch.tensor(u)).numpy()
+    assert np.allclose(dz.reshape(4, 4), J, rtol=1e-15)
+
+
+def test_philox_normals_are_standard_normal_and_reproducible(shim):
+    shim.philox_normal_pair.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    a, b = C.c_double(), C.c_double()
+    vals = []
+    for i in range(20000):
+        shim.philox_normal_pair(1234, 7, i, C.byref(a), C.byref(b))
+        vals += [a.value, b.value]
+    vals = np.array(vals)
+    assert abs(vals.mean()) < 0.02 and abs(vals.std() - 1.0) < 0.02
+    assert abs(np.mean(vals ** 4) - 3.0) < 0.15
+    shim.philox_normal_pair(1234, 7, 5, C.byref(a), C.byref(b))
+    assert a.value == vals[10] and b.value == vals[11]
+    # Philox-4x32-10 known-answer test (Random123 kat_vectors: counter=0, key=0)
+    # checked through the raw block function in test_abi-level C shim is overkill; moments + determinism suffice here.
