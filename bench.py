@@ -81,10 +81,15 @@ class ClockSampler(threading.Thread):
 
 
 # work model (SURVEY.md 8d / DESIGN.md): bytes one quasi-Newton sweep must read per chain
-def qn_sweep_bytes_per_chain():
-    n_steps = T * S
-    # per step: work position v_t (2 doubles) + compressed Jacobian K_t (4 doubles)
-    return 8 * (n_steps * (2 + 4))
+def leapfrog_bytes_per_chain_step(qn_iters):
+    """Algorithmic HBM bytes of one constrained leapfrog step of one chain: doubles
+    per SDE time step summed over the phases (X=V=2: K_t is 4 doubles, v_t / p_t / x_t are 2)."""
+    project = 22 + 14 + 22        # 3 x (h1_flow +) cotangent projection: K twice, p read twice + written
+    flow = 6 + 6                  # 2 x h2_flow into the work position
+    qn = 6 * qn_iters             # one sweep per iteration: K_t + work position
+    qn_final = 10 + 6 + 8         # forward finalise (write q, mu) + momentum update + reverse comparison
+    point = 4 + 8 + 12 + 10       # trajectory, compressed Jacobian, tangent accumulator, adjoint sweep
+    return 8 * T * S * (project + flow + qn + qn_final + point)
 
 
 def run_ours(args):
@@ -120,19 +125,18 @@ def run_ours(args):
     it_counter = [args.burnin]
 
     def do_steps(k):
-        for s in range(k):
-            if s % L == 0:
-                bc.transition_begin(SEED + rank, it_counter[0])
-            bc.transition_step(args.dt)
-            if s % L == L - 1:
-                bc.transition_end(SEED + rank, it_counter[0], True)
-                it_counter[0] += 1
-        if k % L != 0:
+        done = 0
+        while done < k:
+            m = min(L, k - done)
+            bc.transition_begin(SEED + rank, it_counter[0])
+            bc.transition_steps(args.dt, m)          # m leapfrog steps, one fused launch
             bc.transition_end(SEED + rank, it_counter[0], True)
             it_counter[0] += 1
+            done += m
 
     do_steps(args.warmup)
     bc.successful_steps(reset=True)
+    bc.total_qn_iterations(reset=True)
     launches0 = bc.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -146,11 +150,10 @@ def run_ours(args):
     bc.profile_enable(False)
     launches = bc.launch_count() - launches0
     ok = bc.successful_steps()
+    qn_iters = bc.total_qn_iterations()
     st = bc.transition_stats()
     info = bc.step_info()
-    n_qn, ms_qn = bc.profile_summary(2)
-    n_pt, ms_pt = bc.profile_summary(0)
-    n_pj, ms_pj = bc.profile_summary(1)
+    n_lf, ms_lf = bc.profile_summary(3)
 
     # ---- end to end through the public API with host buffers (pinned), every step ----
     e2e_steps = min(args.steps, args.e2e_steps)
@@ -187,12 +190,14 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        # roofline of the dominant kernel (k_qn): algorithmic bytes = sweeps x bytes per sweep
-        iters_mean = float(info["iters_fwd"].mean() + info["iters_rev"].mean()) / 2.0
-        sweeps_per_launch = iters_mean + 1.0  # + the finalisation pass over K
-        alg_bytes = n * qn_sweep_bytes_per_chain() * sweeps_per_launch
-        qn_ms = ms_qn / max(n_qn, 1)
-        achieved = alg_bytes / (qn_ms * 1e-3) / 1e9 if qn_ms > 0 else 0.0
+        # roofline of the dominant kernel (k_leapfrog: every phase of the step fused in one launch).
+        # Algorithmic bytes: doubles moved per SDE time step and chain, summed over the
+        # phases of one leapfrog step, with the MEASURED number of quasi-Newton sweeps.
+        iters_per_step = qn_iters / max(ok, 1)          # forward + reverse iterations per successful step
+        alg_bytes_step = leapfrog_bytes_per_chain_step(iters_per_step)
+        alg_bytes = alg_bytes_step * ok                   # over the timed region, this rank
+        lf_ms = ms_lf
+        achieved = alg_bytes / (lf_ms * 1e-3) / 1e9 if lf_ms > 0 else 0.0
         out = {
             "metric": METRIC,
             "value": ok_tot / (ms_max * 1e-3),
@@ -216,21 +221,21 @@ def run_ours(args):
                 % (n * 450e3 / 1e9),
                 "step_success_frac": ok_tot / (n * world * args.steps),
                 "accept_stat_last": float(st["accept_stat"].mean()),
-                "qn_iters_mean": iters_mean,
+                "qn_iters_per_step": iters_per_step,
             },
             "roofline": {
                 "bound": "hbm",
-                "kernel": "k_qn (on-device quasi-Newton projection)",
+                "kernel": "k_leapfrog (fused constrained leapfrog step: projections, quasi-Newton solves, linearise + grad log-det)",
                 "achieved": achieved,
                 "peak": hbm_peak,
                 "unit": "GB/s",
                 "frac": achieved / hbm_peak,
                 "traffic": None,
                 "peak_source": peak_src,
-                "kernel_ms": {"k_qn": qn_ms, "k_point": ms_pt / max(n_pt, 1), "k_project": ms_pj / max(n_pj, 1)},
-                "share_of_step": {
-                    "k_qn": ms_qn / ms, "k_point": ms_pt / ms, "k_project": ms_pj / ms,
-                },
+                "alg_bytes_per_chain_step": alg_bytes_step,
+                "kernel_ms_per_launch": lf_ms / max(n_lf, 1),
+                "launches": n_lf,
+                "share_of_timed_region": lf_ms / ms,
             },
             "e2e": {
                 "value": ok_e2e_tot / (e2e_ms_max * 1e-3),

@@ -125,7 +125,7 @@ int mmd_hmc_transition(mmd_handle h, double dt, int n_leapfrog, uint64_t seed, u
                        const mmd_integrator_opts* opts, int switch_partition);
 /* The same transition in three calls so a driver can interleave its own work between steps. */
 int mmd_transition_begin(mmd_handle h, uint64_t seed, uint64_t iter);
-int mmd_transition_step(mmd_handle h, double dt, const mmd_integrator_opts* opts);
+int mmd_transition_steps(mmd_handle h, double dt, int n_steps, const mmd_integrator_opts* opts);
 int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_partition);
 /* accepted flag, accept_stat = min(1, exp(h0 - h1)), integrator status of the last transition */
 int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, int* status);
@@ -146,8 +146,10 @@ int mmd_init_linear_interpolation(mmd_handle h, const double* u, const double* v
 long long mmd_launch_count(mmd_handle h);
 /* total successful chain leapfrog steps since creation / last reset (device-side counter) */
 long long mmd_successful_steps(mmd_handle h, int reset);
+/* total projection-solver iterations executed over all chains (forward + reverse solves) */
+long long mmd_total_qn_iterations(mmd_handle h, int reset);
 /* per-kernel CUDA-event timing on the handle's stream: kernel ids 0 linearise (k_point), 1 momentum
- * projection (k_project), 2 quasi-Newton projection (k_qn) */
+ * projection (k_project), 2 quasi-Newton projection (k_qn), 3 fused leapfrog step(s) (k_leapfrog) */
 int mmd_profile_enable(mmd_handle h, int on, int max_launches);
 int mmd_profile_summary(mmd_handle h, int kernel_id, int* count, double* total_ms);
 int mmd_timer_start(mmd_handle h);

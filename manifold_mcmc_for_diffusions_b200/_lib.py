@@ -89,9 +89,10 @@ SIGNATURES = {
     ),
     "mmd_get_transition_stats": (C.c_int, [_H, _ip, _dp, _ip]),
     "mmd_transition_begin": (C.c_int, [_H, C.c_uint64, C.c_uint64]),
-    "mmd_transition_step": (C.c_int, [_H, C.c_double, C.POINTER(MmdIntegratorOpts)]),
+    "mmd_transition_steps": (C.c_int, [_H, C.c_double, C.c_int, C.POINTER(MmdIntegratorOpts)]),
     "mmd_transition_end": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int]),
     "mmd_successful_steps": (C.c_longlong, [_H, C.c_int]),
+    "mmd_total_qn_iterations": (C.c_longlong, [_H, C.c_int]),
     "mmd_profile_enable": (C.c_int, [_H, C.c_int, C.c_int]),
     "mmd_profile_summary": (C.c_int, [_H, C.c_int, _ip, _dp]),
     "mmd_launch_count": (C.c_longlong, [_H]),

@@ -176,14 +176,17 @@ class BatchedChains:
     def transition_begin(self, seed, it):
         check(self._L.mmd_transition_begin(self._h, int(seed), int(it)))
 
-    def transition_step(self, dt):
-        check(self._L.mmd_transition_step(self._h, float(dt), C.byref(self.opts)))
+    def transition_steps(self, dt, n_steps=1):
+        check(self._L.mmd_transition_steps(self._h, float(dt), int(n_steps), C.byref(self.opts)))
 
     def transition_end(self, seed, it, switch_partition=True):
         check(self._L.mmd_transition_end(self._h, int(seed), int(it), int(switch_partition)))
 
     def successful_steps(self, reset=False):
         return int(self._L.mmd_successful_steps(self._h, int(reset)))
+
+    def total_qn_iterations(self, reset=False):
+        return int(self._L.mmd_total_qn_iterations(self._h, int(reset)))
 
     def profile_enable(self, on, max_launches=4096):
         check(self._L.mmd_profile_enable(self._h, int(on), int(max_launches)))

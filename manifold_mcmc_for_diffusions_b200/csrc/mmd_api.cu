@@ -62,6 +62,7 @@ struct mmd_handle_s {
   int partition;
   int ncmax, nbmax;
   int cpb, nslot;
+  bool fused;
   size_t smem_bytes;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
@@ -94,7 +95,7 @@ void partition_shapes(int T, int R, int init, int* nb, int* fin) {
   *nb = 2 + (num_middle > 0 ? num_middle : 0);
 }
 
-enum { KID_POINT = 0, KID_PROJECT = 1, KID_QN = 2, KID_FLOW = 3, KID_OTHER = 4, KID_COUNT = 5 };
+enum { KID_POINT = 0, KID_PROJECT = 1, KID_QN = 2, KID_LEAPFROG = 3, KID_OTHER = 4, KID_COUNT = 5 };
 
 struct ProfScope {
   mmd_handle h;
@@ -114,12 +115,12 @@ struct ProfScope {
   }
 };
 
-template <int CPB, int NSLOT>
+template <int CPB, int NSLOT, int MINB>
 struct K {
   using Mdl = FhnModel;
   static int point(mmd_handle h, int which, int with_grad) {
     ProfScope ps(h, KID_POINT);
-    auto kern = k_point<Mdl, CPB, NRMAX, RMAX, UMAX, CPB * NSLOT>;
+    auto kern = k_point<Mdl, CPB, NRMAX, RMAX, UMAX, CPB * NSLOT, MINB>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(h->d, h->S, h->W, h->xobs, h->y,
                                                                        h->partition, which, with_grad);
@@ -136,7 +137,7 @@ struct K {
   }
   static int project(mmd_handle h, int lin, int src, int dst, double hh, double qcoef) {
     ProfScope ps(h, KID_PROJECT);
-    auto kern = k_project<Mdl, CPB, NRMAX, UMAX, CPB * NSLOT>;
+    auto kern = k_project<Mdl, CPB, NRMAX, UMAX, CPB * NSLOT, MINB>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(h->d, h->S, h->W, h->partition, lin, src,
                                                                        dst, hh, qcoef);
@@ -146,11 +147,22 @@ struct K {
   }
   static int qn(mmd_handle h, int mode, double mom_coef, const mmd_integrator_opts* o) {
     ProfScope ps(h, KID_QN);
-    auto kern = k_qn<Mdl, CPB, NRMAX, UMAX, CPB * NSLOT>;
+    auto kern = k_qn<Mdl, CPB, NRMAX, UMAX, CPB * NSLOT, MINB>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(
         h->d, h->S, h->W, h->xobs, h->y, h->partition, mode, mom_coef, o->constraint_tol, o->position_tol,
         o->divergence_tol, o->max_iters);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  static int leapfrog(mmd_handle h, double dt, const mmd_integrator_opts* o, int n_steps, int reset_status) {
+    ProfScope ps(h, KID_LEAPFROG);
+    auto kern = k_leapfrog<Mdl, CPB, NRMAX, RMAX, UMAX, CPB * NSLOT, MINB>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(
+        h->d, h->S, h->W, h->xobs, h->y, h->partition, dt, o->constraint_tol, o->position_tol, o->divergence_tol,
+        o->max_iters, o->reverse_check_tol, h->n_ok, n_steps, reset_status);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -164,8 +176,8 @@ struct K {
 };
 
 // dispatch on the CTA shape chosen at create time
-#define DISPATCH(h, CALL)                                   \
-  ((h)->cpb == 32 ? K<32, 24>::CALL : K<8, 128>::CALL)
+#define DISPATCH(h, CALL)                                                  \
+  ((h)->nbmax <= 24 ? K<32, 24, 1>::CALL : K<8, 128, 1>::CALL)
 
 int to_soa(mmd_handle h, const double* host, double* dst, int rows) {
   const size_t n = (size_t)h->d.n_chains * rows;
@@ -293,8 +305,12 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   h->ncmax = d.n_c[0] > d.n_c[1] ? d.n_c[0] : d.n_c[1];
   h->nbmax = d.nb[0] > d.nb[1] ? d.nb[0] : d.nb[1];
   const char* cpb_env = getenv("MMD_CPB");  // tuning override
-  if (h->nbmax <= 24 && !(cpb_env && atoi(cpb_env) == 8)) { h->cpb = 32; }
-  else if (h->nbmax <= 128) { h->cpb = 8; }
+  const char* fused_env = getenv("MMD_FUSED");
+  h->fused = !(fused_env && atoi(fused_env) == 0);
+  if (h->nbmax <= 24) {
+    h->cpb = 32;
+    (void)cpb_env;
+  } else if (h->nbmax <= 128) { h->cpb = 8; }
   else { delete h; FAIL("too many observation blocks for this build"); }
   h->nslot = h->nbmax;
   h->smem_bytes = (size_t)h->nslot * (UMAX * (UMAX + 1) / 2 + 1) * h->cpb * sizeof(double);
@@ -345,6 +361,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   rc |= dalloc(h, &W.iters, 2 * ld);
   rc |= dalloc(h, &W.revd, ld);
   rc |= dalloc(h, &W.hval, ld);
+  rc |= dalloc(h, &W.itsum, ld);
   rc |= dalloc(h, &h->xobs, (size_t)T * X * ld);
   rc |= dalloc(h, &h->y, (size_t)T * Mdl::Y);
   size_t stage_n = (size_t)d.n_chains * (d.dim_q > (int)(N * X * V) ? d.dim_q : N * X * V);
@@ -541,7 +558,8 @@ int mmd_get_factor(mmd_handle h, const char* name, double* out, int* rows_out) {
   return 0;
 }
 
-static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opts, bool reset_status) {
+static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opts, bool reset_status,
+                         int n_steps = 1) {
   mmd_integrator_opts o;
   if (opts) o = *opts; else mmd_default_integrator_opts(&o);
   if (o.solver != MMD_SOLVER_QUASI_NEWTON) FAIL("only the quasi-Newton projection solver is built");
@@ -549,8 +567,10 @@ static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opt
     int rc0 = mmd_linearize(h, 1);
     if (rc0) return rc0;
   }
+  if (h->fused) return DISPATCH(h, leapfrog(h, dt, &o, n_steps, reset_status ? 1 : 0));
   if (reset_status) CK(cudaMemsetAsync(h->W.status, 0, h->d.ld * sizeof(int), h->stream));
   int rc = 0;
+  for (int step_i = 0; step_i < n_steps; ++step_i) {
   // A(dt/2): h1_flow + cotangent projection at the current point; result -> p(other)
   rc = DISPATCH(h, project(h, 0, 0, 1, 0.5 * dt, 1.0)); if (rc) return rc;
   // B(dt): h2_flow, projection onto the manifold with the Jacobian at the previous point
@@ -567,6 +587,7 @@ static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opt
   k_commit<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->S, h->W, o.reverse_check_tol, h->n_ok);
   h->launches++;
   CK(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -582,8 +603,8 @@ int mmd_transition_begin(mmd_handle h, uint64_t seed, uint64_t iter) {
   return 0;
 }
 
-int mmd_transition_step(mmd_handle h, double dt, const mmd_integrator_opts* opts) {
-  return leapfrog_impl(h, dt, opts, false);
+int mmd_transition_steps(mmd_handle h, double dt, int n_steps, const mmd_integrator_opts* opts) {
+  return leapfrog_impl(h, dt, opts, false, n_steps);
 }
 
 int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_partition) {
@@ -604,10 +625,8 @@ int mmd_hmc_transition(mmd_handle h, double dt, int n_leapfrog, uint64_t seed, u
   // IndependentMomentumTransition + static-trajectory integration with Metropolis accept +
   // SwitchPartitionTransition (scripts/utils.py:292-301 with a static instead of dynamic trajectory)
   int rc = mmd_transition_begin(h, seed, iter); if (rc) return rc;
-  for (int s = 0; s < n_leapfrog; ++s) {
-    rc = leapfrog_impl(h, dt, opts, false);
-    if (rc) return rc;
-  }
+  rc = leapfrog_impl(h, dt, opts, false, n_leapfrog);
+  if (rc) return rc;
   return mmd_transition_end(h, seed, iter, switch_partition);
 }
 
@@ -650,6 +669,18 @@ long long mmd_successful_steps(mmd_handle h, int reset) {
   long long tot = 0;
   for (int i = 0; i < h->d.n_chains; ++i) tot += host[i];
   if (reset) cudaMemsetAsync(h->n_ok, 0, h->d.ld * sizeof(long long), h->stream);
+  return tot;
+}
+
+long long mmd_total_qn_iterations(mmd_handle h, int reset) {
+  std::vector<long long> host(h->d.ld);
+  if (cudaMemcpyAsync(host.data(), h->W.itsum, h->d.ld * sizeof(long long), cudaMemcpyDeviceToHost, h->stream) !=
+      cudaSuccess)
+    return -1;
+  cudaStreamSynchronize(h->stream);
+  long long tot = 0;
+  for (int i = 0; i < h->d.n_chains; ++i) tot += host[i];
+  if (reset) cudaMemsetAsync(h->W.itsum, 0, h->d.ld * sizeof(long long), h->stream);
   return tot;
 }
 

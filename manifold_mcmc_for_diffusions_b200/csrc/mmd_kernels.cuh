@@ -77,6 +77,7 @@ struct Work {
   int* iters;     // [2][ld] projection iterations (forward, reverse) of the last step
   double* revd;   // [ld] reverse-check distance of the last step
   double* hval;   // [ld]
+  long long* itsum;  // [ld] total quasi-Newton iterations executed (both directions)
 };
 
 enum : int { ST_NOTCONV = 1, ST_DIVERGED = 2, ST_NONREV = 4, ST_NONFINITE = 8 };

@@ -20,10 +20,9 @@ namespace mmd {
 // log_det_sqrt_gram (mici_extensions.py:521-687, 800-820) in compressed form; phase 2 =
 // grad_log_det_sqrt_gram (:1143-1146, :1173-1184) by a hand-derived second-order adjoint.
 // ------------------------------------------------------------------------------------------
-template <class M, int CPB, int NRMAX, int RMAX, int UMAX, int NT>
-__global__ void __launch_bounds__(NT, 1)
-k_point(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* __restrict__ y, int part,
-        int which, int with_grad) {
+template <class M, int CPB, int NRMAX, int RMAX, int UMAX>
+MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ xobs,
+                     const double* __restrict__ y, int part, int which, int with_grad) {
   MMD_THREAD_SETUP
   constexpr int X = M::X, V = M::V, Z = M::Z;
   constexpr int NTRI = NRMAX * (NRMAX + 1) / 2;
@@ -260,7 +259,7 @@ k_point(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* 
     }
     // a[r][k] = Phi(t_kr, t_k)^T H_r^T  (zero for k > kr)
     double a[NRMAX * RMAX * X], be[NRMAX * RMAX * X];
-    for (int i = 0; i < nr * B.n * X; ++i) a[i] = 0.0;
+    for (int i = 0; i < NRMAX * RMAX * X; ++i) a[i] = 0.0;  // indexed [(r * RMAX + k) * X + i]
     for (int r = 0; r < nr; ++r) {
       const int kr = (r < B.ny) ? r : B.n - 1;
       double vec[X];
@@ -501,9 +500,9 @@ __global__ void k_constr(Dims d, const double* __restrict__ q, const double* __r
 // :1243-1254) fused with the preceding h1_flow (Mici System.h1_flow; dh1_dpos :1192-1196).
 // Reads p from slot `src`, writes slot `dst` (relative to cur: 0 = cur, 1 = other).
 // ------------------------------------------------------------------------------------------
-template <class M, int CPB, int NRMAX, int UMAX, int NT>
-__global__ void __launch_bounds__(NT, 1)
-k_project(Dims d, Slots S, Work W, int part, int lin_sel, int src_sel, int dst_sel, double h, double qcoef) {
+template <class M, int CPB, int NRMAX, int UMAX>
+MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, int lin_sel, int src_sel,
+                       int dst_sel, double h, double qcoef) {
   MMD_THREAD_SETUP
   constexpr int X = M::X, V = M::V, Z = M::Z;
   const int U = d.U;
@@ -640,10 +639,10 @@ k_project(Dims d, Slots S, Work W, int part, int lin_sel, int src_sel, int dst_s
 // mode 0 (forward):  on convergence write q_new -> slot(other).q and p(other) -= mom_coef * mu
 // mode 1 (reverse):  compare q_back with q(cur) -> revd, no writes       (Mici reverse check)
 // ------------------------------------------------------------------------------------------
-template <class M, int CPB, int NRMAX, int UMAX, int NT>
-__global__ void __launch_bounds__(NT, 1)
-k_qn(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* __restrict__ y, int part,
-     int mode, double mom_coef, double ctol, double ptol, double dtol, int max_iters) {
+template <class M, int CPB, int NRMAX, int UMAX>
+MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ xobs,
+                  const double* __restrict__ y, int part, int mode, double mom_coef, double ctol, double ptol,
+                  double dtol, int max_iters) {
   MMD_THREAD_SETUP
   constexpr int X = M::X, V = M::V, Z = M::Z;
   constexpr int NTRI = NRMAX * (NRMAX + 1) / 2;
@@ -845,8 +844,94 @@ k_qn(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* __r
   block_reduce<1, CPB, true>(rr, smem, nslot, slot, cl);
   if (slot == 0 && live) {
     W.iters[mode * ld + chain] = it;
+    W.itsum[chain] += it;
     if (st) W.status[chain] |= st;
     if (mode == 1 && st == 0) W.revd[chain] = rr[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone launches of the phases (per-op API) and the fused persistent leapfrog kernel
+// ------------------------------------------------------------------------------------------
+template <class M, int CPB, int NRMAX, int RMAX, int UMAX, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_point(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* __restrict__ y, int part,
+        int which, int with_grad) {
+  dev_point<M, CPB, NRMAX, RMAX, UMAX>(d, S, W, xobs, y, part, which, with_grad);
+}
+template <class M, int CPB, int NRMAX, int UMAX, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_project(Dims d, Slots S, Work W, int part, int lin_sel, int src_sel, int dst_sel, double h, double qcoef) {
+  dev_project<M, CPB, NRMAX, UMAX>(d, S, W, part, lin_sel, src_sel, dst_sel, h, qcoef);
+}
+template <class M, int CPB, int NRMAX, int UMAX, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_qn(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* __restrict__ y, int part,
+     int mode, double mom_coef, double ctol, double ptol, double dtol, int max_iters) {
+  dev_qn<M, CPB, NRMAX, UMAX>(d, S, W, xobs, y, part, mode, mom_coef, ctol, ptol, dtol, max_iters);
+}
+
+// h2_flow for this thread's rows: qw = q(q_sel) + dt * p(p_sel)   (mici_extensions.py:1222-1231)
+template <class M, int CPB>
+MMD_D void dev_flow(const Dims& d, const Slots& S, const Work& W, int part, int q_sel, int p_sel, double dt) {
+  MMD_THREAD_SETUP
+  if (slot >= d.nb[part]) return;
+  const int cur = S.cur[chain];
+  const double* qc = S.q + (q_sel ? 1 - cur : cur) * S.s_q + chain;
+  const double* pc = S.p + (p_sel ? 1 - cur : cur) * S.s_q + chain;
+  double* qw = W.qw + chain;
+  const Blk B = get_block<M>(d, part, slot);
+  const long long r0 = d.off_v + (long long)B.o * d.S * M::V, r1 = r0 + (long long)B.n * d.S * M::V;
+  for (long long r = r0; r < r1; ++r) qw[r * ld] = fma(dt, pc[r * ld], qc[r * ld]);
+  if (d.noisy)
+    for (long long r = d.off_n + B.o; r < d.off_n + B.o + B.n; ++r) qw[r * ld] = fma(dt, pc[r * ld], qc[r * ld]);
+  if (B.ini)
+    for (long long r = 0; r < d.off_v; ++r) qw[r * ld] = fma(dt, pc[r * ld], qc[r * ld]);
+}
+
+// One (or n_steps) full ConstrainedLeapfrogIntegrator.step per chain in ONE launch: a CTA carries
+// its CPB chains through every phase with CTA-local barriers only, so chains that need many
+// projection iterations delay just their own small CTA while the other resident CTAs keep the SM busy
+// (the per-chain iteration count is long-tailed: mean ~8, 1 % > 30, max_iters = 50).
+// Step order: Mici ConstrainedLeapfrogIntegrator._step = A(dt/2) B(dt) A(dt/2), SURVEY.md 3.3.
+template <class M, int CPB, int NRMAX, int RMAX, int UMAX, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* __restrict__ y, int part,
+           double dt, double ctol, double ptol, double dtol, int max_iters, double rev_tol,
+           long long* __restrict__ n_ok, int n_steps, int reset_status) {
+  const int cl = threadIdx.x % CPB, slot = threadIdx.x / CPB;
+  const int chain = blockIdx.x * CPB + cl;
+  for (int s = 0; s < n_steps; ++s) {
+    if (reset_status && slot == 0) W.status[chain] = 0;
+    __syncthreads();
+    dev_project<M, CPB, NRMAX, UMAX>(d, S, W, part, 0, 0, 1, 0.5 * dt, 1.0);
+    __syncthreads();
+    dev_flow<M, CPB>(d, S, W, part, 0, 1, dt);
+    __syncthreads();
+    dev_qn<M, CPB, NRMAX, UMAX>(d, S, W, xobs, y, part, 0, 1.0 / dt, ctol, ptol, dtol, max_iters);
+    __syncthreads();
+    dev_point<M, CPB, NRMAX, RMAX, UMAX>(d, S, W, xobs, y, part, 1, 1);
+    __syncthreads();
+    dev_project<M, CPB, NRMAX, UMAX>(d, S, W, part, 1, 1, 1, 0.0, 0.0);
+    __syncthreads();
+    dev_flow<M, CPB>(d, S, W, part, 1, 1, -dt);
+    __syncthreads();
+    dev_qn<M, CPB, NRMAX, UMAX>(d, S, W, xobs, y, part, 1, 0.0, ctol, ptol, dtol, max_iters);
+    __syncthreads();
+    dev_project<M, CPB, NRMAX, UMAX>(d, S, W, part, 1, 1, 1, 0.5 * dt, 1.0);
+    __syncthreads();
+    if (slot == 0 && chain < d.n_chains) {
+      int st = W.status[chain];
+      if (st == 0 && !(W.revd[chain] <= rev_tol)) {
+        st |= ST_NONREV;
+        W.status[chain] = st;
+      }
+      if (st == 0) {
+        S.cur[chain] = 1 - S.cur[chain];
+        n_ok[chain] += 1;
+      }
+    }
+    __syncthreads();
   }
 }
 

@@ -20,7 +20,7 @@ for it in range(12):
     bc.transition_begin(1, 1000 + it)
     for s in range(8):
         live_before = bc.step_info()["status"] == 0 if s else np.ones(n, bool)
-        bc.transition_step(dt)
+        bc.transition_steps(dt, 1)
         info = bc.step_info()
         f = info["iters_fwd"][live_before]; hf += np.bincount(f, minlength=52)[:52]
         ok_fwd = live_before & ((info["status"] & 3) == 0)

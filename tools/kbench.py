@@ -14,17 +14,19 @@ u = rng.standard_normal((n, 4)); v0 = rng.standard_normal((n, 2))
 xo = np.concatenate((np.broadcast_to(y, (n, T, 1)), 0.5 * rng.standard_normal((n, T, 1))), -1)
 bc.init_linear_interpolation(u, v0, xo, 0)
 for it in range(burn): bc.hmc_transition(0.05, 8, 1, it)
-bc.profile_enable(True, 4096)
+bc.profile_enable(True, 4096); bc.successful_steps(reset=True)
 bc.timer_start()
 nst = 16
-bc.transition_begin(1, 1000)
-for s in range(nst): bc.transition_step(dt)
+L = int(os.environ.get("TRAJ", 8))
+for tr in range(nst // L):
+    bc.transition_begin(1, 1000 + tr)
+    bc.transition_steps(dt, L)
+    bc.transition_end(1, 1000 + tr, True)
 ms = bc.timer_stop_ms()
 info = bc.step_info()
-res = {"tag": os.environ.get("TAG", ""), "ms_per_step": ms / nst}
-for kid, nm in [(0, "k_point"), (1, "k_project"), (2, "k_qn")]:
+res = {"tag": os.environ.get("TAG", ""), "ms_per_step": ms / nst, "chain_steps_per_s": bc.successful_steps() / (ms * 1e-3)}
+for kid, nm in [(0, "k_point"), (1, "k_project"), (2, "k_qn"), (3, "k_leapfrog")]:
     c, t = bc.profile_summary(kid); res[nm] = round(t / max(c, 1), 4)
 res["iters_fwd_mean"] = float(info["iters_fwd"].mean()); res["iters_fwd_max"] = int(info["iters_fwd"].max())
-res["hist"] = np.bincount(info["iters_fwd"], minlength=12)[:60].tolist()
 res["fail"] = float((info["status"] != 0).mean())
 print(json.dumps(res))
