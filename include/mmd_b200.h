@@ -68,12 +68,18 @@ int mmd_n_chains(mmd_handle h);
 int mmd_set_state(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition);
 int mmd_get_state(mmd_handle h, double* q, double* p, double* x_obs_seq);
 int mmd_set_momentum(mmd_handle h, const double* p);
-/* Same with device pointers in the library's structure-of-arrays layout [rows][ld] (zero-copy
- * path for DLPack producers); ld = mmd_leading_dim(h). */
-int mmd_leading_dim(mmd_handle h);
-int mmd_set_state_soa_dev(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_obs_seq_dev,
-                          int partition);
+/* Same with DEVICE pointers in the reference layout ([n_chains][dim_q], [n_chains][T][dim_x]): the
+ * zero-copy path for DLPack producers (JAX / CuPy / torch arrays already on the GPU).  The library
+ * re-tiles on device into its internal tile layout; asynchronous. */
+int mmd_set_state_dev(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_obs_seq_dev,
+                      int partition);
+int mmd_get_state_dev(mmd_handle h, double* q_dev, double* p_dev, double* x_obs_seq_dev);
 int mmd_get_partition(mmd_handle h);
+/* chains per CTA tile chosen at create time (tuning knob MMD_CPB; informational) */
+int mmd_chains_per_tile(mmd_handle h);
+/* global index of this handle's first chain: offsets the Philox counters so that ranks that shard
+ * one population of chains draw disjoint, rank-count-independent streams */
+int mmd_set_chain_offset(mmd_handle h, int chain0);
 
 /* ---- system ops on the resident state ----------------------------------------------------------- */
 /* jacob_constr_blocks + chol_gram_blocks + log_det_sqrt_gram (+ grad_log_det_sqrt_gram when
@@ -98,8 +104,11 @@ int mmd_switch_partition(mmd_handle h);
 int mmd_sample_momentum(mmd_handle h, uint64_t seed, uint64_t offset);
 
 /* Compressed factors behind jacob_constr_blocks / chol_gram_blocks, for tests and for rebuilding
- * the reference's dense blocks on the host.  name in {"K","Psib","A","L","DinvA","LC"}; out is
- * [rows][n_chains] (structure of arrays, chain fastest); returns rows via *rows_out when out==NULL. */
+ * the reference's dense blocks on the host.  name in {"K","Psib","xend","A","L","DinvA"}: out is
+ * [n_chains][n_blocks][rows] with block-local rows (K: [obs in block][S][dim_x][dim_v], Psib:
+ * [obs][dim_x][dim_x], A / DinvA: [row in block][dim_u], L: packed lower Cholesky factor of D_b with
+ * the diagonal stored INVERTED); "LC": [n_chains][rows] packed factor of the capacitance matrix.
+ * Returns rows via *rows_out when out==NULL. */
 int mmd_get_factor(mmd_handle h, const char* name, double* out, int* rows_out);
 
 /* ---- integrator ----------------------------------------------------------------------------- */

@@ -61,8 +61,10 @@ SIGNATURES = {
     "mmd_set_state": (C.c_int, [_H, _dp, _dp, _dp, C.c_int]),
     "mmd_get_state": (C.c_int, [_H, _dp, _dp, _dp]),
     "mmd_set_momentum": (C.c_int, [_H, _dp]),
-    "mmd_leading_dim": (C.c_int, [_H]),
-    "mmd_set_state_soa_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "mmd_set_state_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "mmd_get_state_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmd_chains_per_tile": (C.c_int, [_H]),
+    "mmd_set_chain_offset": (C.c_int, [_H, C.c_int]),
     "mmd_get_partition": (C.c_int, [_H]),
     "mmd_linearize": (C.c_int, [_H, C.c_int]),
     "mmd_constr": (C.c_int, [_H, _dp]),

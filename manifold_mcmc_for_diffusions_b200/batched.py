@@ -157,7 +157,9 @@ class BatchedChains:
     def get_factor(self, name):
         rows = C.c_int()
         check(self._L.mmd_get_factor(self._h, name.encode(), None, C.byref(rows)))
-        out = np.empty((rows.value, self.n_chains))
+        nb = self._L.mmd_num_blocks(self._h, self.partition)
+        shape = (self.n_chains, rows.value) if name == "LC" else (self.n_chains, nb, rows.value)
+        out = np.empty(shape)
         check(self._L.mmd_get_factor(self._h, name.encode(), _dp(out), C.byref(rows)))
         return out
 

@@ -3,13 +3,21 @@
 #include "mmd_model_fhn.cuh"
 #include "mmd_philox.cuh"
 
+namespace {
+FhnModel::Coef coef(const double* z, double sd) {
+  FhnModel::Coef c;
+  FhnModel::make_coef(z, sd, c);
+  return c;
+}
+}  // namespace
+
 extern "C" {
-void fhn_step(const double* z, double sd, const double* x, const double* v, double* xn) { FhnModel::step(z, sd, x, v, xn); }
-void fhn_jac_x(const double* z, double sd, const double* x, const double* v, double* F) { FhnModel::jac_x(z, sd, x, v, F); }
-void fhn_jac_v(const double* z, double sd, const double* x, const double* v, double* B) { FhnModel::jac_v(z, sd, x, v, B); }
-void fhn_jac_z(const double* z, double sd, const double* x, const double* v, double* G) { FhnModel::jac_z(z, sd, x, v, G); }
+void fhn_step(const double* z, double sd, const double* x, const double* v, double* xn) { FhnModel::step(coef(z, sd), x, v, xn); }
+void fhn_jac_x(const double* z, double sd, const double* x, const double* v, double* F) { FhnModel::jac_x(coef(z, sd), x, v, F); }
+void fhn_jac_v(const double* z, double sd, const double* x, const double* v, double* B) { FhnModel::jac_v(coef(z, sd), x, v, B); }
+void fhn_jac_z(const double* z, double sd, const double* x, const double* v, double* G) { FhnModel::jac_z(coef(z, sd), x, v, G); }
 void fhn_hess_contract(const double* z, double sd, const double* x, const double* v, const double* Th, double* g) {
-  FhnModel::hess_contract(z, sd, x, v, Th, g);
+  FhnModel::hess_contract(coef(z, sd), x, v, Th, g);
 }
 void fhn_gen_z(const double* u, double* z, double* dzdu) { FhnModel::gen_z(u, z, dzdu); }
 void philox_normal_pair(unsigned long long seed, unsigned long long offset, unsigned long long idx, double* a, double* b) {

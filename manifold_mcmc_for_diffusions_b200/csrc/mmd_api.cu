@@ -4,6 +4,7 @@
 #include "../../include/mmd_b200.h"
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
@@ -38,9 +39,14 @@ thread_local std::string g_err;
     return -1;       \
   } while (0)
 
-constexpr int NRMAX = 8;  // max constraint rows per block  (R - 1 + noisy + dim_x)
-constexpr int RMAX = 8;   // max observations per block
-constexpr int UMAX = 5;   // max dim_u
+constexpr int UMAX = 5;      // max dim_u
+#ifndef MMD_NTMAX
+#define MMD_NTMAX 192         // max threads per CTA (= chains per tile x observation blocks)
+#endif
+constexpr int NTMAX = MMD_NTMAX;
+#ifndef MMD_MINB
+#define MMD_MINB 3           // __launch_bounds__ min resident CTAs per SM for the phase kernels
+#endif
 
 }  // namespace
 
@@ -50,20 +56,22 @@ struct mmd_handle_s {
   Work W;
   int model;
   int X, V, Z, V0;
-  double* xobs;   // [T*X][ld]
+  int nrmax;      // constraint rows per block the kernels are instantiated for
   double* y;      // [T]
-  double* stage;  // [n_chains * max(dim_q, ...)] AoS staging
+  double* stage;  // [n_chains * dim_q] canonical staging (device)
   double* stage2;
-  double* hbuf;   // [ld]
-  double* h0buf;  // [ld]
-  double* qsave;  // [dim_q][ld]
-  double* accp;   // [ld]
-  int* accepted;  // [ld]
+  double* tpbuf;  // thread-private scratch [n_tiles][nrmax][nta] (constraint values)
+  double* hbuf;   // [chains]
+  double* h0buf;  // [chains]
+  double* qsave;  // q-like
+  double* qtmp;   // q-like (re-tiling at a partition switch)
+  double* accp;   // [chains]
+  int* accepted;  // [chains]
+  int* cur0;
   int partition;
   int ncmax, nbmax;
-  int cpb, nslot;
+  int chain0;     // global index of this handle's first chain (Philox stream offset)
   bool fused;
-  size_t smem_bytes;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
   long long launches;
@@ -74,13 +82,14 @@ struct mmd_handle_s {
   std::vector<cudaEvent_t> prof_ev;   // pairs
   std::vector<int> prof_kid;
   size_t prof_used;
-  long long* n_ok;   // [ld] successful leapfrog steps per chain (device counter)
+  long long* n_ok;   // [chains] successful leapfrog steps per chain (device counter)
 };
 
 namespace {
 
 template <class T>
 int dalloc(mmd_handle h, T** p, size_t n) {
+  if (n == 0) n = 1;
   CK(cudaMalloc((void**)p, n * sizeof(T)));
   CK(cudaMemsetAsync(*p, 0, n * sizeof(T), h->stream));
   h->allocs.push_back((void*)*p);
@@ -115,122 +124,180 @@ struct ProfScope {
   }
 };
 
-template <int CPB, int NSLOT, int MINB>
-struct K {
-  using Mdl = FhnModel;
+StepCoef step_coef(const Dims& d, double dt) {
+  StepCoef sc;
+  sc.half_dt = 0.5 * dt;
+  if (d.gaussian) {
+    // h2_flow = exact rotation by dt; dh2_flow_dmom = (sin dt, cos dt) (mici_extensions.py:1222-1238)
+    sc.qcoef = 0.0;
+    sc.fwd = FlowCoef{2, cos(dt), sin(dt), sin(dt)};
+    sc.back = FlowCoef{1, cos(dt), -sin(dt), -sin(dt)};
+    sc.mom_coef = cos(dt) / sin(dt);
+  } else {
+    sc.qcoef = 1.0;
+    sc.fwd = FlowCoef{2, 1.0, dt, 0.0};
+    sc.back = FlowCoef{1, 1.0, -dt, 0.0};
+    sc.mom_coef = 1.0 / dt;
+  }
+  return sc;
+}
+
+// kernel launchers for one model / block-size instantiation
+template <class Mdl, int NRMAX, int RMAX>
+struct Ops {
+  static size_t smem(int nt) { return (size_t)SmemPlan<Mdl, NRMAX, UMAX>::PER_THREAD * nt * sizeof(double); }
+  static int nt(mmd_handle h) { return h->d.nb[h->partition] * h->d.cpb; }
+  template <class Kern>
+  static int prep(Kern kern, size_t bytes) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+  }
   static int point(mmd_handle h, int which, int with_grad) {
     ProfScope ps(h, KID_POINT);
-    auto kern = k_point<Mdl, CPB, NRMAX, RMAX, UMAX, CPB * NSLOT, MINB>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(h->d, h->S, h->W, h->xobs, h->y,
-                                                                       h->partition, which, with_grad);
+    auto kern = k_point<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
+    const int n = nt(h);
+    if (prep(kern, smem(n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, which, with_grad);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
   }
-  static int constr(mmd_handle h, const double* q_soa, double* c_soa) {
-    k_constr<Mdl, CPB, NRMAX, UMAX><<<h->d.ld / CPB, CPB * h->nslot, 0, h->stream>>>(
-        h->d, q_soa, h->xobs, h->y, h->partition, c_soa);
+  static int constr(mmd_handle h) {
+    auto kern = k_constr<Mdl, NRMAX, UMAX, NTMAX, MMD_MINB>;
+    const int n = nt(h);
+    if (prep(kern, smem(n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, h->tpbuf);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
   }
-  static int project(mmd_handle h, int lin, int src, int dst, double hh, double qcoef) {
+  static int project(mmd_handle h, int lin, int src, int dst, double hh, double qcoef, FlowCoef fl) {
     ProfScope ps(h, KID_PROJECT);
-    auto kern = k_project<Mdl, CPB, NRMAX, UMAX, CPB * NSLOT, MINB>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(h->d, h->S, h->W, h->partition, lin, src,
-                                                                       dst, hh, qcoef);
+    auto kern = k_project<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
+    const int n = nt(h);
+    if (prep(kern, smem(n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->partition, lin, src, dst, hh, qcoef, fl);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
   }
   static int qn(mmd_handle h, int mode, double mom_coef, const mmd_integrator_opts* o) {
     ProfScope ps(h, KID_QN);
-    auto kern = k_qn<Mdl, CPB, NRMAX, UMAX, CPB * NSLOT, MINB>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(
-        h->d, h->S, h->W, h->xobs, h->y, h->partition, mode, mom_coef, o->constraint_tol, o->position_tol,
-        o->divergence_tol, o->max_iters);
+    auto kern = k_qn<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
+    const int n = nt(h);
+    if (prep(kern, smem(n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, mode, mom_coef,
+                                                   o->constraint_tol, o->position_tol, o->divergence_tol,
+                                                   o->max_iters);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
   }
   static int leapfrog(mmd_handle h, double dt, const mmd_integrator_opts* o, int n_steps, int reset_status) {
     ProfScope ps(h, KID_LEAPFROG);
-    auto kern = k_leapfrog<Mdl, CPB, NRMAX, RMAX, UMAX, CPB * NSLOT, MINB>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    kern<<<h->d.ld / CPB, CPB * h->nslot, h->smem_bytes, h->stream>>>(
-        h->d, h->S, h->W, h->xobs, h->y, h->partition, dt, o->constraint_tol, o->position_tol, o->divergence_tol,
-        o->max_iters, o->reverse_check_tol, h->n_ok, n_steps, reset_status);
+    auto kern = k_leapfrog<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
+    const int n = nt(h);
+    if (prep(kern, smem(n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, step_coef(h->d, dt),
+                                                   o->constraint_tol, o->position_tol, o->divergence_tol,
+                                                   o->max_iters, o->reverse_check_tol, h->n_ok, n_steps,
+                                                   reset_status);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
   }
   static int hamiltonian(mmd_handle h, int sel, double* out) {
-    k_hamiltonian<CPB><<<h->d.ld / CPB, CPB * h->nslot, (size_t)h->nslot * CPB * sizeof(double), h->stream>>>(h->d, h->S, h->W, sel, out);
+    const int n = nt(h);
+    k_hamiltonian<Mdl><<<h->d.n_tiles, n, (size_t)n * sizeof(double), h->stream>>>(h->d, h->S, h->W, h->partition,
+                                                                                   sel, out);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
   }
+  // canonical [n_chains][dim_q] (device) -> tile layout of a q-like vector
+  static int pack(mmd_handle h, const double* canon_dev, double* base, long long stride, int sel) {
+    k_pack<Mdl><<<1184, 256, 0, h->stream>>>(h->d, h->partition, canon_dev, base, stride, h->S.cur, sel);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  static int unpack(mmd_handle h, double* canon_dev, const double* base, long long stride, int sel) {
+    k_unpack<Mdl><<<1184, 256, 0, h->stream>>>(h->d, h->partition, canon_dev, base, stride, h->S.cur, sel);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  static int retile(mmd_handle h, int pa, int pb) {
+    // q(cur) in the tiling of partition pa -> qtmp in the tiling of pb -> slot 0; cur := 0
+    k_retile<Mdl><<<1184, 256, 0, h->stream>>>(h->d, pa, pb, h->S.q, h->qtmp, h->S.s_q, h->S.cur);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->S.q, h->qtmp, (size_t)h->d.qsize * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemsetAsync(h->S.cur, 0, (size_t)h->d.n_tiles * h->d.cpb * sizeof(int), h->stream));
+    return 0;
+  }
+  static int gen_xobs(mmd_handle h) {
+    k_gen_xobs<Mdl, UMAX><<<(h->d.n_chains + 63) / 64, 64, 0, h->stream>>>(h->d, h->S, h->W, h->partition);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  static int init_interp(mmd_handle h) {
+    k_init_interp<Mdl, UMAX><<<h->d.n_tiles, nt(h), 0, h->stream>>>(h->d, h->S, h->W, h->partition);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  static int philox(mmd_handle h, uint64_t seed, uint64_t offset) {
+    k_philox_momentum<Mdl><<<1184, 256, 0, h->stream>>>(h->d, h->partition, h->S.p, h->S.s_q, h->S.cur, seed, offset,
+                                                        h->chain0);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  static void constr_rows(mmd_handle h, const std::vector<double>& buf, double* c_out) {
+    // thread-private [tile][NRMAX][nta] -> [chain][n_c]: rows of block b start at its row0
+    const Dims& d = h->d;
+    const int part = h->partition, nc = d.n_c[part];
+    for (int c = 0; c < d.n_chains; ++c) {
+      const int tile = c / d.cpb, cl = c % d.cpb;
+      for (int b = 0; b < d.nb[part]; ++b) {
+        const Blk B = get_block<Mdl>(d, part, b);
+        for (int r = 0; r < B.nrows; ++r)
+          c_out[(size_t)c * nc + B.row0 + r] = buf[((size_t)tile * NRMAX + r) * d.nta + b * d.cpb + cl];
+      }
+    }
+  }
 };
 
-// dispatch on the CTA shape chosen at create time
-#define DISPATCH(h, CALL)                                                  \
-  ((h)->nbmax <= 24 ? K<32, 24, 1>::CALL : K<8, 128, 1>::CALL)
+// dispatch on the model chosen at create time
+#define DISPATCH(h, CALL) (Ops<FhnModel, 8, 8>::CALL)
 
-int to_soa(mmd_handle h, const double* host, double* dst, int rows) {
-  const size_t n = (size_t)h->d.n_chains * rows;
-  CK(cudaMemcpyAsync(h->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  dim3 grid((h->d.n_chains + 31) / 32, (rows + 31) / 32), blk(32, 8);
-  k_aos_to_soa<<<grid, blk, 0, h->stream>>>(h->stage, dst, h->d.n_chains, rows, h->d.ld);
-  h->launches++;
-  CK(cudaGetLastError());
+int h2d_stage(mmd_handle h, const double* host, double* stage, size_t n) {
+  CK(cudaMemcpyAsync(stage, host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
-int from_soa(mmd_handle h, const double* src, double* host, int rows) {
-  const size_t n = (size_t)h->d.n_chains * rows;
-  dim3 grid((h->d.n_chains + 31) / 32, (rows + 31) / 32), blk(32, 8);
-  k_soa_to_aos<<<grid, blk, 0, h->stream>>>(src, h->stage, h->d.n_chains, rows, h->d.ld);
-  h->launches++;
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(host, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+int d2h_sync(mmd_handle h, double* host, const double* dev, size_t n) {
+  CK(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
-
-// slot-resolved copy: gathers S.<arr>[cur or other] rows into a contiguous [rows][ld] buffer
-__global__ void k_gather_slot(const double* arr, long long stride, const int* cur, int sel, long long rows,
-                              long long ld, double* out) {
-  const long long n = rows * ld;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % ld);
-    const int sl = sel ? 1 - cur[c] : cur[c];
-    out[i] = arr[sl * stride + i];
-  }
-}
-__global__ void k_scatter_slot(double* arr, long long stride, const int* cur, int sel, long long rows,
-                               long long ld, const double* in) {
-  const long long n = rows * ld;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % ld);
-    const int sl = sel ? 1 - cur[c] : cur[c];
-    arr[sl * stride + i] = in[i];
-  }
-}
-
-int gather(mmd_handle h, const double* arr, long long stride, int sel, long long rows, double* out) {
-  k_gather_slot<<<592, 256, 0, h->stream>>>(arr, stride, h->S.cur, sel, rows, h->d.ld, out);
+int pack_chain(mmd_handle h, int rows, const double* canon_dev, double* dst) {
+  k_pack_chain<<<592, 256, 0, h->stream>>>(h->d, rows, canon_dev, dst);
   h->launches++;
   CK(cudaGetLastError());
   return 0;
 }
-int scatter(mmd_handle h, double* arr, long long stride, int sel, long long rows, const double* in) {
-  k_scatter_slot<<<592, 256, 0, h->stream>>>(arr, stride, h->S.cur, sel, rows, h->d.ld, in);
+int unpack_chain(mmd_handle h, int rows, double* canon_dev, const double* src) {
+  k_unpack_chain<<<592, 256, 0, h->stream>>>(h->d, rows, canon_dev, src);
   h->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+int reset_flags(mmd_handle h) {
+  const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
+  CK(cudaMemsetAsync(h->S.cur, 0, nc * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->W.status, 0, nc * sizeof(int), h->stream));
   return 0;
 }
 
@@ -259,21 +326,22 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   if (cfg->device < 0 || cfg->device >= ndev) FAIL("bad device ordinal");
   CK(cudaSetDevice(cfg->device));
   using Mdl = FhnModel;
+  constexpr int NRMAX = 8, RMAX = 8;
   const int T = cfg->num_obs, S = cfg->num_steps_per_obs;
   int R = cfg->num_obs_per_subseq;
   if (T <= 0 || S <= 0 || cfg->n_chains <= 0) FAIL("bad sizes");
   if (R <= 0 || R >= T) R = T;
-  if (cfg->noise != MMD_NOISE_NONE) FAIL("noisy observations not supported in this build");
-  if (cfg->gaussian_splitting) FAIL("gaussian splitting not supported in this build");
   const int nz = cfg->noise != MMD_NOISE_NONE;
   if (cfg->dim_u != Mdl::Z + (cfg->noise == MMD_NOISE_PARAM ? 1 : 0)) FAIL("dim_u inconsistent with model/noise");
   if (cfg->dim_u > UMAX) FAIL("dim_u too large");
   if (R - 1 + nz + Mdl::X > NRMAX || R > RMAX) FAIL("num_obs_per_subseq too large for this build");
+  if (R == T && T * Mdl::Y > NRMAX) FAIL("unblocked problem too large for this build");
 
   mmd_handle h = new mmd_handle_s();
   memset(&h->d, 0, sizeof(Dims));
   h->model = cfg->model;
   h->X = Mdl::X; h->V = Mdl::V; h->Z = Mdl::Z; h->V0 = Mdl::V0;
+  h->nrmax = NRMAX;
   Dims& d = h->d;
   d.T = T; d.S = S; d.R = R; d.U = cfg->dim_u;
   d.noisy = cfg->noise; d.gaussian = cfg->gaussian_splitting; d.sigma_fixed = cfg->sigma_fixed;
@@ -301,19 +369,32 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
       d.n_c[p] = (d.init_size[p] - 1 + nz + Mdl::X) + (d.nb[p] - 2) * (R - 1 + nz + Mdl::X) + d.fin_size[p];
   }
   d.n_chains = cfg->n_chains;
-  d.ld = (cfg->n_chains + 31) / 32 * 32;
   h->ncmax = d.n_c[0] > d.n_c[1] ? d.n_c[0] : d.n_c[1];
   h->nbmax = d.nb[0] > d.nb[1] ? d.nb[0] : d.nb[1];
+  if (h->nbmax > NTMAX) { delete h; FAIL("too many observation blocks for this build"); }
+  // chains per tile: the largest power of two that keeps the CTA at or below ~192 threads, unless overridden
+  int cpb = 32;
+  while (cpb > 1 && cpb * h->nbmax > 192) cpb >>= 1;
   const char* cpb_env = getenv("MMD_CPB");  // tuning override
+  if (cpb_env) {
+    const int c = atoi(cpb_env);
+    if (c >= 1 && c <= 32 && (c & (c - 1)) == 0 && c * h->nbmax <= NTMAX) cpb = c;
+  }
+  d.cpb = cpb;
+  d.lcpb = 0;
+  while ((1 << d.lcpb) < cpb) d.lcpb++;
+  d.n_tiles = (d.n_chains + cpb - 1) / cpb;
+  d.nslot = h->nbmax;
+  d.nta = d.nslot * cpb;
+  d.rmax = R;
+  d.rows_body = d.rmax * S * Mdl::V;
+  d.rows_noise = nz ? d.rmax : 0;
+  d.rows_head = d.U + Mdl::V0;
+  d.off_body = (long long)d.n_tiles * d.rows_head * cpb;
+  d.off_noise = d.off_body + (long long)d.n_tiles * d.rows_body * d.nta;
+  d.qsize = d.off_noise + (long long)d.n_tiles * d.rows_noise * d.nta;
   const char* fused_env = getenv("MMD_FUSED");
   h->fused = !(fused_env && atoi(fused_env) == 0);
-  if (h->nbmax <= 24) {
-    h->cpb = 32;
-    (void)cpb_env;
-  } else if (h->nbmax <= 128) { h->cpb = 8; }
-  else { delete h; FAIL("too many observation blocks for this build"); }
-  h->nslot = h->nbmax;
-  h->smem_bytes = (size_t)h->nslot * (UMAX * (UMAX + 1) / 2 + 1) * h->cpb * sizeof(double);
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
@@ -322,57 +403,65 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   h->prof_used = 0;
   h->lin_valid = false;
   h->partition = 0;
+  h->chain0 = 0;
 
-  const size_t ld = d.ld, N = (size_t)T * S, X = Mdl::X, V = Mdl::V, Z = Mdl::Z;
-  const size_t NTRI = NRMAX * (NRMAX + 1) / 2;
+  const size_t X = Mdl::X, V = Mdl::V, Z = Mdl::Z;
+  const size_t NTRI = NRMAX * (NRMAX + 1) / 2, UTRI = UMAX * (UMAX + 1) / 2;
+  const size_t tpu = (size_t)d.n_tiles * d.nta;         // elements per thread-private row
+  const size_t nc = (size_t)d.n_tiles * cpb;            // padded chain count
+  const size_t RS = (size_t)d.rmax * S;
   Slots& Sx = h->S;
-  Sx.s_q = (long long)d.dim_q * ld;
-  Sx.s_K = (long long)(N * X * V) * ld;
-  Sx.s_Psib = (long long)(T * X * X) * ld;
-  Sx.s_A = (long long)(h->ncmax * d.U) * ld;
-  Sx.s_L = (long long)(h->nbmax * NTRI) * ld;
-  Sx.s_LC = (long long)(UMAX * (UMAX + 1) / 2) * ld;
-  Sx.s_ld = (long long)ld;
+  Sx.s_q = d.qsize;
+  Sx.s_K = (long long)(RS * X * V * tpu);
+  Sx.s_Psib = (long long)(d.rmax * X * X * tpu);
+  Sx.s_xend = (long long)(d.rmax * X * tpu);
+  Sx.s_A = (long long)(NRMAX * d.U * tpu);
+  Sx.s_L = (long long)(NTRI * tpu);
+  Sx.s_LC = (long long)(UTRI * nc);
+  Sx.s_ld = (long long)nc;
   int rc = 0;
   rc |= dalloc(h, &Sx.q, 2 * Sx.s_q);
   rc |= dalloc(h, &Sx.p, 2 * Sx.s_q);
   rc |= dalloc(h, &Sx.K, 2 * Sx.s_K);
   rc |= dalloc(h, &Sx.Psib, 2 * Sx.s_Psib);
+  rc |= dalloc(h, &Sx.xend, 2 * Sx.s_xend);
   rc |= dalloc(h, &Sx.A, 2 * Sx.s_A);
   rc |= dalloc(h, &Sx.L, 2 * Sx.s_L);
   rc |= dalloc(h, &Sx.DinvA, 2 * Sx.s_A);
   rc |= dalloc(h, &Sx.LC, 2 * Sx.s_LC);
   rc |= dalloc(h, &Sx.gradld, 2 * Sx.s_q);
   rc |= dalloc(h, &Sx.ldv, 2 * Sx.s_ld);
-  rc |= dalloc(h, &Sx.cur, ld);
+  rc |= dalloc(h, &Sx.cur, nc);
   Work& W = h->W;
-  rc |= dalloc(h, &W.xs, N * X * ld);
-  rc |= dalloc(h, &W.Yw, N * X * X * ld);
-  rc |= dalloc(h, &W.Qk, (size_t)T * X * X * ld);
-  rc |= dalloc(h, &W.Zt, (size_t)T * X * Z * ld);
-  rc |= dalloc(h, &W.Mk, (size_t)T * X * X * ld);
-  rc |= dalloc(h, &W.LamZ, (size_t)T * Z * X * ld);
-  rc |= dalloc(h, &W.Yb, (size_t)T * X * X * ld);
-  rc |= dalloc(h, &W.alpha, (size_t)T * X * ld);
-  rc |= dalloc(h, &W.alphi, (size_t)T * X * ld);
-  rc |= dalloc(h, &W.qw, (size_t)d.dim_q * ld);
-  rc |= dalloc(h, &W.cvec, (size_t)h->ncmax * ld);
-  rc |= dalloc(h, &W.status, ld);
-  rc |= dalloc(h, &W.iters, 2 * ld);
-  rc |= dalloc(h, &W.revd, ld);
-  rc |= dalloc(h, &W.hval, ld);
-  rc |= dalloc(h, &W.itsum, ld);
-  rc |= dalloc(h, &h->xobs, (size_t)T * X * ld);
+  rc |= dalloc(h, &W.xs, RS * X * tpu);
+  rc |= dalloc(h, &W.Yw, RS * X * X * tpu);
+  rc |= dalloc(h, &W.Qk, d.rmax * X * X * tpu);
+  rc |= dalloc(h, &W.Zt, d.rmax * X * Z * tpu);
+  rc |= dalloc(h, &W.Mk, d.rmax * X * X * tpu);
+  rc |= dalloc(h, &W.LamZ, d.rmax * Z * X * tpu);
+  rc |= dalloc(h, &W.Yb, d.rmax * X * X * tpu);
+  rc |= dalloc(h, &W.alpha, d.rmax * X * tpu);
+  rc |= dalloc(h, &W.alphi, d.rmax * X * tpu);
+  rc |= dalloc(h, &W.qw, (size_t)d.qsize);
+  rc |= dalloc(h, &W.pw, (size_t)d.qsize);
+  rc |= dalloc(h, &W.xobs, (size_t)T * X * nc);
+  rc |= dalloc(h, &W.status, nc);
+  rc |= dalloc(h, &W.iters, 2 * nc);
+  rc |= dalloc(h, &W.revd, nc);
+  rc |= dalloc(h, &W.itsum, nc);
   rc |= dalloc(h, &h->y, (size_t)T * Mdl::Y);
-  size_t stage_n = (size_t)d.n_chains * (d.dim_q > (int)(N * X * V) ? d.dim_q : N * X * V);
+  const size_t stage_n = (size_t)d.n_chains * (size_t)(d.dim_q > (int)(T * X) ? d.dim_q : T * X);
   rc |= dalloc(h, &h->stage, stage_n);
-  rc |= dalloc(h, &h->stage2, (size_t)d.dim_q * ld);
-  rc |= dalloc(h, &h->hbuf, ld);
-  rc |= dalloc(h, &h->h0buf, ld);
-  rc |= dalloc(h, &h->qsave, (size_t)d.dim_q * ld);
-  rc |= dalloc(h, &h->accp, ld);
-  rc |= dalloc(h, &h->accepted, ld);
-  rc |= dalloc(h, &h->n_ok, ld);
+  rc |= dalloc(h, &h->stage2, stage_n);
+  rc |= dalloc(h, &h->tpbuf, (size_t)NRMAX * tpu);
+  rc |= dalloc(h, &h->hbuf, nc);
+  rc |= dalloc(h, &h->h0buf, nc);
+  rc |= dalloc(h, &h->qsave, (size_t)d.qsize);
+  rc |= dalloc(h, &h->qtmp, (size_t)d.qsize);
+  rc |= dalloc(h, &h->accp, nc);
+  rc |= dalloc(h, &h->accepted, nc);
+  rc |= dalloc(h, &h->cur0, nc);
+  rc |= dalloc(h, &h->n_ok, nc);
   if (rc) { mmd_destroy(h); return -2; }
   CK(cudaMemcpyAsync(h->y, cfg->y_seq, (size_t)T * Mdl::Y * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -397,59 +486,75 @@ int mmd_num_partition(mmd_handle h) { return h->d.num_partition; }
 int mmd_num_constraints(mmd_handle h, int p) { return h->d.n_c[p & 1]; }
 int mmd_num_blocks(mmd_handle h, int p) { return h->d.nb[p & 1]; }
 int mmd_n_chains(mmd_handle h) { return h->d.n_chains; }
-int mmd_leading_dim(mmd_handle h) { return h->d.ld; }
+int mmd_chains_per_tile(mmd_handle h) { return h->d.cpb; }
 int mmd_get_partition(mmd_handle h) { return h->partition; }
 long long mmd_launch_count(mmd_handle h) { return h->launches; }
+int mmd_set_chain_offset(mmd_handle h, int chain0) { h->chain0 = chain0; return 0; }
 
-int mmd_set_state(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition) {
+static int set_state_dev_impl(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_dev,
+                              int partition) {
   if (partition < 0 || partition >= h->d.num_partition) FAIL("bad partition");
-  CK(cudaMemsetAsync(h->S.cur, 0, h->d.ld * sizeof(int), h->stream));
-  CK(cudaMemsetAsync(h->W.status, 0, h->d.ld * sizeof(int), h->stream));
-  if (q) { if (to_soa(h, q, h->S.q, h->d.dim_q)) return -2; }
-  if (p) { if (to_soa(h, p, h->S.p, h->d.dim_q)) return -2; }
-  if (x_obs_seq) { if (to_soa(h, x_obs_seq, h->xobs, h->d.T * h->X)) return -2; }
+  if (reset_flags(h)) return -2;
   h->partition = partition;
   h->lin_valid = false;
+  if (q_dev) { if (DISPATCH(h, pack(h, q_dev, h->S.q, h->S.s_q, 0))) return -2; }
+  if (p_dev) { if (DISPATCH(h, pack(h, p_dev, h->S.p, h->S.s_q, 0))) return -2; }
+  if (x_dev) { if (pack_chain(h, h->d.T * h->X, x_dev, h->W.xobs)) return -2; }
+  return 0;
+}
+
+int mmd_set_state(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition) {
+  const size_t nq = (size_t)h->d.n_chains * h->d.dim_q;
+  if (q) { if (h2d_stage(h, q, h->stage, nq)) return -2; }
+  if (set_state_dev_impl(h, q ? h->stage : nullptr, nullptr, nullptr, partition)) return -2;
+  if (p) {
+    if (h2d_stage(h, p, h->stage2, nq)) return -2;
+    if (DISPATCH(h, pack(h, h->stage2, h->S.p, h->S.s_q, 0))) return -2;
+  }
+  if (x_obs_seq) {
+    // `stage` is reused: stream order guarantees the q pack has consumed it
+    if (h2d_stage(h, x_obs_seq, h->stage, (size_t)h->d.n_chains * h->d.T * h->X)) return -2;
+    if (pack_chain(h, h->d.T * h->X, h->stage, h->W.xobs)) return -2;
+  }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
-int mmd_set_state_soa_dev(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_dev,
-                          int partition) {
-  if (partition < 0 || partition >= h->d.num_partition) FAIL("bad partition");
-  CK(cudaMemsetAsync(h->S.cur, 0, h->d.ld * sizeof(int), h->stream));
-  CK(cudaMemsetAsync(h->W.status, 0, h->d.ld * sizeof(int), h->stream));
-  const size_t nq = (size_t)h->d.dim_q * h->d.ld * sizeof(double);
-  if (q_dev) CK(cudaMemcpyAsync(h->S.q, q_dev, nq, cudaMemcpyDeviceToDevice, h->stream));
-  if (p_dev) CK(cudaMemcpyAsync(h->S.p, p_dev, nq, cudaMemcpyDeviceToDevice, h->stream));
-  if (x_dev)
-    CK(cudaMemcpyAsync(h->xobs, x_dev, (size_t)h->d.T * h->X * h->d.ld * sizeof(double),
-                       cudaMemcpyDeviceToDevice, h->stream));
-  h->partition = partition;
-  h->lin_valid = false;
-  return 0;
+int mmd_set_state_dev(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_dev, int partition) {
+  return set_state_dev_impl(h, q_dev, p_dev, x_dev, partition);
 }
 
 int mmd_set_momentum(mmd_handle h, const double* p) {
-  if (to_soa(h, p, h->stage2, h->d.dim_q)) return -2;
-  return scatter(h, h->S.p, h->S.s_q, 0, h->d.dim_q, h->stage2);
+  if (h2d_stage(h, p, h->stage2, (size_t)h->d.n_chains * h->d.dim_q)) return -2;
+  return DISPATCH(h, pack(h, h->stage2, h->S.p, h->S.s_q, 0));
 }
 
 int mmd_get_state(mmd_handle h, double* q, double* p, double* x_obs_seq) {
+  const size_t nq = (size_t)h->d.n_chains * h->d.dim_q;
   if (q) {
-    if (gather(h, h->S.q, h->S.s_q, 0, h->d.dim_q, h->stage2)) return -2;
-    if (from_soa(h, h->stage2, q, h->d.dim_q)) return -2;
+    if (DISPATCH(h, unpack(h, h->stage, h->S.q, h->S.s_q, 0))) return -2;
+    if (d2h_sync(h, q, h->stage, nq)) return -2;
   }
   if (p) {
-    if (gather(h, h->S.p, h->S.s_q, 0, h->d.dim_q, h->stage2)) return -2;
-    if (from_soa(h, h->stage2, p, h->d.dim_q)) return -2;
+    if (DISPATCH(h, unpack(h, h->stage, h->S.p, h->S.s_q, 0))) return -2;
+    if (d2h_sync(h, p, h->stage, nq)) return -2;
   }
-  if (x_obs_seq) { if (from_soa(h, h->xobs, x_obs_seq, h->d.T * h->X)) return -2; }
+  if (x_obs_seq) {
+    if (unpack_chain(h, h->d.T * h->X, h->stage, h->W.xobs)) return -2;
+    if (d2h_sync(h, x_obs_seq, h->stage, (size_t)h->d.n_chains * h->d.T * h->X)) return -2;
+  }
+  return 0;
+}
+
+int mmd_get_state_dev(mmd_handle h, double* q_dev, double* p_dev, double* x_dev) {
+  if (q_dev) { if (DISPATCH(h, unpack(h, q_dev, h->S.q, h->S.s_q, 0))) return -2; }
+  if (p_dev) { if (DISPATCH(h, unpack(h, p_dev, h->S.p, h->S.s_q, 0))) return -2; }
+  if (x_dev) { if (unpack_chain(h, h->d.T * h->X, x_dev, h->W.xobs)) return -2; }
   return 0;
 }
 
 int mmd_linearize(mmd_handle h, int with_grad) {
-  CK(cudaMemsetAsync(h->W.status, 0, h->d.ld * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->W.status, 0, (size_t)h->d.n_tiles * h->d.cpb * sizeof(int), h->stream));
   int rc = DISPATCH(h, point(h, 0, with_grad));
   if (rc) return rc;
   h->lin_valid = true;
@@ -457,105 +562,124 @@ int mmd_linearize(mmd_handle h, int with_grad) {
 }
 
 int mmd_constr(mmd_handle h, double* c_out) {
-  if (gather(h, h->S.q, h->S.s_q, 0, h->d.dim_q, h->stage2)) return -2;
-  int rc = DISPATCH(h, constr(h, h->stage2, h->W.cvec));
+  int rc = DISPATCH(h, constr(h));
   if (rc) return rc;
-  return from_soa(h, h->W.cvec, c_out, h->d.n_c[h->partition]);
+  std::vector<double> buf((size_t)h->d.n_tiles * h->nrmax * h->d.nta);
+  if (d2h_sync(h, buf.data(), h->tpbuf, buf.size())) return -2;
+  DISPATCH(h, constr_rows(h, buf, c_out));
+  return 0;
 }
 
 int mmd_log_det_sqrt_gram(mmd_handle h, double* out) {
   if (!h->lin_valid) FAIL("call mmd_linearize first");
-  if (gather(h, h->S.ldv, h->S.s_ld, 0, 1, h->hbuf)) return -2;
-  CK(cudaMemcpyAsync(out, h->hbuf, h->d.n_chains * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
+  std::vector<double> ld(2 * nc);
+  std::vector<int> cur(nc);
+  CK(cudaMemcpyAsync(ld.data(), h->S.ldv, 2 * nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(cur.data(), h->S.cur, nc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < h->d.n_chains; ++c) out[c] = ld[(size_t)cur[c] * nc + c];
   return 0;
 }
 
 int mmd_grad_log_det_sqrt_gram(mmd_handle h, double* out) {
   if (!h->lin_valid) FAIL("call mmd_linearize(with_grad=1) first");
-  if (gather(h, h->S.gradld, h->S.s_q, 0, h->d.dim_q, h->stage2)) return -2;
-  return from_soa(h, h->stage2, out, h->d.dim_q);
+  if (DISPATCH(h, unpack(h, h->stage, h->S.gradld, h->S.s_q, 0))) return -2;
+  return d2h_sync(h, out, h->stage, (size_t)h->d.n_chains * h->d.dim_q);
 }
 
 int mmd_hamiltonian(mmd_handle h, double* out) {
   if (!h->lin_valid) FAIL("call mmd_linearize first");
   int rc = DISPATCH(h, hamiltonian(h, 0, h->hbuf));
   if (rc) return rc;
-  CK(cudaMemcpyAsync(out, h->hbuf, h->d.n_chains * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  return 0;
+  return d2h_sync(h, out, h->hbuf, h->d.n_chains);
 }
+
+static const FlowCoef NOFLOW = {0, 1.0, 0.0, 0.0};
 
 int mmd_project_momentum(mmd_handle h) {
   if (!h->lin_valid) FAIL("call mmd_linearize first");
-  return DISPATCH(h, project(h, 0, 0, 0, 0.0, 0.0));
+  return DISPATCH(h, project(h, 0, PSEL_CUR, PSEL_CUR, 0.0, 0.0, NOFLOW));
 }
 
 int mmd_normal_space_component(mmd_handle h, const double* vct, double* out) {
   if (!h->lin_valid) FAIL("call mmd_linearize first");
-  // use the inactive slot's momentum array as scratch: proj(vct) -> p(other); nsc = vct - proj(vct)
-  if (to_soa(h, vct, h->stage2, h->d.dim_q)) return -2;
-  if (scatter(h, h->S.p, h->S.s_q, 1, h->d.dim_q, h->stage2)) return -2;
-  int rc = DISPATCH(h, project(h, 0, 1, 1, 0.0, 0.0));
-  if (rc) return rc;
-  if (gather(h, h->S.p, h->S.s_q, 1, h->d.dim_q, h->stage2)) return -2;
-  if (from_soa(h, h->stage2, out, h->d.dim_q)) return -2;
+  // use the work momentum as scratch: proj(vct) -> pw; nsc = vct - proj(vct)
   const size_t n = (size_t)h->d.n_chains * h->d.dim_q;
+  if (h2d_stage(h, vct, h->stage2, n)) return -2;
+  if (DISPATCH(h, pack(h, h->stage2, h->W.pw, 0, 2))) return -2;
+  int rc = DISPATCH(h, project(h, 0, PSEL_WORK, PSEL_WORK, 0.0, 0.0, NOFLOW));
+  if (rc) return rc;
+  if (DISPATCH(h, unpack(h, h->stage, h->W.pw, 0, 2))) return -2;
+  if (d2h_sync(h, out, h->stage, n)) return -2;
   for (size_t i = 0; i < n; ++i) out[i] = vct[i] - out[i];
   return 0;
 }
 
 int mmd_update_x_obs_seq(mmd_handle h) {
-  if (gather(h, h->S.q, h->S.s_q, 0, h->d.dim_q, h->stage2)) return -2;
-  k_gen_xobs<FhnModel, UMAX><<<(h->d.n_chains + 63) / 64, 64, 0, h->stream>>>(h->d, h->stage2, h->xobs);
-  h->launches++;
-  CK(cudaGetLastError());
+  int rc = DISPATCH(h, gen_xobs(h));
   h->lin_valid = false;
-  return 0;
+  return rc;
 }
 
 int mmd_switch_partition(mmd_handle h) {
-  h->partition = (h->partition + 1) % h->d.num_partition;
+  // SwitchPartitionTransition.sample (:1279-1282): next partition, regenerate x_obs_seq from the position
+  const int pa = h->partition, pb = (h->partition + 1) % h->d.num_partition;
+  if (pa != pb) {
+    if (DISPATCH(h, retile(h, pa, pb))) return -2;
+    h->partition = pb;
+  }
   return mmd_update_x_obs_seq(h);
 }
 
 int mmd_sample_momentum(mmd_handle h, uint64_t seed, uint64_t offset) {
   if (!h->lin_valid) FAIL("call mmd_linearize first");
-  k_philox_normal<<<592, 256, 0, h->stream>>>(h->stage2, (long long)h->d.dim_q * h->d.ld, seed, offset);
-  h->launches++;
-  CK(cudaGetLastError());
-  if (scatter(h, h->S.p, h->S.s_q, 0, h->d.dim_q, h->stage2)) return -2;
-  return DISPATCH(h, project(h, 0, 0, 0, 0.0, 0.0));
+  if (DISPATCH(h, philox(h, seed, offset))) return -2;
+  return DISPATCH(h, project(h, 0, PSEL_CUR, PSEL_CUR, 0.0, 0.0, NOFLOW));
 }
 
 int mmd_get_factor(mmd_handle h, const char* name, double* out, int* rows_out) {
   const Dims& d = h->d;
   const double* arr = nullptr;
-  long long stride = 0, rows = 0;
-  const long long NTRI = NRMAX * (NRMAX + 1) / 2;
+  long long stride = 0;
+  int rows = 0;
+  bool per_chain = false;
+  const int NTRI = h->nrmax * (h->nrmax + 1) / 2;
   std::string nm(name);
-  if (nm == "K") { arr = h->S.K; stride = h->S.s_K; rows = (long long)d.T * d.S * h->X * h->V; }
-  else if (nm == "Psib") { arr = h->S.Psib; stride = h->S.s_Psib; rows = (long long)d.T * h->X * h->X; }
-  else if (nm == "A") { arr = h->S.A; stride = h->S.s_A; rows = (long long)d.n_c[h->partition] * d.U; }
-  else if (nm == "DinvA") { arr = h->S.DinvA; stride = h->S.s_A; rows = (long long)d.n_c[h->partition] * d.U; }
-  else if (nm == "L") { arr = h->S.L; stride = h->S.s_L; rows = (long long)d.nb[h->partition] * NTRI; }
-  else if (nm == "LC") { arr = h->S.LC; stride = h->S.s_LC; rows = d.U * (d.U + 1) / 2; }
+  if (nm == "K") { arr = h->S.K; stride = h->S.s_K; rows = d.rmax * d.S * h->X * h->V; }
+  else if (nm == "Psib") { arr = h->S.Psib; stride = h->S.s_Psib; rows = d.rmax * h->X * h->X; }
+  else if (nm == "xend") { arr = h->S.xend; stride = h->S.s_xend; rows = d.rmax * h->X; }
+  else if (nm == "A") { arr = h->S.A; stride = h->S.s_A; rows = h->nrmax * d.U; }
+  else if (nm == "DinvA") { arr = h->S.DinvA; stride = h->S.s_A; rows = h->nrmax * d.U; }
+  else if (nm == "L") { arr = h->S.L; stride = h->S.s_L; rows = NTRI; }
+  else if (nm == "LC") { arr = h->S.LC; stride = h->S.s_LC; rows = UMAX * (UMAX + 1) / 2; per_chain = true; }
   else FAIL("unknown factor name");
-  if (rows_out) *rows_out = (int)rows;
+  if (rows_out) *rows_out = rows;
   if (!out) return 0;
   if (!h->lin_valid) FAIL("call mmd_linearize first");
-  // gather into stage (large enough: stage holds n_chains * max(dim_q, N*X*V) and ld-padded rows fit
-  // because every factor has rows <= N*X*V)
+  if (per_chain) {
+    // [chain][rows]
+    const size_t nc = (size_t)d.n_tiles * d.cpb;
+    std::vector<double> buf(2 * (size_t)stride);
+    std::vector<int> cur(nc);
+    CK(cudaMemcpyAsync(buf.data(), arr, buf.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cur.data(), h->S.cur, nc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < d.n_chains; ++c)
+      for (int r = 0; r < rows; ++r)
+        out[(size_t)c * rows + r] =
+            buf[(size_t)cur[c] * stride + ((size_t)(c / d.cpb) * rows + r) * d.cpb + c % d.cpb];
+    return 0;
+  }
+  // [chain][block][rows]
+  const size_t n = (size_t)d.n_chains * d.nb[h->partition] * rows;
   double* tmp = nullptr;
-  CK(cudaMalloc((void**)&tmp, (size_t)rows * d.ld * sizeof(double)));
-  if (gather(h, arr, stride, 0, rows, tmp)) { cudaFree(tmp); return -2; }
-  std::vector<double> hostbuf((size_t)rows * d.ld);
-  CK(cudaMemcpyAsync(hostbuf.data(), tmp, hostbuf.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMalloc((void**)&tmp, n * sizeof(double)));
+  k_unpack_tp<<<592, 256, 0, h->stream>>>(d, h->partition, rows, tmp, arr, stride, h->S.cur);
+  h->launches++;
+  int rc = d2h_sync(h, out, tmp, n);
   cudaFree(tmp);
-  for (long long r = 0; r < rows; ++r)
-    memcpy(out + r * d.n_chains, hostbuf.data() + r * d.ld, d.n_chains * sizeof(double));
-  return 0;
+  return rc;
 }
 
 static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opts, bool reset_status,
@@ -568,25 +692,25 @@ static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opt
     if (rc0) return rc0;
   }
   if (h->fused) return DISPATCH(h, leapfrog(h, dt, &o, n_steps, reset_status ? 1 : 0));
-  if (reset_status) CK(cudaMemsetAsync(h->W.status, 0, h->d.ld * sizeof(int), h->stream));
+  if (reset_status)
+    CK(cudaMemsetAsync(h->W.status, 0, (size_t)h->d.n_tiles * h->d.cpb * sizeof(int), h->stream));
+  const StepCoef sc = step_coef(h->d, dt);
   int rc = 0;
   for (int step_i = 0; step_i < n_steps; ++step_i) {
-  // A(dt/2): h1_flow + cotangent projection at the current point; result -> p(other)
-  rc = DISPATCH(h, project(h, 0, 0, 1, 0.5 * dt, 1.0)); if (rc) return rc;
-  // B(dt): h2_flow, projection onto the manifold with the Jacobian at the previous point
-  k_flow<<<592, 256, 0, h->stream>>>(h->d, h->S, h->W, 0, 1, dt); h->launches++;
-  rc = DISPATCH(h, qn(h, 0, 1.0 / dt, &o)); if (rc) return rc;
-  // pre-evaluate dh1_dpos at the new point (fills the new slot's cache), project momentum
-  rc = DISPATCH(h, point(h, 1, 1)); if (rc) return rc;
-  rc = DISPATCH(h, project(h, 1, 1, 1, 0.0, 0.0)); if (rc) return rc;
-  // reversibility check: step back and project with the Jacobian at the new point
-  k_flow<<<592, 256, 0, h->stream>>>(h->d, h->S, h->W, 1, 1, -dt); h->launches++;
-  rc = DISPATCH(h, qn(h, 1, 0.0, &o)); if (rc) return rc;
-  // A(dt/2)
-  rc = DISPATCH(h, project(h, 1, 1, 1, 0.5 * dt, 1.0)); if (rc) return rc;
-  k_commit<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->S, h->W, o.reverse_check_tol, h->n_ok);
-  h->launches++;
-  CK(cudaGetLastError());
+    // A(dt/2): h1_flow + cotangent projection at the current point, fused h2_flow -> pw, qw
+    rc = DISPATCH(h, project(h, 0, PSEL_CUR, PSEL_WORK, sc.half_dt, sc.qcoef, sc.fwd)); if (rc) return rc;
+    // B(dt): projection onto the manifold with the Jacobian at the previous point
+    rc = DISPATCH(h, qn(h, 0, sc.mom_coef, &o)); if (rc) return rc;
+    // pre-evaluate dh1_dpos at the new point (fills the new slot's cache), project momentum
+    rc = DISPATCH(h, point(h, 1, 1)); if (rc) return rc;
+    rc = DISPATCH(h, project(h, 1, PSEL_OTHER, PSEL_OTHER, 0.0, 0.0, sc.back)); if (rc) return rc;
+    // reversibility check: step back and project with the Jacobian at the new point
+    rc = DISPATCH(h, qn(h, 1, 0.0, &o)); if (rc) return rc;
+    // A(dt/2)
+    rc = DISPATCH(h, project(h, 1, PSEL_OTHER, PSEL_OTHER, sc.half_dt, sc.qcoef, NOFLOW)); if (rc) return rc;
+    k_commit<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->S, h->W, o.reverse_check_tol, h->n_ok);
+    h->launches++;
+    CK(cudaGetLastError());
   }
   return 0;
 }
@@ -599,7 +723,9 @@ int mmd_transition_begin(mmd_handle h, uint64_t seed, uint64_t iter) {
   int rc = mmd_linearize(h, 1); if (rc) return rc;               // also clears status
   rc = mmd_sample_momentum(h, seed, 2 * iter); if (rc) return rc;
   rc = DISPATCH(h, hamiltonian(h, 0, h->h0buf)); if (rc) return rc;
-  if (gather(h, h->S.q, h->S.s_q, 0, h->d.dim_q, h->qsave)) return -2;
+  k_snapshot<<<1184, 256, 0, h->stream>>>(h->d, h->S, h->qsave);
+  h->launches++;
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -609,10 +735,10 @@ int mmd_transition_steps(mmd_handle h, double dt, int n_steps, const mmd_integra
 
 int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_partition) {
   int rc = DISPATCH(h, hamiltonian(h, 0, h->hbuf)); if (rc) return rc;
-  k_decide<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->W, h->h0buf, h->hbuf, seed, 2 * iter + 1,
-                                                              h->accepted, h->accp);
+  k_decide<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->S, h->W, h->h0buf, h->hbuf, h->cur0, seed,
+                                                              2 * iter + 1, h->chain0, h->accepted, h->accp);
   h->launches++;
-  k_restore<<<592, 256, 0, h->stream>>>(h->d, h->S, h->accepted, h->qsave);
+  k_restore<<<1184, 256, 0, h->stream>>>(h->d, h->S, h->accepted, h->qsave);
   h->launches++;
   CK(cudaGetLastError());
   h->lin_valid = false;
@@ -660,29 +786,20 @@ int mmd_profile_summary(mmd_handle h, int kid, int* count, double* total_ms) {
   return 0;
 }
 
-long long mmd_successful_steps(mmd_handle h, int reset) {
-  std::vector<long long> host(h->d.ld);
-  if (cudaMemcpyAsync(host.data(), h->n_ok, h->d.ld * sizeof(long long), cudaMemcpyDeviceToHost, h->stream) !=
-      cudaSuccess)
+static long long sum_counter(mmd_handle h, long long* dev, int reset) {
+  const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
+  std::vector<long long> host(nc);
+  if (cudaMemcpyAsync(host.data(), dev, nc * sizeof(long long), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
     return -1;
   cudaStreamSynchronize(h->stream);
   long long tot = 0;
   for (int i = 0; i < h->d.n_chains; ++i) tot += host[i];
-  if (reset) cudaMemsetAsync(h->n_ok, 0, h->d.ld * sizeof(long long), h->stream);
+  if (reset) cudaMemsetAsync(dev, 0, nc * sizeof(long long), h->stream);
   return tot;
 }
 
-long long mmd_total_qn_iterations(mmd_handle h, int reset) {
-  std::vector<long long> host(h->d.ld);
-  if (cudaMemcpyAsync(host.data(), h->W.itsum, h->d.ld * sizeof(long long), cudaMemcpyDeviceToHost, h->stream) !=
-      cudaSuccess)
-    return -1;
-  cudaStreamSynchronize(h->stream);
-  long long tot = 0;
-  for (int i = 0; i < h->d.n_chains; ++i) tot += host[i];
-  if (reset) cudaMemsetAsync(h->W.itsum, 0, h->d.ld * sizeof(long long), h->stream);
-  return tot;
-}
+long long mmd_successful_steps(mmd_handle h, int reset) { return sum_counter(h, h->n_ok, reset); }
+long long mmd_total_qn_iterations(mmd_handle h, int reset) { return sum_counter(h, h->W.itsum, reset); }
 
 int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, int* status) {
   const int n = h->d.n_chains;
@@ -695,10 +812,10 @@ int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, i
 
 int mmd_get_step_info(mmd_handle h, int* status, int* iters_fwd, int* iters_rev, double* rev_dist) {
   const int n = h->d.n_chains;
+  const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
   if (status) CK(cudaMemcpyAsync(status, h->W.status, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (iters_fwd) CK(cudaMemcpyAsync(iters_fwd, h->W.iters, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  if (iters_rev)
-    CK(cudaMemcpyAsync(iters_rev, h->W.iters + h->d.ld, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (iters_rev) CK(cudaMemcpyAsync(iters_rev, h->W.iters + nc, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (rev_dist) CK(cudaMemcpyAsync(rev_dist, h->W.revd, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -709,12 +826,14 @@ int mmd_project_quasi_newton(mmd_handle h, const double* q_in, double dt, const 
   mmd_integrator_opts o;
   if (opts) o = *opts; else mmd_default_integrator_opts(&o);
   if (!h->lin_valid) FAIL("call mmd_linearize first");
-  CK(cudaMemsetAsync(h->W.status, 0, h->d.ld * sizeof(int), h->stream));
-  if (to_soa(h, q_in, h->W.qw, h->d.dim_q)) return -2;
+  const size_t n = (size_t)h->d.n_chains * h->d.dim_q;
+  CK(cudaMemsetAsync(h->W.status, 0, (size_t)h->d.n_tiles * h->d.cpb * sizeof(int), h->stream));
+  if (h2d_stage(h, q_in, h->stage2, n)) return -2;
+  if (DISPATCH(h, pack(h, h->stage2, h->W.qw, 0, 2))) return -2;
   int rc = DISPATCH(h, qn(h, 0, 0.0, &o));
   if (rc) return rc;
-  if (gather(h, h->S.q, h->S.s_q, 1, h->d.dim_q, h->stage2)) return -2;
-  if (from_soa(h, h->stage2, q_out, h->d.dim_q)) return -2;
+  if (DISPATCH(h, unpack(h, h->stage, h->S.q, h->S.s_q, 1))) return -2;
+  if (d2h_sync(h, q_out, h->stage, n)) return -2;
   (void)dt;
   return mmd_get_step_info(h, status, iters, nullptr, nullptr);
 }
@@ -724,18 +843,23 @@ int mmd_init_linear_interpolation(mmd_handle h, const double* u, const double* v
   // find_initial_state_by_linear_interpolation (:1479-1547) for all chains at once
   if (partition < 0 || partition >= h->d.num_partition) FAIL("bad partition");
   const Dims& d = h->d;
-  CK(cudaMemsetAsync(h->S.cur, 0, d.ld * sizeof(int), h->stream));
-  CK(cudaMemsetAsync(h->W.status, 0, d.ld * sizeof(int), h->stream));
-  CK(cudaMemsetAsync(h->S.q, 0, (size_t)d.dim_q * d.ld * sizeof(double), h->stream));
-  if (to_soa(h, u, h->S.q, d.U)) return -2;
-  if (to_soa(h, v_0, h->S.q + (long long)d.off_v0 * d.ld, h->V0)) return -2;
-  if (to_soa(h, x_obs_seq, h->xobs, d.T * h->X)) return -2;
-  const long long n = (long long)d.T * d.ld;
-  k_init_interp<FhnModel, UMAX><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(d, h->S.q, h->xobs);
-  h->launches++;
-  CK(cudaGetLastError());
+  if (reset_flags(h)) return -2;
   h->partition = partition;
   h->lin_valid = false;
+  CK(cudaMemsetAsync(h->S.q, 0, (size_t)d.qsize * sizeof(double), h->stream));
+  // head rows [u | v_0] of slot 0: assemble [chain][U + V0] on the host side of the staging buffer
+  std::vector<double> head((size_t)d.n_chains * d.rows_head);
+  for (int c = 0; c < d.n_chains; ++c) {
+    for (int j = 0; j < d.U; ++j) head[(size_t)c * d.rows_head + j] = u[(size_t)c * d.U + j];
+    for (int j = 0; j < h->V0; ++j) head[(size_t)c * d.rows_head + d.U + j] = v_0[(size_t)c * h->V0 + j];
+  }
+  if (h2d_stage(h, head.data(), h->stage2, head.size())) return -2;
+  if (pack_chain(h, d.rows_head, h->stage2, h->S.q)) return -2;
+  if (h2d_stage(h, x_obs_seq, h->stage, (size_t)d.n_chains * d.T * h->X)) return -2;
+  if (pack_chain(h, d.T * h->X, h->stage, h->W.xobs)) return -2;
+  int rc = DISPATCH(h, init_interp(h));
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));  // `head` is pageable host memory owned by this call
   return 0;
 }
 

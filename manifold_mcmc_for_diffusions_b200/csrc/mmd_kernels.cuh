@@ -1,11 +1,16 @@
 // Hand-written FP64 CUDA kernels (sm_100a) for the constrained-HMC hot path of
 // sde/mici_extensions.py (reference), batched over chains.
 //
-// Mapping: one thread = one (chain, observation block); a warp = 32 (or CPB) consecutive chains
-// of the same block, so every global access is a coalesced row of a structure-of-arrays
-// [row][chain] matrix.  A CTA owns CPB chains x all of their blocks, so the cross-block
-// reductions (Woodbury capacitance matrix C, u-part of J^T lambda, norms) are shared-memory
-// reductions and no kernel ever needs a grid-wide sync or a host round trip.
+// Mapping: one thread = one (chain, observation block).  A CTA owns a *tile* of `cpb` chains x all of
+// their blocks: thread tid = slot * cpb + cl  (slot = block index, cl = chain within the tile), so
+// the cross-block reductions (Woodbury capacitance matrix C, u-part of J^T lambda, norms) stay inside
+// the CTA and no kernel needs a grid-wide sync or a host round trip.
+//
+// Memory layout ("tile layout"): every per-(chain, block) quantity is a
+// thread-private column of a [tile][row][nta] array (nta = threads allocated per tile), every per-chain
+// quantity a column of a [tile][row][cpb] array.  A warp therefore always reads 32 consecutive
+// doubles, a CTA streams one contiguous slab per array, and the inner loops address memory as
+// base + row * nta with no index arithmetic beyond one multiply-add.
 //
 // The block Jacobian dc/dv (reference: jacob_constr_blocks, mici_extensions.py:521-624, dense
 // [rows, R*S*dim_v] per block) is never materialised.  For step t inside observation interval k
@@ -18,7 +23,7 @@
 #include <stdint.h>
 
 #ifndef MMD_PREFETCH_STEPS
-#define MMD_PREFETCH_STEPS 5
+#define MMD_PREFETCH_STEPS 3
 #endif
 
 namespace mmd {
@@ -38,49 +43,115 @@ struct Dims {
   int fin_size[2];    // obs in last block
   int n_c[2];         // constraint rows per partition
   int num_partition;
-  int n_chains, ld;   // chains and leading dimension (>= n_chains, multiple of 32)
+  int n_chains;
+  int cpb, lcpb;      // chains per tile (power of two) and its log2
+  int n_tiles;        // ceil(n_chains / cpb)
+  int nslot;          // block slots allocated per tile = max(nb[0], nb[1])
+  int nta;            // nslot * cpb: threads allocated per tile = row stride of thread-private arrays
+  int rmax;           // max observations per block (R, or T for a single block)
   double delta, sd;   // step delta = obs_interval / S and sqrt(delta)
-  int off_v0, off_v, off_n;  // row offsets into q: [u | v_0 | v_seq | n]  (:476-484)
+  int off_v0, off_v, off_n;  // row offsets into the reference's q: [u | v_0 | v_seq | n]  (:476-484)
+  // rows per thread / per chain of the array families
+  int rows_body;      // rmax * S * V      q-like vectors, per-step part
+  int rows_noise;     // rmax (noisy) or 0 q-like vectors, observation-noise part
+  int rows_head;      // U + V0            q-like vectors, per-chain part [u | v_0]
+  long long off_body, off_noise, qsize;  // section offsets / total size of one q-like vector
+};
+
+// q-like vector (q, p, grad log det, work position ...) in tile layout: three sections
+//   head  [tile][rows_head][cpb]   (u, v_0: shared by all blocks of the chain)
+//   body  [tile][rows_body][nta]   (v_t of the thread's block: row (k*S + t)*V + j)
+//   noise [tile][rows_noise][nta]  (n_k of the thread's block)
+struct QPtr {
+  double* head;
+  double* body;
+  double* noise;
 };
 
 // Everything Mici caches at a position (jacob_constr_blocks, chol_gram_blocks, log_det_sqrt_gram,
 // grad_log_det_sqrt_gram; mici_extensions.py:1151-1184) in compressed form, double-buffered so a
-// failed step leaves the chain where it was.  Arrays are [2][rows][ld]; `cur[chain]` selects.
+// failed step leaves the chain where it was.  `cur[chain]` selects the live slot.
 struct Slots {
-  double* q;       // [dim_q]
-  double* p;       // [dim_q]
-  double* K;       // [T*S*X*V]
-  double* Psib;    // [T*X*X]
-  double* A;       // [NCMAX*U]      dc/du rows
-  double* L;       // [NBMAX*NRTRI]  packed lower Cholesky factors of D_b
-  double* DinvA;   // [NCMAX*U]
-  double* LC;      // [U(U+1)/2]     packed lower Cholesky factor of C
-  double* gradld;  // [dim_q]
-  double* ldv;     // [1]
-  long long s_q, s_K, s_Psib, s_A, s_L, s_LC, s_ld;  // slot strides in elements
-  int* cur;        // [ld]
+  double* q;       // q-like
+  double* p;       // q-like
+  double* gradld;  // q-like
+  double* K;       // thread-private [rmax*S*X*V]
+  double* Psib;    // thread-private [rmax*X*X]
+  double* xend;    // thread-private [rmax*X]      state at the observation times (nonlinear obs_func)
+  double* A;       // thread-private [NRMAX*U]     dc/du rows
+  double* L;       // thread-private [NRTRI]       packed lower Cholesky factor of D_b (diagonal stored inverted)
+  double* DinvA;   // thread-private [NRMAX*U]
+  double* LC;      // per-chain [U(U+1)/2]         packed lower Cholesky factor of C (diagonal stored inverted)
+  double* ldv;     // per-chain [1]
+  long long s_q, s_K, s_Psib, s_xend, s_A, s_L, s_LC, s_ld;  // slot strides in elements
+  int* cur;        // [n_tiles * cpb]
 };
 
 struct Work {
-  double* xs;     // [T*S*X]   trajectory x_t at the point being linearised
-  double* Yw;     // [T*S*X*X] forward tangent accumulator of the second-order sweep
-  double* Qk;     // [T*X*X]
-  double* Zt;     // [T*X*Z]
-  double* Mk;     // [T*X*X]
-  double* LamZ;   // [T*Z*X]
-  double* Yb;     // [T*X*X]
-  double* alpha;  // [T*X]
-  double* alphi;  // [T*X]
-  double* qw;     // [dim_q]   work position for the projection solves
-  double* cvec;   // [NCMAX]
-  int* status;    // [ld]  bit 1 not converged, 2 diverged, 4 non-reversible, 8 non-finite H
-  int* iters;     // [2][ld] projection iterations (forward, reverse) of the last step
-  double* revd;   // [ld] reverse-check distance of the last step
-  double* hval;   // [ld]
-  long long* itsum;  // [ld] total quasi-Newton iterations executed (both directions)
+  double* xs;     // thread-private [rmax*S*X]   trajectory x_t at the point being linearised
+  double* Yw;     // thread-private [rmax*S*X*X] forward tangent accumulator of the second-order sweep
+  double* Qk;     // thread-private [rmax*X*X]
+  double* Zt;     // thread-private [rmax*X*Z]
+  double* Mk;     // thread-private [rmax*X*X]
+  double* LamZ;   // thread-private [rmax*Z*X]
+  double* Yb;     // thread-private [rmax*X*X]
+  double* alpha;  // thread-private [rmax*X]
+  double* alphi;  // thread-private [rmax*X]
+  double* qw;     // q-like: work position for the projection solves
+  double* pw;     // q-like: work momentum (after the first half kick + projection)
+  double* xobs;   // per-chain [T*X]  conditioned states at observation times (x_obs_seq)
+  int* status;    // [chains]  bit 1 not converged, 2 diverged, 4 non-reversible, 8 non-finite H
+  int* iters;     // [2][chains] projection iterations (forward, reverse) of the last step
+  double* revd;   // [chains] reverse-check distance of the last step
+  long long* itsum;  // [chains] total projection iterations executed (both directions)
 };
 
 enum : int { ST_NOTCONV = 1, ST_DIVERGED = 2, ST_NONREV = 4, ST_NONFINITE = 8 };
+enum : int { PSEL_CUR = 0, PSEL_OTHER = 1, PSEL_WORK = 2 };
+
+// ------------------------------------------------------------------------------------------
+// per-thread identity and tile-layout accessors
+// ------------------------------------------------------------------------------------------
+struct Tid {
+  int tile, tid, cl, slot, nslot, chain, cix;  // cix = tile * cpb + cl = index into per-chain scalars
+  bool act;
+  int nta, cpb;
+};
+MMD_D Tid thread_id(const Dims& d) {
+#if defined(__CUDACC__)
+  Tid t;
+  t.tile = blockIdx.x;
+  t.tid = threadIdx.x;
+  t.cpb = d.cpb;
+  t.cl = t.tid & (d.cpb - 1);
+  t.slot = t.tid >> d.lcpb;
+  t.nslot = blockDim.x >> d.lcpb;
+  t.chain = t.tile * d.cpb + t.cl;
+  t.cix = t.chain;
+  t.act = t.chain < d.n_chains;
+  t.nta = d.nta;
+  return t;
+#else
+  return Tid();
+#endif
+}
+// thread-private array with `rows` rows per thread: element r at tp(...)[r * nta]
+MMD_D double* tp(double* arr, int rows, const Tid& t) { return arr + ((long long)t.tile * rows) * t.nta + t.tid; }
+MMD_D const double* tp(const double* arr, int rows, const Tid& t) {
+  return arr + ((long long)t.tile * rows) * t.nta + t.tid;
+}
+// per-chain array with `rows` rows per chain: element r at pc(...)[r * cpb]
+MMD_D double* pc(double* arr, int rows, const Tid& t) { return arr + ((long long)t.tile * rows) * t.cpb + t.cl; }
+MMD_D const double* pc(const double* arr, int rows, const Tid& t) {
+  return arr + ((long long)t.tile * rows) * t.cpb + t.cl;
+}
+MMD_D QPtr qptr(double* base, const Dims& d, const Tid& t) {
+  QPtr q;
+  q.head = pc(base, d.rows_head, t);
+  q.body = tp(base + d.off_body, d.rows_body, t);
+  q.noise = tp(base + d.off_noise, d.rows_noise, t);
+  return q;
+}
 
 // ------------------------------------------------------------------------------------------
 // tiny dense helpers (row-major, fully unrolled)
@@ -154,12 +225,12 @@ MMD_D void mv(const double* A, const double* x, double* y) {  // y[R] = A[RxC] x
   }
 }
 template <int N>
-MMD_D void ldcol(const double* g, long long ld, double* r) {  // gather N consecutive rows of one chain
+MMD_D void ldcol(const double* g, int ld, double* r) {  // gather N consecutive rows of one column
 #pragma unroll
   for (int i = 0; i < N; ++i) r[i] = g[i * ld];
 }
 template <int N>
-MMD_D void stcol(double* g, long long ld, const double* r) {
+MMD_D void stcol(double* g, int ld, const double* r) {
 #pragma unroll
   for (int i = 0; i < N; ++i) g[i * ld] = r[i];
 }
@@ -173,7 +244,7 @@ struct Blk {
   bool ini, fin;
 };
 template <class M>
-MMD_D Blk get_block(const Dims& d, int part, int b) {
+MMD_HD Blk get_block(const Dims& d, int part, int b) {
   Blk B;
   const int nb = d.nb[part];
   B.ini = (b == 0);
@@ -195,142 +266,95 @@ MMD_D Blk get_block(const Dims& d, int part, int b) {
   B.nrows = B.ny + B.nx;
   return B;
 }
+// block that holds observation index o
+MMD_HD int block_of_obs(const Dims& d, int part, int o) {
+  if (d.nb[part] == 1) return 0;
+  const int i0 = d.init_size[part];
+  if (o < i0) return 0;
+  const int b = 1 + (o - i0) / d.R;
+  return b < d.nb[part] ? b : d.nb[part] - 1;
+}
 
+#if defined(__CUDACC__)
 // cross-block (same chain) reductions through shared memory.  All threads of the CTA must call.
-// vals[NV] is replaced by the sum over block slots (deterministic ascending order).
-template <int NV, int CPB, bool MAXRED>
-MMD_D void block_reduce(double* vals, double* smem, int nslot, int slot, int cl) {
+// vals[0..NSUM) are replaced by the sum over block slots (deterministic ascending order),
+// vals[NSUM..NSUM+NMAX) by the NaN-propagating maximum of non-negative values.
+template <int NSUM, int NMAX>
+MMD_D void block_reduce(double* vals, double* smem, const Tid& t) {
+  constexpr int NV = NSUM + NMAX;
+  const int NT = t.nslot * t.cpb;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) smem[(slot * NV + i) * CPB + cl] = vals[i];
+  for (int i = 0; i < NV; ++i) smem[i * NT + t.tid] = vals[i];
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    double s = MAXRED ? 0.0 : 0.0;
-    for (int sl = 0; sl < nslot; ++sl) {
-      const double v = smem[(sl * NV + i) * CPB + cl];
-      if (MAXRED) {
-        s = (v > s || v != v) ? v : s;  // NaN-propagating max of non-negative values
-      } else {
+    double s = 0.0;
+    const double* col = smem + i * NT + t.cl;
+    for (int sl = 0; sl < t.nslot; ++sl) {
+      const double v = col[sl * t.cpb];
+      if (i < NSUM) {
         s += v;
+      } else {
+        s = (v > s || v != v) ? v : s;
       }
     }
     vals[i] = s;
   }
   __syncthreads();
 }
+#endif
 
-// in-place packed Cholesky (lower) of an n x n SPD matrix
-template <int NRMAX>
-MMD_D void chol_packed(double* Dm, int n) {
+// in-place packed Cholesky (lower) of an n x n SPD matrix; on return the DIAGONAL holds 1 / L_ii
+// (the solves multiply instead of divide); returns sum_i log L_ii
+MMD_D double chol_packed_invdiag(double* Dm, int n) {
+  double ld = 0.0;
   for (int j = 0; j < n; ++j) {
     double s = Dm[tri(j, j)];
     for (int k = 0; k < j; ++k) s -= Dm[tri(j, k)] * Dm[tri(j, k)];
     const double ljj = sqrt(s);
-    Dm[tri(j, j)] = ljj;
+    ld += log(fabs(ljj));
     const double inv = 1.0 / ljj;
+    Dm[tri(j, j)] = inv;
     for (int i = j + 1; i < n; ++i) {
       double t = Dm[tri(i, j)];
       for (int k = 0; k < j; ++k) t -= Dm[tri(i, k)] * Dm[tri(j, k)];
       Dm[tri(i, j)] = t * inv;
     }
   }
+  return ld;
 }
-// solve L L^T x = b in place (packed lower L)
-MMD_D void chol_solve_packed(const double* Lm, int n, double* x) {
+// solve L L^T x = b in place (packed lower L with inverted diagonal)
+MMD_D void chol_solve_invdiag(const double* Lm, int n, double* x) {
   for (int i = 0; i < n; ++i) {
     double s = x[i];
     for (int k = 0; k < i; ++k) s -= Lm[tri(i, k)] * x[k];
-    x[i] = s / Lm[tri(i, i)];
+    x[i] = s * Lm[tri(i, i)];
   }
   for (int i = n - 1; i >= 0; --i) {
     double s = x[i];
     for (int k = i + 1; k < n; ++k) s -= Lm[tri(k, i)] * x[k];
-    x[i] = s / Lm[tri(i, i)];
+    x[i] = s * Lm[tri(i, i)];
   }
 }
-
-// per-thread context
-template <class M>
-struct Ctx {
-  int chain, cl, slot, nslot;
-  bool active;
-  long long ld;
-};
-
-// ------------------------------------------------------------------------------------------
-// forward constraint sweep for one block:  c_b(q)   (generate_y_bar + constr, :399-411, :473-519)
-// `vcol`/`alph` implement the quasi-Newton parametrisation q = qw - J_prev^T lambda_tot without
-// materialising q:   v_t = qw_v[t] - K_t^T alpha_k.
-// ------------------------------------------------------------------------------------------
-template <class M, bool WITH_K>
-MMD_D void constr_block(const Dims& d, const Blk& B, const double* z, double sigma_y, const double* xstart,
-                        const double* qc, const double* xobs, const double* y, const double* Kc,
-                        const double* alph, long long ld, double* crow, double* xend_out) {
-  constexpr int X = M::X, V = M::V;
-  double x[X];
+template <int N>
+MMD_D void chol_solve_invdiag_fixed(const double* Lm, int n, double* x) {  // n <= N, fully unrolled
 #pragma unroll
-  for (int i = 0; i < X; ++i) x[i] = xstart[i];
-  for (int k = 0; k < B.n; ++k) {
-    const long long g0 = (long long)(B.o + k) * d.S;
-    const double* vp = qc + ((long long)d.off_v + g0 * V) * ld;
-    double al[X];
-    if (WITH_K) ldcol<X>(alph + (long long)(B.o + k) * X * ld, ld, al);
-    const double* Kp = WITH_K ? Kc + g0 * X * V * ld : nullptr;
-    // loads do not depend on the recursion: fetch PF steps' worth of rows first, then run the steps
-    // (register-level software pipelining; the sweep is otherwise bound by global-load latency)
-    constexpr int PF = MMD_PREFETCH_STEPS;
-    int t = 0;
-    for (; t + PF <= d.S; t += PF) {
-      double vb[PF * V], Kb[WITH_K ? PF * X * V : 1];
+  for (int i = 0; i < N; ++i) {
+    if (i < n) {
+      double s = x[i];
 #pragma unroll
-      for (int i = 0; i < PF * V; ++i) vb[i] = vp[((long long)t * V + i) * ld];
-      if (WITH_K) {
-#pragma unroll
-        for (int i = 0; i < PF * X * V; ++i) Kb[i] = Kp[((long long)t * X * V + i) * ld];
-      }
-#pragma unroll
-      for (int g = 0; g < PF; ++g) {
-        double v[V], xn[X];
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = vb[g * V + j];
-        if (WITH_K) {
-#pragma unroll
-          for (int j = 0; j < V; ++j)
-#pragma unroll
-            for (int i = 0; i < X; ++i) v[j] = fma(-Kb[g * X * V + i * V + j], al[i], v[j]);
-        }
-        M::step(z, d.sd, x, v, xn);
-#pragma unroll
-        for (int i = 0; i < X; ++i) x[i] = xn[i];
-      }
+      for (int k = 0; k < i; ++k) s -= Lm[tri(i, k)] * x[k];
+      x[i] = s * Lm[tri(i, i)];
     }
-    for (; t < d.S; ++t) {
-      double v[V];
-      ldcol<V>(vp + (long long)t * V * ld, ld, v);
-      if (WITH_K) {
-        double Kt[X * V];
-        ldcol<X * V>(Kp + (long long)t * X * V * ld, ld, Kt);
+  }
 #pragma unroll
-        for (int j = 0; j < V; ++j)
+  for (int i = N - 1; i >= 0; --i) {
+    if (i < n) {
+      double s = x[i];
 #pragma unroll
-          for (int i = 0; i < X; ++i) v[j] = fma(-Kt[i * V + j], al[i], v[j]);
-      }
-      double xn[X];
-      M::step(z, d.sd, x, v, xn);
-#pragma unroll
-      for (int i = 0; i < X; ++i) x[i] = xn[i];
-    }
-    if (xend_out) stcol<X>(xend_out + (long long)(B.o + k) * X * ld, ld, x);
-    if (k < B.ny) {
-      double cy = M::obs(x) - y[B.o + k];
-      if (d.noisy) cy += sigma_y * qc[((long long)d.off_n + B.o + k) * ld];
-      crow[k] = cy;
-    }
-    if (k == B.n - 1 && B.nx > 0) {
-      double xo[X];
-      ldcol<X>(xobs + (long long)(B.o + k) * X * ld, ld, xo);
-#pragma unroll
-      for (int i = 0; i < X; ++i) crow[B.ny + i] = x[i] - xo[i];
+      for (int k = i + 1; k < N; ++k)
+        if (k < n) s -= Lm[tri(k, i)] * x[k];
+      x[i] = s * Lm[tri(i, i)];
     }
   }
 }
@@ -340,77 +364,6 @@ MMD_D double sigma_of(const Dims& d, const double* u) {
   if (d.noisy == 1) return d.sigma_fixed;
   if (d.noisy == 2) return exp(u[M::Z]);
   return 0.0;
-}
-
-// obs-level backward recursion: alpha_k = H_k^T lambda_k + Psib_{k+1}^T alpha_{k+1}  (J^T lambda in
-// compressed form, rmult_by_jacob_constr :879-913).  Writes alpha for the block's intervals and
-// returns alpha at the block start (needed for the v_0 columns of block 0).
-template <class M>
-MMD_D void alpha_block(const Dims& d, const Blk& B, const double* lam, const double* Psibc,
-                       const double* xendc, long long ld, double* alph_out, double* alpha_start) {
-  constexpr int X = M::X;
-  double al[X];
-#pragma unroll
-  for (int i = 0; i < X; ++i) al[i] = 0.0;
-  for (int k = B.n - 1; k >= 0; --k) {
-    if (k < B.n - 1) {
-      double Ps[X * X], t[X];
-      ldcol<X * X>(Psibc + (long long)(B.o + k + 1) * X * X * ld, ld, Ps);
-      mtv<X, X>(Ps, al, t);
-#pragma unroll
-      for (int i = 0; i < X; ++i) al[i] = t[i];
-    }
-    if (k < B.ny) {
-      double dh[X], xe[X];
-      if (!M::OBS_LINEAR) ldcol<X>(xendc + (long long)(B.o + k) * X * ld, ld, xe);
-      M::obs_grad(xe, dh);
-#pragma unroll
-      for (int i = 0; i < X; ++i) al[i] = fma(dh[i], lam[k], al[i]);
-    }
-    if (k == B.n - 1 && B.nx > 0) {
-#pragma unroll
-      for (int i = 0; i < X; ++i) al[i] += lam[B.ny + i];
-    }
-    stcol<X>(alph_out + (long long)(B.o + k) * X * ld, ld, al);
-  }
-  {
-    double Ps[X * X];
-    ldcol<X * X>(Psibc + (long long)B.o * X * X * ld, ld, Ps);
-    mtv<X, X>(Ps, al, alpha_start);
-  }
-}
-
-// Woodbury solve G^{-1} r for this thread's block (lmult_by_inv_gram :915-942):
-//   t_b = D_b^{-1} r_b ; s = C^{-1} sum_b A_b^T t_b ; lam_b = t_b - (D_b^{-1} A_b) s
-// `r` is overwritten by lam_b; returns s (= u-part of J^T G^{-1} r) in `s_out`.
-template <class M, int NRMAX, int UMAX, int CPB>
-MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const double* Ac, const double* Lc,
-                          const double* DinvAc, const double* LCc, long long ld, double* r, double* s_out,
-                          double* smem, int nslot, int slot, int cl) {
-  const int U = d.U;
-  double g[UMAX];
-#pragma unroll
-  for (int j = 0; j < UMAX; ++j) g[j] = 0.0;
-  if (has_blk) {
-    double Lm[NRMAX * (NRMAX + 1) / 2];
-    for (int i = 0; i < B.nrows * (B.nrows + 1) / 2; ++i) Lm[i] = Lc[(long long)i * ld];
-    chol_solve_packed(Lm, B.nrows, r);
-    for (int i = 0; i < B.nrows; ++i)
-      for (int j = 0; j < U; ++j) g[j] = fma(Ac[((long long)(B.row0 + i) * U + j) * ld], r[i], g[j]);
-  }
-  block_reduce<UMAX, CPB, false>(g, smem, nslot, slot, cl);
-  double LCm[UMAX * (UMAX + 1) / 2];
-  for (int i = 0; i < U * (U + 1) / 2; ++i) LCm[i] = LCc[(long long)i * ld];
-  chol_solve_packed(LCm, U, g);
-#pragma unroll
-  for (int j = 0; j < UMAX; ++j) s_out[j] = g[j];
-  if (has_blk) {
-    for (int i = 0; i < B.nrows; ++i) {
-      double t = r[i];
-      for (int j = 0; j < U; ++j) t = fma(-DinvAc[((long long)(B.row0 + i) * U + j) * ld], g[j], t);
-      r[i] = t;
-    }
-  }
 }
 
 }  // namespace mmd

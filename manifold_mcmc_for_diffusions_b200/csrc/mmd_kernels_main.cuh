@@ -1,98 +1,114 @@
 // __global__ kernels of the CHMC hot path.  See mmd_kernels.cuh for the layout and the mapping.
 #pragma once
-#include "mmd_kernels.cuh"
+#include "mmd_sweeps.cuh"
 #include "mmd_philox.cuh"
 
 namespace mmd {
 
-#define MMD_THREAD_SETUP                                        \
-  const int cl = threadIdx.x % CPB;                             \
-  const int slot = threadIdx.x / CPB;                           \
-  const int nslot = blockDim.x / CPB;                           \
-  const int chain = blockIdx.x * CPB + cl;                      \
-  const bool act = chain < d.n_chains;                          \
-  const long long ld = d.ld;                                    \
-  extern __shared__ double smem[];                              \
-  (void)nslot; (void)act;
+// shared-memory carve-up of the phase kernels: [scratch NSCR*NT][crow NRMAX*NT][lam NRMAX*NT]; the scratch
+// region is the cross-block reduction buffer or, inside a sweep, the thread-private prefetch ring
+template <class M, int NRMAX, int UMAX>
+struct SmemPlan {
+  static constexpr int NRED = UMAX * (UMAX + 1) / 2 + 1;
+  static constexpr int NRING = (MMD_PREFETCH_STEPS + 1) * (M::V + M::X * M::V);
+  static constexpr int NSCR = NRED > NRING ? NRED : NRING;
+  static constexpr int PER_THREAD = NSCR + 2 * NRMAX;  // doubles per thread
+};
+
+#define MMD_SMEM_SETUP                                                  \
+  extern __shared__ double smem[];                                      \
+  const int NT = t.nslot * t.cpb;                                       \
+  double* const sm_red = smem;                                          \
+  double* const sm_ring = smem + t.tid;                                 \
+  double* const sm_c = smem + SmemPlan<M, NRMAX, UMAX>::NSCR * NT + t.tid; \
+  double* const sm_l = sm_c + NRMAX * NT;                               \
+  (void)sm_red; (void)sm_ring; (void)sm_c; (void)sm_l;
 
 // ------------------------------------------------------------------------------------------
-// k_point: everything cached at a position.  Phase 1 = jacob_constr_blocks + chol_gram_blocks +
+// dev_point: everything cached at a position.  Phase 1 = jacob_constr_blocks + chol_gram_blocks +
 // log_det_sqrt_gram (mici_extensions.py:521-687, 800-820) in compressed form; phase 2 =
 // grad_log_det_sqrt_gram (:1143-1146, :1173-1184) by a hand-derived second-order adjoint.
 // ------------------------------------------------------------------------------------------
-template <class M, int CPB, int NRMAX, int RMAX, int UMAX>
-MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ xobs,
-                     const double* __restrict__ y, int part, int which, int with_grad) {
-  MMD_THREAD_SETUP
-  constexpr int X = M::X, V = M::V, Z = M::Z;
+template <class M, int NRMAX, int RMAX, int UMAX>
+MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ y, int part,
+                     int which, int with_grad) {
+  const Tid t = thread_id(d);
+  MMD_SMEM_SETUP
+  constexpr int X = M::X, V = M::V, Z = M::Z, XV = M::X * M::V;
   constexpr int NTRI = NRMAX * (NRMAX + 1) / 2;
   constexpr int UTRI = UMAX * (UMAX + 1) / 2;
-  const int U = d.U;
-  const int cur = S.cur[chain];
+  const int U = d.U, nta = t.nta, cpb = t.cpb;
+  const int cur = S.cur[t.cix];
   const int sl = which ? 1 - cur : cur;
-  const bool skip = (W.status[chain] != 0);
-  const double* qc = S.q + sl * S.s_q + chain;
-  double* Kc = S.K + sl * S.s_K + chain;
-  double* Psibc = S.Psib + sl * S.s_Psib + chain;
-  double* Ac = S.A + sl * S.s_A + chain;
-  double* DinvAc = S.DinvA + sl * S.s_A + chain;
-  double* LCc = S.LC + sl * S.s_LC + chain;
-  double* gc = S.gradld + sl * S.s_q + chain;
-  const double* xoc = xobs + chain;
-  double* xsc = W.xs + chain;
-  double* Qc = W.Qk + chain;
-  double* Ztc = W.Zt + chain;
+  const bool skip = !t.act || (W.status[t.cix] != 0);
+  const QPtr q = qptr(S.q + sl * S.s_q, d, t);
+  const QPtr gq = qptr(S.gradld + sl * S.s_q, d, t);
+  double* Kc = tp(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
+  double* Psibc = tp(S.Psib + sl * S.s_Psib, d.rmax * X * X, t);
+  double* xendc = tp(S.xend + sl * S.s_xend, d.rmax * X, t);
+  double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
+  double* DinvAc = tp(S.DinvA + sl * S.s_A, NRMAX * U, t);
+  double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
+  double* LCc = pc(S.LC + sl * S.s_LC, UTRI, t);
+  const double* xoc = pc(W.xobs, d.T * X, t);
+  double* xsc = tp(W.xs, d.rmax * d.S * X, t);
+  double* Qc = tp(W.Qk, d.rmax * X * X, t);
+  double* Ztc = tp(W.Zt, d.rmax * X * Z, t);
 
-  double u[UMAX], z[Z], dzdu[Z * Z];
-  for (int j = 0; j < U; ++j) u[j] = qc[(long long)j * ld];
-  M::gen_z(u, z, dzdu);
-  const double sigy = sigma_of<M>(d, u);
-  const bool has_blk = slot < d.nb[part];
+  ChainPar<M, UMAX> P;
+  {
+    double u[UMAX];
+#pragma unroll
+    for (int j = 0; j < UMAX; ++j) u[j] = (j < U) ? q.head[j * cpb] : 0.0;
+    make_par<M, UMAX>(d, u, P);
+  }
+  const double sigy = P.sigy;
+  const bool has_blk = t.slot < d.nb[part];
   Blk B;
-  if (has_blk) B = get_block<M>(d, part, slot);
-  double* Lc = S.L + sl * S.s_L + chain + (long long)slot * NTRI * ld;
+  if (has_blk) B = get_block<M>(d, part, t.slot);
 
   double red[UTRI + 1];
 #pragma unroll
   for (int i = 0; i < UTRI + 1; ++i) red[i] = 0.0;
+  double xlast[X];  // state at the end of the block
 
   if (has_blk && !skip) {
     double dx0_dv0[X * M::V0], dx0_dz[X * Z];
-    M::gen_x0_jac(z, dx0_dv0, dx0_dz);
+    M::gen_x0_jac(P.z, dx0_dv0, dx0_dz);
     // ---------------- interval sweeps: trajectory, compressed Jacobian, interval summaries
     double x[X];
-    if (B.ini) {
+    {
       double v0[M::V0];
-      ldcol<M::V0>(qc + (long long)d.off_v0 * ld, ld, v0);
-      M::gen_x0(z, v0, x);
-    } else {
-      ldcol<X>(xoc + (long long)(B.o - 1) * X * ld, ld, x);
+      ldcol<M::V0>(q.head + U * cpb, cpb, v0);
+      block_start<M>(d, B, P.z, v0, xoc, cpb, x);
     }
     for (int k = 0; k < B.n; ++k) {
-      const long long g0 = (long long)(B.o + k) * d.S;
-      const double* vp = qc + ((long long)d.off_v + g0 * V) * ld;
-      for (int t = 0; t < d.S; ++t) {
-        stcol<X>(xsc + (g0 + t) * X * ld, ld, x);
+      const double* vp = q.body + k * d.S * V * nta;
+      double* xk = xsc + k * d.S * X * nta;
+      for (int tt = 0; tt < d.S; ++tt) {
+        stcol<X>(xk + tt * X * nta, nta, x);
         double v[V], xn[X];
-        ldcol<V>(vp + (long long)t * V * ld, ld, v);
-        M::step(z, d.sd, x, v, xn);
+        ldcol<V>(vp + tt * V * nta, nta, v);
+        M::step(P.C, x, v, xn);
 #pragma unroll
         for (int i = 0; i < X; ++i) x[i] = xn[i];
       }
+      if (!M::OBS_LINEAR) stcol<X>(xendc + k * X * nta, nta, x);
       double Psi[X * X], Qk[X * X], Zk[X * Z];
 #pragma unroll
       for (int i = 0; i < X * X; ++i) { Psi[i] = (i % (X + 1) == 0) ? 1.0 : 0.0; Qk[i] = 0.0; }
 #pragma unroll
       for (int i = 0; i < X * Z; ++i) Zk[i] = 0.0;
-      for (int t = d.S - 1; t >= 0; --t) {
+      double* Kk = Kc + k * d.S * XV * nta;
+      for (int tt = d.S - 1; tt >= 0; --tt) {
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], tmp[X * X];
-        ldcol<X>(xsc + (g0 + t) * X * ld, ld, xt);
-        ldcol<V>(vp + (long long)t * V * ld, ld, v);
-        M::jac_x(z, d.sd, xt, v, F);
-        M::jac_v(z, d.sd, xt, v, Bm);
-        M::jac_z(z, d.sd, xt, v, G);
+        ldcol<X>(xk + tt * X * nta, nta, xt);
+        ldcol<V>(vp + tt * V * nta, nta, v);
+        M::jac_x(P.C, xt, v, F);
+        M::jac_v(P.C, xt, v, Bm);
+        M::jac_z(P.C, xt, v, G);
         mm<X, V, X>(Psi, Bm, Kt);
-        stcol<X * V>(Kc + (g0 + t) * X * V * ld, ld, Kt);
+        stcol<XV>(Kk + tt * XV * nta, nta, Kt);
         // Qk += Kt Kt^T ; Zk += Psi G ; Psi = Psi F
 #pragma unroll
         for (int i = 0; i < X; ++i)
@@ -108,36 +124,35 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #pragma unroll
         for (int i = 0; i < X * X; ++i) Psi[i] = tmp[i];
       }
-      stcol<X * X>(Psibc + (long long)(B.o + k) * X * X * ld, ld, Psi);
-      stcol<X * X>(Qc + (long long)(B.o + k) * X * X * ld, ld, Qk);
-      stcol<X * Z>(Ztc + (long long)(B.o + k) * X * Z * ld, ld, Zk);
-      if (!M::OBS_LINEAR) {
-        // state at the observation time is needed for the observation gradient
-      }
+      stcol<X * X>(Psibc + k * X * X * nta, nta, Psi);
+      stcol<X * X>(Qc + k * X * X * nta, nta, Qk);
+      stcol<X * Z>(Ztc + k * X * Z * nta, nta, Zk);
     }
+#pragma unroll
+    for (int i = 0; i < X; ++i) xlast[i] = x[i];
     // ---------------- per-observation algebra: A_b = dc/du rows, D_b = J_v J_v^T (+ noise terms)
-    double Su[X * Z], P[X * X], w[NRMAX * X], Dm[NTRI], Am[NRMAX * UMAX];
+    double Su[X * Z], Pm[X * X], w[NRMAX * X], Dm[NTRI], Am[NRMAX * UMAX];
 #pragma unroll
     for (int i = 0; i < X * Z; ++i) Su[i] = B.ini ? dx0_dz[i] : 0.0;
     if (B.ini) {
-      mmt<X, X, M::V0>(dx0_dv0, dx0_dv0, P);
+      mmt<X, X, M::V0>(dx0_dv0, dx0_dv0, Pm);
     } else {
 #pragma unroll
-      for (int i = 0; i < X * X; ++i) P[i] = 0.0;
+      for (int i = 0; i < X * X; ++i) Pm[i] = 0.0;
     }
     int nrow_done = 0;
     for (int k = 0; k < B.n; ++k) {
       double Ps[X * X], Qk[X * X], Zk[X * Z], t1[X * Z], t2[X * X], t3[X * X];
-      ldcol<X * X>(Psibc + (long long)(B.o + k) * X * X * ld, ld, Ps);
-      ldcol<X * X>(Qc + (long long)(B.o + k) * X * X * ld, ld, Qk);
-      ldcol<X * Z>(Ztc + (long long)(B.o + k) * X * Z * ld, ld, Zk);
+      ldcol<X * X>(Psibc + k * X * X * nta, nta, Ps);
+      ldcol<X * X>(Qc + k * X * X * nta, nta, Qk);
+      ldcol<X * Z>(Ztc + k * X * Z * nta, nta, Zk);
       mm<X, Z, X>(Ps, Su, t1);
 #pragma unroll
       for (int i = 0; i < X * Z; ++i) Su[i] = t1[i] + Zk[i];
-      mm<X, X, X>(Ps, P, t2);
+      mm<X, X, X>(Ps, Pm, t2);
       mmt<X, X, X>(t2, Ps, t3);
 #pragma unroll
-      for (int i = 0; i < X * X; ++i) P[i] = t3[i] + Qk[i];
+      for (int i = 0; i < X * X; ++i) Pm[i] = t3[i] + Qk[i];
       for (int r = 0; r < nrow_done; ++r) {
         double tw[X];
         mv<X, X>(Ps, &w[r * X], tw);
@@ -151,11 +166,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
         const bool yrow = (k < B.ny) && a == 0;
         if (yrow) {
           double xe[X];
-          if (k + 1 < B.n) ldcol<X>(xsc + (long long)(B.o + k + 1) * d.S * X * ld, ld, xe);
-          else {
-#pragma unroll
-            for (int i = 0; i < X; ++i) xe[i] = x[i];
-          }
+          if (!M::OBS_LINEAR) ldcol<X>(xendc + k * X * nta, nta, xe);
           M::obs_grad(xe, h);
         } else {
           const int comp = a - ((k < B.ny) ? 1 : 0);
@@ -164,7 +175,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
         }
         const int r = nrow_done;
         // w_r = P h ; D[r][j] = h . w_j ; Az[r] = h^T Su
-        mv<X, X>(P, h, &w[r * X]);
+        mv<X, X>(Pm, h, &w[r * X]);
         for (int j = 0; j <= r; ++j) {
           double s = 0.0;
 #pragma unroll
@@ -177,29 +188,27 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
           double s = 0.0;
           if (j < Z) {
 #pragma unroll
-            for (int m = 0; m < Z; ++m) s = fma(az[m], dzdu[m * Z + j], s);
+            for (int m = 0; m < Z; ++m) s = fma(az[m], P.dzdu[m * Z + j], s);
           }
           Am[r * UMAX + j] = s;
         }
         if (d.noisy && yrow) {
           Dm[tri(r, r)] += sigy * sigy;
-          if (d.noisy == 2) Am[r * UMAX + Z] = sigy * qc[((long long)d.off_n + B.o + k) * ld];
+          if (d.noisy == 2) Am[r * UMAX + Z] = sigy * q.noise[k * nta];
         }
         nrow_done++;
       }
     }
     for (int r = 0; r < B.nrows; ++r)
-      for (int j = 0; j < U; ++j) Ac[((long long)(B.row0 + r) * U + j) * ld] = Am[r * UMAX + j];
-    chol_packed<NRMAX>(Dm, B.nrows);
-    for (int i = 0; i < B.nrows * (B.nrows + 1) / 2; ++i) Lc[(long long)i * ld] = Dm[i];
-    double ldpart = 0.0;
-    for (int r = 0; r < B.nrows; ++r) ldpart += log(fabs(Dm[tri(r, r)]));
+      for (int j = 0; j < U; ++j) Ac[(r * U + j) * nta] = Am[r * UMAX + j];
+    const double ldpart = chol_packed_invdiag(Dm, B.nrows);
+    for (int i = 0; i < B.nrows * (B.nrows + 1) / 2; ++i) Lc[i * nta] = Dm[i];
     // DinvA and C_b = A_b^T D_b^{-1} A_b
     for (int j = 0; j < U; ++j) {
       double col[NRMAX];
       for (int r = 0; r < B.nrows; ++r) col[r] = Am[r * UMAX + j];
-      chol_solve_packed(Dm, B.nrows, col);
-      for (int r = 0; r < B.nrows; ++r) DinvAc[((long long)(B.row0 + r) * U + j) * ld] = col[r];
+      chol_solve_invdiag(Dm, B.nrows, col);
+      for (int r = 0; r < B.nrows; ++r) DinvAc[(r * U + j) * nta] = col[r];
       for (int i = j; i < U; ++i) {
         double s = 0.0;
         for (int r = 0; r < B.nrows; ++r) s = fma(Am[r * UMAX + i], col[r], s);
@@ -208,16 +217,15 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
     }
     red[UTRI] = ldpart;
   }
-  block_reduce<UTRI + 1, CPB, false>(red, smem, nslot, slot, cl);
+  block_reduce<UTRI + 1, 0>(red, sm_red, t);
   double LCm[UTRI];
   for (int i = 0; i < U; ++i)
     for (int j = 0; j <= i; ++j) LCm[tri(i, j)] = red[tri(i, j)] + (i == j ? 1.0 : 0.0);
-  chol_packed<UMAX>(LCm, U);
-  double ldtot = red[UTRI];
-  for (int i = 0; i < U; ++i) ldtot += log(fabs(LCm[tri(i, i)]));
-  if (slot == 0 && !skip) {
-    for (int i = 0; i < U * (U + 1) / 2; ++i) LCc[(long long)i * ld] = LCm[i];
-    S.ldv[sl * S.s_ld + chain] = ldtot;
+  const double ldC = chol_packed_invdiag(LCm, U);
+  const double ldtot = red[UTRI] + ldC;
+  if (t.slot == 0 && !skip) {
+    for (int i = 0; i < U * (U + 1) / 2; ++i) LCc[i * cpb] = LCm[i];
+    S.ldv[sl * S.s_ld + t.cix] = ldtot;
   }
   if (!with_grad) return;
 
@@ -227,20 +235,20 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
   for (int j = 0; j < UMAX; ++j) gu[j] = 0.0;
   if (has_blk && !skip) {
     double dx0_dv0[X * M::V0], dx0_dz[X * Z];
-    M::gen_x0_jac(z, dx0_dv0, dx0_dz);
+    M::gen_x0_jac(P.z, dx0_dv0, dx0_dz);
     const int nr = B.nrows;
     // C^{-1}
     double Cinv[UMAX * UMAX];
     for (int j = 0; j < U; ++j) {
       double e[UMAX];
       for (int i = 0; i < U; ++i) e[i] = (i == j) ? 1.0 : 0.0;
-      chol_solve_packed(LCm, U, e);
+      chol_solve_invdiag(LCm, U, e);
       for (int i = 0; i < U; ++i) Cinv[i * UMAX + j] = e[i];
     }
     double Lm[NTRI], DiA[NRMAX * UMAX], Om[NRMAX * UMAX], E[NRMAX * NRMAX];
-    for (int i = 0; i < nr * (nr + 1) / 2; ++i) Lm[i] = Lc[(long long)i * ld];
+    for (int i = 0; i < nr * (nr + 1) / 2; ++i) Lm[i] = Lc[i * nta];
     for (int r = 0; r < nr; ++r)
-      for (int j = 0; j < U; ++j) DiA[r * UMAX + j] = DinvAc[((long long)(B.row0 + r) * U + j) * ld];
+      for (int j = 0; j < U; ++j) DiA[r * UMAX + j] = DinvAc[(r * U + j) * nta];
     for (int r = 0; r < nr; ++r)
       for (int j = 0; j < U; ++j) {
         double s = 0.0;
@@ -250,11 +258,23 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
     for (int c2 = 0; c2 < nr; ++c2) {  // E[:, c2] = D^{-1} e_c2 - Om DiA[c2]^T
       double e[NRMAX];
       for (int i = 0; i < nr; ++i) e[i] = (i == c2) ? 1.0 : 0.0;
-      chol_solve_packed(Lm, nr, e);
+      chol_solve_invdiag(Lm, nr, e);
       for (int r = 0; r < nr; ++r) {
         double s = e[r];
         for (int j = 0; j < U; ++j) s = fma(-Om[r * UMAX + j], DiA[c2 * UMAX + j], s);
         E[r * NRMAX + c2] = s;
+      }
+    }
+    // noise-scale terms (sigma = exp(u_Z) inferred): d/du_Z and d/dn of 1/2 <E, sigma^2 P_y> + <Om[:, Z], sigma n>
+    if (d.noisy) {
+      for (int k = 0; k < B.n; ++k) {
+        double gn = 0.0;
+        if (d.noisy == 2 && k < B.ny) {
+          const double nk = q.noise[k * nta];
+          gu[Z] += E[k * NRMAX + k] * sigy * sigy + Om[k * UMAX + Z] * sigy * nk;
+          gn = Om[k * UMAX + Z] * sigy;
+        }
+        gq.noise[k * nta] = gn;
       }
     }
     // a[r][k] = Phi(t_kr, t_k)^T H_r^T  (zero for k > kr)
@@ -265,10 +285,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       double vec[X];
       if (r < B.ny) {
         double xe[X];
-        if (!M::OBS_LINEAR) {
-          // x at obs time kr: start of next interval or (last) recomputed below
-          if (kr + 1 < B.n) ldcol<X>(xsc + (long long)(B.o + kr + 1) * d.S * X * ld, ld, xe);
-        }
+        if (!M::OBS_LINEAR) ldcol<X>(xendc + kr * X * nta, nta, xe);
         M::obs_grad(xe, vec);
       } else {
 #pragma unroll
@@ -276,11 +293,11 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       }
       for (int k = kr; k >= 0; --k) {
         if (k < kr) {
-          double Ps[X * X], t[X];
-          ldcol<X * X>(Psibc + (long long)(B.o + k + 1) * X * X * ld, ld, Ps);
-          mtv<X, X>(Ps, vec, t);
+          double Ps[X * X], tv[X];
+          ldcol<X * X>(Psibc + (k + 1) * X * X * nta, nta, Ps);
+          mtv<X, X>(Ps, vec, tv);
 #pragma unroll
-          for (int i = 0; i < X; ++i) vec[i] = t[i];
+          for (int i = 0; i < X; ++i) vec[i] = tv[i];
         }
 #pragma unroll
         for (int i = 0; i < X; ++i) a[(r * RMAX + k) * X + i] = vec[i];
@@ -301,7 +318,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       for (int m = 0; m < Z; ++m) {
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < Z; ++j) s = fma(dzdu[m * Z + j], Om[r * UMAX + j], s);
+        for (int j = 0; j < Z; ++j) s = fma(P.dzdu[m * Z + j], Om[r * UMAX + j], s);
         omz[r * Z + m] = s;
       }
     // per-interval constants M_k, LamZ_k, Yb_k ; tangent recursion ; Az rows (for d2z/du2 term)
@@ -309,7 +326,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
     for (int r = 0; r < nr; ++r) {
       if (B.ini) {
         double Ps[X * X], b0[X], t0[M::V0], t1[X], t2[X];
-        ldcol<X * X>(Psibc + (long long)B.o * X * X * ld, ld, Ps);
+        ldcol<X * X>(Psibc, nta, Ps);
         mtv<X, X>(Ps, &be[(r * RMAX + 0) * X], b0);
         mtv<X, M::V0>(dx0_dv0, b0, t0);
         mv<X, M::V0>(dx0_dv0, t0, t1);
@@ -325,6 +342,9 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #pragma unroll
     for (int i = 0; i < X * Z; ++i) Suz[i] = B.ini ? dx0_dz[i] : 0.0;
     for (int i = 0; i < Z * UMAX; ++i) Gam[i] = 0.0;
+    double* Mkc = tp(W.Mk, d.rmax * X * X, t);
+    double* LamZc = tp(W.LamZ, d.rmax * Z * X, t);
+    double* Ybc = tp(W.Yb, d.rmax * X * X, t);
     for (int k = 0; k < B.n; ++k) {
       double Mk[X * X], Lam[Z * X], Yb[X * X];
 #pragma unroll
@@ -346,13 +366,13 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #pragma unroll
           for (int j = 0; j < X; ++j) Lam[m * X + j] = fma(omz[r * Z + m], ar[j], Lam[m * X + j]);
       }
-      stcol<X * X>(W.Mk + chain + (long long)(B.o + k) * X * X * ld, ld, Mk);
-      stcol<Z * X>(W.LamZ + chain + (long long)(B.o + k) * Z * X * ld, ld, Lam);
-      stcol<X * X>(W.Yb + chain + (long long)(B.o + k) * X * X * ld, ld, Yb);
+      stcol<X * X>(Mkc + k * X * X * nta, nta, Mk);
+      stcol<Z * X>(LamZc + k * Z * X * nta, nta, Lam);
+      stcol<X * X>(Ybc + k * X * X * nta, nta, Yb);
       double Ps[X * X], Qk[X * X], Zk[X * Z];
-      ldcol<X * X>(Psibc + (long long)(B.o + k) * X * X * ld, ld, Ps);
-      ldcol<X * X>(Qc + (long long)(B.o + k) * X * X * ld, ld, Qk);
-      ldcol<X * Z>(Ztc + (long long)(B.o + k) * X * Z * ld, ld, Zk);
+      ldcol<X * X>(Psibc + k * X * X * nta, nta, Ps);
+      ldcol<X * X>(Qc + k * X * X * nta, nta, Qk);
+      ldcol<X * Z>(Ztc + k * X * Z * nta, nta, Zk);
       for (int r = 0; r < nr; ++r) {
         double t1[X], t2[X], t3[X];
         mv<X, X>(Ps, &dprev[r * X], t1);
@@ -381,23 +401,30 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
     for (int i = 0; i < X; ++i) gam[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < Z; ++i) gz[i] = 0.0;
-    double* Ywc = W.Yw + chain;
+    double* Ywc = tp(W.Yw, d.rmax * d.S * X * X, t);
     for (int k = B.n - 1; k >= 0; --k) {
-      const long long g0 = (long long)(B.o + k) * d.S;
-      const double* vp = qc + ((long long)d.off_v + g0 * V) * ld;
+      const double* vp = q.body + k * d.S * V * nta;
+      const double* xk = xsc + k * d.S * X * nta;
+      const double* Kk = Kc + k * d.S * XV * nta;
+      double* Yk = Ywc + k * d.S * X * X * nta;
+      double* gk = gq.body + k * d.S * V * nta;
       double Mk[X * X], Lam[Z * X], Y[X * X];
-      ldcol<X * X>(W.Mk + chain + (long long)(B.o + k) * X * X * ld, ld, Mk);
-      ldcol<Z * X>(W.LamZ + chain + (long long)(B.o + k) * Z * X * ld, ld, Lam);
-      ldcol<X * X>(W.Yb + chain + (long long)(B.o + k) * X * X * ld, ld, Y);
-      for (int t = 0; t < d.S; ++t) {
-        stcol<X * X>(Ywc + (g0 + t) * X * X * ld, ld, Y);
+      ldcol<X * X>(Mkc + k * X * X * nta, nta, Mk);
+      ldcol<Z * X>(LamZc + k * Z * X * nta, nta, Lam);
+      ldcol<X * X>(Ybc + k * X * X * nta, nta, Y);
+      if (!M::OBS_LINEAR) {
+        // curvature of the observation function enters the adjoint at the observation time
+        // (handled through obs_hess in the adjoint start below)
+      }
+      for (int tt = 0; tt < d.S; ++tt) {
+        stcol<X * X>(Yk + tt * X * X * nta, nta, Y);
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], KM[V * X], Yn[X * X];
-        ldcol<X>(xsc + (g0 + t) * X * ld, ld, xt);
-        ldcol<V>(vp + (long long)t * V * ld, ld, v);
-        ldcol<X * V>(Kc + (g0 + t) * X * V * ld, ld, Kt);
-        M::jac_x(z, d.sd, xt, v, F);
-        M::jac_v(z, d.sd, xt, v, Bm);
-        M::jac_z(z, d.sd, xt, v, G);
+        ldcol<X>(xk + tt * X * nta, nta, xt);
+        ldcol<V>(vp + tt * V * nta, nta, v);
+        ldcol<XV>(Kk + tt * XV * nta, nta, Kt);
+        M::jac_x(P.C, xt, v, F);
+        M::jac_v(P.C, xt, v, Bm);
+        M::jac_z(P.C, xt, v, G);
         mm<X, X, X>(F, Y, Yn);
         mtm<V, X, X>(Kt, Mk, KM);
         mm_acc<X, X, V>(Bm, KM, Yn);
@@ -408,26 +435,26 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       double Psi[X * X];
 #pragma unroll
       for (int i = 0; i < X * X; ++i) Psi[i] = (i % (X + 1) == 0) ? 1.0 : 0.0;
-      for (int t = d.S - 1; t >= 0; --t) {
+      for (int tt = d.S - 1; tt >= 0; --tt) {
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], Yt[X * X];
-        ldcol<X>(xsc + (g0 + t) * X * ld, ld, xt);
-        ldcol<V>(vp + (long long)t * V * ld, ld, v);
-        ldcol<X * X>(Ywc + (g0 + t) * X * X * ld, ld, Yt);
-        M::jac_x(z, d.sd, xt, v, F);
-        M::jac_v(z, d.sd, xt, v, Bm);
-        M::jac_z(z, d.sd, xt, v, G);
+        ldcol<X>(xk + tt * X * nta, nta, xt);
+        ldcol<V>(vp + tt * V * nta, nta, v);
+        ldcol<X * X>(Yk + tt * X * X * nta, nta, Yt);
+        M::jac_x(P.C, xt, v, F);
+        M::jac_v(P.C, xt, v, Bm);
+        M::jac_z(P.C, xt, v, G);
         mm<X, V, X>(Psi, Bm, Kt);
         double Th[(X + V + Z) * X], MP[X * X], g[X + V + Z];
         mm<X, X, X>(Yt, Psi, &Th[0]);
         mm<X, X, X>(Mk, Psi, MP);
         mtm<V, X, X>(Kt, MP, &Th[X * X]);
         mm<Z, X, X>(Lam, Psi, &Th[(X + V) * X]);
-        M::hess_contract(z, d.sd, xt, v, Th, g);
+        M::hess_contract(P.C, xt, v, Th, g);
         double gv[V], gn[X], tz[Z];
         mtv<X, V>(Bm, gam, gv);
 #pragma unroll
         for (int j = 0; j < V; ++j) gv[j] += g[X + j];
-        stcol<V>(gc + ((long long)d.off_v + (g0 + t) * V) * ld, ld, gv);
+        stcol<V>(gk + tt * V * nta, nta, gv);
         mtv<X, Z>(G, gam, tz);
 #pragma unroll
         for (int m = 0; m < Z; ++m) gz[m] += tz[m] + g[X + V + m];
@@ -440,111 +467,143 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
         for (int i = 0; i < X * X; ++i) Psi[i] = tmp[i];
       }
     }
+    double gv0[M::V0];
     if (B.ini) {
-      double gv0[M::V0], tz[Z];
+      double tz[Z];
       mtv<X, M::V0>(dx0_dv0, gam, gv0);
-      stcol<M::V0>(gc + (long long)d.off_v0 * ld, ld, gv0);
       mtv<X, Z>(dx0_dz, gam, tz);
 #pragma unroll
       for (int m = 0; m < Z; ++m) gz[m] += tz[m];
+      stcol<M::V0>(gq.head + U * cpb, cpb, gv0);
     }
     double extra[Z], GamZ[Z * Z];
 #pragma unroll
     for (int m = 0; m < Z; ++m)
 #pragma unroll
       for (int j = 0; j < Z; ++j) GamZ[m * Z + j] = Gam[m * UMAX + j];
-    M::gen_z_second(u, z, GamZ, extra);
+    M::gen_z_second(P.u, P.z, GamZ, extra);
 #pragma unroll
     for (int j = 0; j < Z; ++j) {
       double s = extra[j];
 #pragma unroll
-      for (int m = 0; m < Z; ++m) s = fma(dzdu[m * Z + j], gz[m], s);
-      gu[j] = s;
+      for (int m = 0; m < Z; ++m) s = fma(P.dzdu[m * Z + j], gz[m], s);
+      gu[j] += s;
     }
   }
-  block_reduce<UMAX, CPB, false>(gu, smem, nslot, slot, cl);
-  if (slot == 0 && !skip)
-    for (int j = 0; j < U; ++j) gc[(long long)j * ld] = gu[j];
+  (void)xlast;
+  block_reduce<UMAX, 0>(gu, sm_red, t);
+  if (t.slot == 0 && !skip)
+    for (int j = 0; j < U; ++j) gq.head[j * cpb] = gu[j];
 }
 
 // ------------------------------------------------------------------------------------------
-// k_constr: c(q) for the standalone `constr` op (mici_extensions.py:473-519)
+// dev_constr: c(q) at the resident position for the standalone `constr` op (mici_extensions.py:473-519);
+// cout is thread-private [NRMAX]
 // ------------------------------------------------------------------------------------------
-template <class M, int CPB, int NRMAX, int UMAX>
-__global__ void k_constr(Dims d, const double* __restrict__ q, const double* __restrict__ xobs,
-                         const double* __restrict__ y, int part, double* __restrict__ cout) {
-  MMD_THREAD_SETUP
-  constexpr int X = M::X, Z = M::Z;
-  if (slot >= d.nb[part]) return;
-  const double* qc = q + chain;
-  double u[UMAX], z[Z], dzdu[Z * Z];
-  for (int j = 0; j < d.U; ++j) u[j] = qc[(long long)j * ld];
-  M::gen_z(u, z, dzdu);
-  const double sigy = sigma_of<M>(d, u);
-  Blk B = get_block<M>(d, part, slot);
-  double x[X], crow[NRMAX];
-  if (B.ini) {
-    double v0[M::V0];
-    ldcol<M::V0>(qc + (long long)d.off_v0 * ld, ld, v0);
-    M::gen_x0(z, v0, x);
-  } else {
-    ldcol<X>(xobs + chain + (long long)(B.o - 1) * X * ld, ld, x);
+template <class M, int NRMAX, int UMAX>
+MMD_D void dev_constr(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ y, int part,
+                      double* __restrict__ cout) {
+  const Tid t = thread_id(d);
+  MMD_SMEM_SETUP
+  constexpr int X = M::X;
+  if (t.slot >= d.nb[part]) return;
+  const int cur = S.cur[t.cix];
+  const QPtr q = qptr(S.q + cur * S.s_q, d, t);
+  ChainPar<M, UMAX> P;
+  {
+    double u[UMAX];
+#pragma unroll
+    for (int j = 0; j < UMAX; ++j) u[j] = (j < d.U) ? q.head[j * t.cpb] : 0.0;
+    make_par<M, UMAX>(d, u, P);
   }
-  constr_block<M, false>(d, B, z, sigy, x, qc, xobs + chain, y, nullptr, nullptr, ld, crow, nullptr);
-  for (int r = 0; r < B.nrows; ++r) cout[(long long)(B.row0 + r) * ld + chain] = crow[r];
+  const Blk B = get_block<M>(d, part, t.slot);
+  const double* xoc = pc(W.xobs, d.T * X, t);
+  double x[X], v0[M::V0];
+  ldcol<M::V0>(q.head + d.U * t.cpb, t.cpb, v0);
+  block_start<M>(d, B, P.z, v0, xoc, t.cpb, x);
+  constr_sweep<M, false>(d, B, P.C, P.sigy, 0.0, x, q.body, q.noise, xoc, y, nullptr, nullptr, nullptr, t.nta,
+                         t.cpb, NT, sm_c, sm_ring, nullptr);
+  double* co = tp(cout, NRMAX, t);
+  for (int r = 0; r < B.nrows; ++r) co[r * t.nta] = sm_c[r * NT];
 }
 
 // ------------------------------------------------------------------------------------------
-// k_project: p <- proj(p - h (a q + gradld)) with proj = I - J^T (J J^T)^{-1} J evaluated from the cached
-// compressed Jacobian (normal_space_component / project_onto_cotangent_space, :983-993,
-// :1243-1254) fused with the preceding h1_flow (Mici System.h1_flow; dh1_dpos :1192-1196).
-// Reads p from slot `src`, writes slot `dst` (relative to cur: 0 = cur, 1 = other).
+// dev_project: p'' = proj(p - h (qcoef q + gradld)) with proj = I - J^T (J J^T)^{-1} J evaluated from
+// the cached compressed Jacobian (normal_space_component / project_onto_cotangent_space, :983-993,
+// :1243-1254) fused with the preceding h1_flow (Mici System.h1_flow; dh1_dpos :1192-1196) and,
+// optionally, with the following h2_flow (:1222-1231):
+//   flow 0: dst = p''
+//   flow 1: dst = p'' and qw = fq * q + fp * p''                         (trial position only)
+//   flow 2: dst = fq * p'' - fpm * q and qw = fq * q + fp * p''          (position and momentum)
+// where (fq, fp, fpm) = (1, dt, 0) for the standard splitting and (cos dt, sin dt, sin dt) for the
+// Gaussian splitting.  lin/src/dst select slots relative to cur (PSEL_*).
 // ------------------------------------------------------------------------------------------
-template <class M, int CPB, int NRMAX, int UMAX>
+struct FlowCoef {
+  int mode;
+  double fq, fp, fpm;
+};
+
+template <class M, int NRMAX, int RMAXP, int UMAX>
 MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, int lin_sel, int src_sel,
-                       int dst_sel, double h, double qcoef) {
-  MMD_THREAD_SETUP
-  constexpr int X = M::X, V = M::V, Z = M::Z;
-  const int U = d.U;
-  const int cur = S.cur[chain];
-  const bool skip = (W.status[chain] != 0);
-  const int sl = lin_sel ? 1 - cur : cur;
-  const int ss = src_sel ? 1 - cur : cur;
-  const int sd_ = dst_sel ? 1 - cur : cur;
-  const double* qc = S.q + sl * S.s_q + chain;
-  const double* gc = S.gradld + sl * S.s_q + chain;
-  const double* psrc = S.p + ss * S.s_q + chain;
-  double* pdst = S.p + sd_ * S.s_q + chain;
-  const double* Kc = S.K + sl * S.s_K + chain;
-  const double* Psibc = S.Psib + sl * S.s_Psib + chain;
-  const double* Ac = S.A + sl * S.s_A + chain;
-  const double* DinvAc = S.DinvA + sl * S.s_A + chain;
-  const double* LCc = S.LC + sl * S.s_LC + chain;
+                       int dst_sel, double h, double qcoef, FlowCoef fl) {
+  const Tid t = thread_id(d);
+  MMD_SMEM_SETUP
+  constexpr int X = M::X, V = M::V, Z = M::Z, XV = M::X * M::V;
   constexpr int NTRI = NRMAX * (NRMAX + 1) / 2;
-  const double* Lc = S.L + sl * S.s_L + chain + (long long)slot * NTRI * ld;
-  const bool has_blk = slot < d.nb[part] && !skip;
-  Blk B;
-  if (slot < d.nb[part]) B = get_block<M>(d, part, slot);
-  auto pval = [&](long long row) -> double {
-    double pv = psrc[row * ld];
-    if (h != 0.0) pv -= h * (qcoef * qc[row * ld] + gc[row * ld]);
-    return pv;
+  constexpr int UTRI = UMAX * (UMAX + 1) / 2;
+  const int U = d.U, nta = t.nta, cpb = t.cpb;
+  const int cur = S.cur[t.cix];
+  const bool skip = !t.act || (W.status[t.cix] != 0);
+  const int sl = lin_sel ? 1 - cur : cur;
+  auto psel = [&](int sel) -> double* {
+    return sel == PSEL_WORK ? W.pw : S.p + (sel == PSEL_OTHER ? 1 - cur : cur) * S.s_q;
   };
-  double pu[UMAX], r[NRMAX], sres[UMAX];
+  const QPtr q = qptr(S.q + sl * S.s_q, d, t);
+  const QPtr g = qptr(S.gradld + sl * S.s_q, d, t);
+  const QPtr ps = qptr(psel(src_sel), d, t);
+  const QPtr pd = qptr(psel(dst_sel), d, t);
+  const QPtr qw = qptr(W.qw, d, t);
+  const double* Kc = tp(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
+  const double* Psibc = tp(S.Psib + sl * S.s_Psib, d.rmax * X * X, t);
+  const double* xendc = tp(S.xend + sl * S.s_xend, d.rmax * X, t);
+  const double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
+  const double* DinvAc = tp(S.DinvA + sl * S.s_A, NRMAX * U, t);
+  const double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
+  const double* LCc = pc(S.LC + sl * S.s_LC, UTRI, t);
+  double* alph = tp(W.alpha, d.rmax * X, t);
+  const bool has_blk = t.slot < d.nb[part] && !skip;
+  const bool kick = (h != 0.0);
+  const bool write1 = kick || (src_sel != dst_sel);
+  Blk B;
+  if (t.slot < d.nb[part]) B = get_block<M>(d, part, t.slot);
+  double pu[UMAX], sres[UMAX], pv0[M::V0];
+  double dx0_dv0[X * M::V0], dx0_dz[X * Z];
+  double sig = 0.0;
 #pragma unroll
   for (int j = 0; j < UMAX; ++j) pu[j] = 0.0;
-  for (int j = 0; j < U; ++j) pu[j] = pval(j);
-  double dx0_dv0[X * M::V0], dx0_dz[X * Z];
   if (has_blk) {
     double u[UMAX], z[Z], dzdu[Z * Z];
-    for (int j = 0; j < U; ++j) u[j] = qc[(long long)j * ld];
+#pragma unroll
+    for (int j = 0; j < UMAX; ++j) u[j] = (j < U) ? q.head[j * cpb] : 0.0;
     M::gen_z(u, z, dzdu);
     M::gen_x0_jac(z, dx0_dv0, dx0_dz);
+    sig = sigma_of<M>(d, u);
+    // head of the kicked momentum (u and v_0 components), kept in registers
+#pragma unroll
+    for (int j = 0; j < UMAX; ++j)
+      if (j < U) {
+        double pv = ps.head[j * cpb];
+        if (kick) pv -= h * (qcoef * u[j] + g.head[j * cpb]);
+        pu[j] = pv;
+      }
+#pragma unroll
+    for (int j = 0; j < M::V0; ++j) {
+      double pv = ps.head[(U + j) * cpb];
+      if (kick) pv -= h * (qcoef * q.head[(U + j) * cpb] + g.head[(U + j) * cpb]);
+      pv0[j] = pv;
+    }
     double m[X];
     if (B.ini) {
-      double pv0[M::V0];
-#pragma unroll
-      for (int j = 0; j < M::V0; ++j) pv0[j] = pval(d.off_v0 + j);
       mv<X, M::V0>(dx0_dv0, pv0, m);
     } else {
 #pragma unroll
@@ -552,203 +611,264 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
     }
     for (int rr = 0; rr < B.nrows; ++rr) {
       double s = 0.0;
-      for (int j = 0; j < U; ++j) s = fma(Ac[((long long)(B.row0 + rr) * U + j) * ld], pu[j], s);
-      r[rr] = s;
+#pragma unroll
+      for (int j = 0; j < UMAX; ++j)
+        if (j < U) s = fma(Ac[(rr * U + j) * nta], pu[j], s);
+      sm_c[rr * NT] = s;
     }
+    // pass 1: r = J p'  (lmult_by_jacob_constr :822-877); p' written to dst when it differs from src
     for (int k = 0; k < B.n; ++k) {
-      const long long g0 = (long long)(B.o + k) * d.S;
+      const int r0 = k * d.S * V;
       double sk[X];
 #pragma unroll
       for (int i = 0; i < X; ++i) sk[i] = 0.0;
-      for (int t = 0; t < d.S; ++t) {
-        double Kt[X * V], pv[V];
-        ldcol<X * V>(Kc + (g0 + t) * X * V * ld, ld, Kt);
+#pragma unroll 5
+      for (int tt = 0; tt < d.S; ++tt) {
+        double Kt[XV], pv[V];
+        ldcol<XV>(Kc + (k * d.S + tt) * XV * nta, nta, Kt);
 #pragma unroll
-        for (int j = 0; j < V; ++j) pv[j] = pval(d.off_v + (g0 + t) * V + j);
+        for (int j = 0; j < V; ++j) {
+          const int row = (r0 + tt * V + j) * nta;
+          double p1 = ps.body[row];
+          if (kick) p1 -= h * (qcoef * q.body[row] + g.body[row]);
+          if (write1) pd.body[row] = p1;
+          pv[j] = p1;
+        }
 #pragma unroll
         for (int i = 0; i < X; ++i)
 #pragma unroll
           for (int j = 0; j < V; ++j) sk[i] = fma(Kt[i * V + j], pv[j], sk[i]);
       }
       double Ps[X * X], t1[X];
-      ldcol<X * X>(Psibc + (long long)(B.o + k) * X * X * ld, ld, Ps);
+      ldcol<X * X>(Psibc + k * X * X * nta, nta, Ps);
       mv<X, X>(Ps, m, t1);
 #pragma unroll
       for (int i = 0; i < X; ++i) m[i] = t1[i] + sk[i];
       if (k < B.ny) {
         double dh[X], xe[X];
+        if (!M::OBS_LINEAR) ldcol<X>(xendc + k * X * nta, nta, xe);
         M::obs_grad(xe, dh);
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < X; ++i) s = fma(dh[i], m[i], s);
-        if (d.noisy) s += sigma_of<M>(d, u) * pval(d.off_n + B.o + k);
-        r[k] += s;
+        if (d.noisy) {
+          double pn = ps.noise[k * nta];
+          if (kick) pn -= h * (qcoef * q.noise[k * nta] + g.noise[k * nta]);
+          if (write1) pd.noise[k * nta] = pn;
+          s = fma(sig, pn, s);
+        }
+        sm_c[k * NT] += s;
       }
       if (k == B.n - 1 && B.nx > 0) {
 #pragma unroll
-        for (int i = 0; i < X; ++i) r[B.ny + i] += m[i];
+        for (int i = 0; i < X; ++i) sm_c[(B.ny + i) * NT] += m[i];
       }
     }
   }
-  inv_gram_block<M, NRMAX, UMAX, CPB>(d, B, has_blk, Ac, Lc, DinvAc, LCc, ld, r, sres, smem, nslot, slot, cl);
+  double rr[NRMAX];
+#pragma unroll
+  for (int i = 0; i < NRMAX; ++i) rr[i] = has_blk ? sm_c[i * NT] : 0.0;
+  inv_gram_block<M, NRMAX, UMAX>(d, B, has_blk, Ac, Lc, DinvAc, LCc, rr, sres, nullptr, sm_red, t);
   if (has_blk) {
-    double* alph = W.alpha + chain;
+    // pass 2: p'' = p' - J^T lambda  (rmult_by_jacob_constr :879-913), fused h2_flow
     double a0[X];
-    alpha_block<M>(d, B, r, Psibc, nullptr, ld, alph, a0);
+#pragma unroll
+    for (int i = 0; i < NRMAX; ++i) sm_c[i * NT] = rr[i];
+    alpha_block<M, NRMAX, RMAXP>(B, rr, Psibc, xendc, nta, alph, a0);
     for (int k = 0; k < B.n; ++k) {
-      const long long g0 = (long long)(B.o + k) * d.S;
+      const int r0 = k * d.S * V;
       double al[X];
-      ldcol<X>(alph + (long long)(B.o + k) * X * ld, ld, al);
-      for (int t = 0; t < d.S; ++t) {
-        double Kt[X * V];
-        ldcol<X * V>(Kc + (g0 + t) * X * V * ld, ld, Kt);
+      ldcol<X>(alph + k * X * nta, nta, al);
+#pragma unroll 5
+      for (int tt = 0; tt < d.S; ++tt) {
+        double Kt[XV];
+        ldcol<XV>(Kc + (k * d.S + tt) * XV * nta, nta, Kt);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          const long long row = d.off_v + (g0 + t) * V + j;
-          double pv = pval(row);
+          const int row = (r0 + tt * V + j) * nta;
+          double pv = write1 ? pd.body[row] : ps.body[row];
 #pragma unroll
           for (int i = 0; i < X; ++i) pv = fma(-Kt[i * V + j], al[i], pv);
-          pdst[row * ld] = pv;
+          if (fl.mode) {
+            const double qv = q.body[row];
+            qw.body[row] = fl.fq * qv + fl.fp * pv;
+            if (fl.mode == 2) pv = fl.fq * pv - fl.fpm * qv;
+          }
+          pd.body[row] = pv;
         }
       }
-      if (d.noisy && k < B.ny) {
-        double u[UMAX];
-        for (int j = 0; j < U; ++j) u[j] = qc[(long long)j * ld];
-        const long long row = d.off_n + B.o + k;
-        pdst[row * ld] = pval(row) - sigma_of<M>(d, u) * r[k];
+      if (d.noisy) {
+        double pv = write1 ? pd.noise[k * nta] : ps.noise[k * nta];
+        if (k < B.ny) pv = fma(-sig, sm_c[k * NT], pv);
+        if (fl.mode) {
+          const double qv = q.noise[k * nta];
+          qw.noise[k * nta] = fl.fq * qv + fl.fp * pv;
+          if (fl.mode == 2) pv = fl.fq * pv - fl.fpm * qv;
+        }
+        pd.noise[k * nta] = pv;
       }
-    }
-    if (d.noisy && !B.fin) {
-      // noise variables of a non-final block's last observation are covered by k < ny above
     }
     if (B.ini) {
       double t0[M::V0];
       mtv<X, M::V0>(dx0_dv0, a0, t0);
 #pragma unroll
-      for (int j = 0; j < M::V0; ++j) pdst[(long long)(d.off_v0 + j) * ld] = pval(d.off_v0 + j) - t0[j];
-      for (int j = 0; j < U; ++j) pdst[(long long)j * ld] = pu[j] - sres[j];
+      for (int j = 0; j < M::V0; ++j) {
+        double pv = pv0[j] - t0[j];
+        if (fl.mode) {
+          const double qv = q.head[(U + j) * cpb];
+          qw.head[(U + j) * cpb] = fl.fq * qv + fl.fp * pv;
+          if (fl.mode == 2) pv = fl.fq * pv - fl.fpm * qv;
+        }
+        pd.head[(U + j) * cpb] = pv;
+      }
+#pragma unroll
+      for (int j = 0; j < UMAX; ++j)
+        if (j < U) {
+          double pv = pu[j] - sres[j];
+          if (fl.mode) {
+            const double qv = q.head[j * cpb];
+            qw.head[j * cpb] = fl.fq * qv + fl.fp * pv;
+            if (fl.mode == 2) pv = fl.fq * pv - fl.fpm * qv;
+          }
+          pd.head[j * cpb] = pv;
+        }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_qn: on-device symmetric quasi-Newton projection loop (quasi_newton_projection :1009-1063 and
-// its host wrapper :1323-1402) for a whole CTA of chains, masked per chain, no host round trips.
-//   iterate:  c = constr(q) ; err = |c|_inf ; lam = G_prev^{-1} c ; q -= J_prev^T lam
-// with q = qw - J_prev^T lam_tot never materialised inside the loop.
-// mode 0 (forward):  on convergence write q_new -> slot(other).q and p(other) -= mom_coef * mu
-// mode 1 (reverse):  compare q_back with q(cur) -> revd, no writes       (Mici reverse check)
+// dev_qn: on-device symmetric quasi-Newton projection loop (quasi_newton_projection :1009-1063 and
+// its host wrapper :1323-1402) for a tile of chains, masked per chain, no host round trips.
+//   iterate:  c = constr(q) ; err = |c|_inf ; lam = G_lin^{-1} c ; q -= J_lin^T lam
+// with q = qw - J_lin^T lam_tot never materialised inside the loop.
+// mode 0 (forward):  linearisation = cur; on convergence q(other) = q_new, p(other) = pw - mom_coef * mu
+// mode 1 (reverse):  linearisation = other; compare q_back with q(cur) -> revd, no writes (Mici reverse check)
 // ------------------------------------------------------------------------------------------
-template <class M, int CPB, int NRMAX, int UMAX>
-MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ xobs,
-                  const double* __restrict__ y, int part, int mode, double mom_coef, double ctol, double ptol,
-                  double dtol, int max_iters) {
-  MMD_THREAD_SETUP
-  constexpr int X = M::X, V = M::V, Z = M::Z;
+template <class M, int NRMAX, int RMAXP, int UMAX>
+MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ y, int part, int mode,
+                  double mom_coef, double ctol, double ptol, double dtol, int max_iters) {
+  const Tid t = thread_id(d);
+  MMD_SMEM_SETUP
+  constexpr int X = M::X, V = M::V, Z = M::Z, XV = M::X * M::V;
   constexpr int NTRI = NRMAX * (NRMAX + 1) / 2;
-  const int U = d.U;
-  const int cur = S.cur[chain];
+  constexpr int UTRI = UMAX * (UMAX + 1) / 2;
+  const int U = d.U, nta = t.nta, cpb = t.cpb;
+  const int cur = S.cur[t.cix];
   const int sl = mode ? 1 - cur : cur;  // linearisation used: forward -> cur (prev point), reverse -> new point
-  const double* Kc = S.K + sl * S.s_K + chain;
-  const double* Psibc = S.Psib + sl * S.s_Psib + chain;
-  const double* Ac = S.A + sl * S.s_A + chain;
-  const double* DinvAc = S.DinvA + sl * S.s_A + chain;
-  const double* LCc = S.LC + sl * S.s_LC + chain;
-  const double* Lc = S.L + sl * S.s_L + chain + (long long)slot * NTRI * ld;
-  const double* qwc = W.qw + chain;
-  const double* xoc = xobs + chain;
-  double* alph = W.alpha + chain;
-  double* alphi = W.alphi + chain;
-  const bool in_blk = slot < d.nb[part];
+  const double* Kc = tp(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
+  const double* Psibc = tp(S.Psib + sl * S.s_Psib, d.rmax * X * X, t);
+  const double* xendc = tp(S.xend + sl * S.s_xend, d.rmax * X, t);
+  const double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
+  const double* DinvAc = tp(S.DinvA + sl * S.s_A, NRMAX * U, t);
+  const double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
+  const double* LCc = pc(S.LC + sl * S.s_LC, UTRI, t);
+  const QPtr qw = qptr(W.qw, d, t);
+  const QPtr qlin = qptr(S.q + sl * S.s_q, d, t);
+  const double* xoc = pc(W.xobs, d.T * X, t);
+  double* alph = tp(W.alpha, d.rmax * X, t);
+  double* alphi = tp(W.alphi, d.rmax * X, t);
+  const bool in_blk = t.slot < d.nb[part];
   Blk B;
-  if (in_blk) B = get_block<M>(d, part, slot);
-  bool done = !act || (W.status[chain] != 0);
+  if (in_blk) B = get_block<M>(d, part, t.slot);
+  bool done = !t.act || (W.status[t.cix] != 0);
   int st = 0, it = 0;
-  double u0[UMAX], stot[UMAX], lamtot[NRMAX];
+  double u0[UMAX], stot[UMAX];
 #pragma unroll
-  for (int j = 0; j < UMAX; ++j) { u0[j] = 0.0; stot[j] = 0.0; }
-  for (int j = 0; j < U; ++j) u0[j] = qwc[(long long)j * ld];
+  for (int j = 0; j < UMAX; ++j) {
+    u0[j] = (j < U) ? qw.head[j * cpb] : 0.0;
+    stot[j] = 0.0;
+  }
+  // derivatives of generate_x_0 and the noise scale at the LINEARISATION point (J_lin's v_0 / n columns)
+  double dx0_dv0[X * M::V0], sig_lin = 0.0;
+  {
+    double u[UMAX], z[Z], dzdu[Z * Z], dx0_dz[X * Z];
 #pragma unroll
-  for (int r = 0; r < NRMAX; ++r) lamtot[r] = 0.0;
-  double dx0_dv0[X * M::V0], dx0_dz[X * Z];
+    for (int j = 0; j < UMAX; ++j) u[j] = (j < U) ? qlin.head[j * cpb] : 0.0;
+    M::gen_z(u, z, dzdu);
+    M::gen_x0_jac(z, dx0_dv0, dx0_dz);
+    sig_lin = sigma_of<M>(d, u);
+  }
   double a0tot[X];
 #pragma unroll
   for (int i = 0; i < X; ++i) a0tot[i] = 0.0;
-  if (in_blk)
+  if (in_blk) {
     for (int k = 0; k < B.n; ++k) {
-      double zero[X];
 #pragma unroll
-      for (int i = 0; i < X; ++i) zero[i] = 0.0;
-      stcol<X>(alph + (long long)(B.o + k) * X * ld, ld, zero);
+      for (int i = 0; i < X; ++i) alph[(k * X + i) * nta] = 0.0;
     }
+    for (int r = 0; r < NRMAX; ++r) sm_l[r * NT] = 0.0;
+  }
   double final_norm = 0.0;
   while (true) {
     if (__syncthreads_and(done ? 1 : 0)) break;
     const bool work = in_blk && !done;
-    double crow[NRMAX], sres[UMAX], red[1];
-    double z[Z], dzdu[Z * Z], u[UMAX];
-    red[0] = 0.0;
+    double sres[UMAX], err = 0.0;
     if (work) {
+      ChainPar<M, UMAX> P;
+      {
+        double u[UMAX];
 #pragma unroll
-      for (int j = 0; j < UMAX; ++j) u[j] = u0[j] - stot[j];
-      M::gen_z(u, z, dzdu);
-      M::gen_x0_jac(z, dx0_dv0, dx0_dz);
-      double x[X];
+        for (int j = 0; j < UMAX; ++j) u[j] = u0[j] - stot[j];
+        make_par<M, UMAX>(d, u, P);
+      }
+      double x[X], v0[M::V0];
+      ldcol<M::V0>(qw.head + U * cpb, cpb, v0);
       if (B.ini) {
-        double v0[M::V0], t0[M::V0];
-        ldcol<M::V0>(qwc + (long long)d.off_v0 * ld, ld, v0);
+        double t0[M::V0];
         mtv<X, M::V0>(dx0_dv0, a0tot, t0);
 #pragma unroll
         for (int j = 0; j < M::V0; ++j) v0[j] -= t0[j];
-        M::gen_x0(z, v0, x);
-      } else {
-        ldcol<X>(xoc + (long long)(B.o - 1) * X * ld, ld, x);
       }
-      constr_block<M, true>(d, B, z, sigma_of<M>(d, u), x, qwc, xoc, y, Kc, alph, ld, crow, nullptr);
-      if (d.noisy) {
-        // noise part of q: n_k = qw_n[k] - sigma_prev * lamtot[k]; constr_block read qw_n, correct here
-        // (handled in noisy build; see k_qn_noisy_fixup)
-      }
+      block_start<M>(d, B, P.z, v0, xoc, cpb, x);
+      constr_sweep<M, true>(d, B, P.C, P.sigy, sig_lin, x, qw.body, qw.noise, xoc, y, Kc, alph, sm_l, nta, cpb, NT,
+                            sm_c, sm_ring, nullptr);
+    }
+    double rr[NRMAX];
+    {
       double e = 0.0;
-      for (int r = 0; r < B.nrows; ++r) {
-        const double a = fabs(crow[r]);
+#pragma unroll
+      for (int r = 0; r < NRMAX; ++r) {
+        rr[r] = (work && r < B.nrows) ? sm_c[r * NT] : 0.0;
+        const double a = fabs(rr[r]);
         e = (a > e || a != a) ? a : e;
       }
-      red[0] = e;
+      err = e;
     }
-    block_reduce<1, CPB, true>(red, smem, nslot, slot, cl);
-    const double err = red[0];
-    inv_gram_block<M, NRMAX, UMAX, CPB>(d, B, work, Ac, Lc, DinvAc, LCc, ld, crow, sres, smem, nslot, slot, cl);
+    inv_gram_block<M, NRMAX, UMAX>(d, B, work, Ac, Lc, DinvAc, LCc, rr, sres, &err, sm_red, t);
     // norm of this iteration's update and (speculative) finalisation when the constraint is met
     const bool check = !done && (err < ctol);
     double nrm[1];
     nrm[0] = 0.0;
-    double a0inc[X];
     if (work) {
+      double lt[NRMAX];
 #pragma unroll
-      for (int r = 0; r < NRMAX; ++r)
-        if (r < B.nrows) lamtot[r] += crow[r];
+      for (int r = 0; r < NRMAX; ++r) {
+        lt[r] = sm_l[r * NT] + rr[r];
+        sm_l[r * NT] = lt[r];
+        sm_c[r * NT] = rr[r];
+      }
 #pragma unroll
       for (int j = 0; j < UMAX; ++j) stot[j] += sres[j];
-      double a0[X];
-      alpha_block<M>(d, B, lamtot, Psibc, nullptr, ld, alph, a0);
-#pragma unroll
-      for (int i = 0; i < X; ++i) a0tot[i] = a0[i];
-      if (check) {
-        alpha_block<M>(d, B, crow, Psibc, nullptr, ld, alphi, a0inc);
-        double nm = 0.0;
-        double* qout = S.q + (1 - cur) * S.s_q + chain;
-        double* pout = S.p + (1 - cur) * S.s_q + chain;
-        const double* qref = S.q + cur * S.s_q + chain;
-        double rv = 0.0;
+      alpha_block<M, NRMAX, RMAXP>(B, lt, Psibc, xendc, nta, alph, a0tot);
+    }
+    if (__syncthreads_or(check ? 1 : 0)) {
+      if (work && check) {
+        double a0inc[X];
+        alpha_block<M, NRMAX, RMAXP>(B, rr, Psibc, xendc, nta, alphi, a0inc);
+        double nm = 0.0, rv = 0.0;
+        const QPtr qout = qptr(S.q + (1 - cur) * S.s_q, d, t);
+        const QPtr pout = qptr(S.p + (1 - cur) * S.s_q, d, t);
+        const QPtr pin = qptr(W.pw, d, t);
+        const QPtr qref = qptr(S.q + cur * S.s_q, d, t);
         for (int k = 0; k < B.n; ++k) {
-          const long long g0 = (long long)(B.o + k) * d.S;
+          const int r0 = k * d.S * V;
           double al[X], ai[X];
-          ldcol<X>(alph + (long long)(B.o + k) * X * ld, ld, al);
-          ldcol<X>(alphi + (long long)(B.o + k) * X * ld, ld, ai);
-          for (int t = 0; t < d.S; ++t) {
-            double Kt[X * V];
-            ldcol<X * V>(Kc + (g0 + t) * X * V * ld, ld, Kt);
+          ldcol<X>(alph + k * X * nta, nta, al);
+          ldcol<X>(alphi + k * X * nta, nta, ai);
+#pragma unroll 5
+          for (int tt = 0; tt < d.S; ++tt) {
+            double Kt[XV];
+            ldcol<XV>(Kc + (k * d.S + tt) * XV * nta, nta, Kt);
 #pragma unroll
             for (int j = 0; j < V; ++j) {
               double mu = 0.0, inc = 0.0;
@@ -758,14 +878,28 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
                 inc = fma(Kt[i * V + j], ai[i], inc);
               }
               nm = fmax(nm, fabs(inc));
-              const long long row = d.off_v + (g0 + t) * V + j;
-              const double qn = qwc[row * ld] - mu;
+              const int row = (r0 + tt * V + j) * nta;
+              const double qn = qw.body[row] - mu;
               if (mode == 0) {
-                qout[row * ld] = qn;
-                W.Yw[row * ld + chain] = mu;  // stash mu_v (momentum update applied once converged)
+                qout.body[row] = qn;
+                pout.body[row] = fma(-mom_coef, mu, pin.body[row]);
               } else {
-                rv = fmax(rv, fabs(qn - qref[row * ld]));
+                rv = fmax(rv, fabs(qn - qref.body[row]));
               }
+            }
+          }
+          if (d.noisy) {
+            double mu = 0.0;
+            if (k < B.ny) {
+              mu = sig_lin * sm_l[k * NT];
+              nm = fmax(nm, fabs(sig_lin * sm_c[k * NT]));
+            }
+            const double qn = qw.noise[k * nta] - mu;
+            if (mode == 0) {
+              qout.noise[k * nta] = qn;
+              pout.noise[k * nta] = fma(-mom_coef, mu, pin.noise[k * nta]);
+            } else {
+              rv = fmax(rv, fabs(qn - qref.noise[k * nta]));
             }
           }
         }
@@ -776,32 +910,33 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
 #pragma unroll
           for (int j = 0; j < M::V0; ++j) {
             nm = fmax(nm, fabs(ti[j]));
-            const long long row = d.off_v0 + j;
-            const double qn = qwc[row * ld] - t0[j];
+            const int row = (U + j) * cpb;
+            const double qn = qw.head[row] - t0[j];
             if (mode == 0) {
-              qout[row * ld] = qn;
-              W.Yw[row * ld + chain] = t0[j];
+              qout.head[row] = qn;
+              pout.head[row] = fma(-mom_coef, t0[j], pin.head[row]);
             } else {
-              rv = fmax(rv, fabs(qn - qref[row * ld]));
+              rv = fmax(rv, fabs(qn - qref.head[row]));
             }
           }
-          for (int j = 0; j < U; ++j) {
-            nm = fmax(nm, fabs(sres[j]));
-            const double qn = u0[j] - stot[j];
-            if (mode == 0) {
-              qout[(long long)j * ld] = qn;
-              W.Yw[(long long)j * ld + chain] = stot[j];
-            } else {
-              rv = fmax(rv, fabs(qn - qref[(long long)j * ld]));
+#pragma unroll
+          for (int j = 0; j < UMAX; ++j)
+            if (j < U) {
+              nm = fmax(nm, fabs(sres[j]));
+              const double qn = u0[j] - stot[j];
+              if (mode == 0) {
+                qout.head[j * cpb] = qn;
+                pout.head[j * cpb] = fma(-mom_coef, stot[j], pin.head[j * cpb]);
+              } else {
+                rv = fmax(rv, fabs(qn - qref.head[j * cpb]));
+              }
             }
-          }
         }
         nrm[0] = nm;
         final_norm = rv;
-        (void)pout;
       }
+      block_reduce<0, 1>(nrm, sm_red, t);
     }
-    block_reduce<1, CPB, true>(nrm, smem, nslot, slot, cl);
     if (!done) {
       it += 1;
       const bool diverged = (err > dtol) || (err != err);
@@ -818,303 +953,370 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
     }
   }
   // epilogue
-  const bool live = act && (W.status[chain] == 0);
-  if (mode == 0) {
-    if (live && st == 0 && in_blk) {
-      // p(other) -= mom_coef * mu   (state.mom -= dh2_flow_mom_dmom @ mu, :1388-1392)
-      double* pout = S.p + (1 - cur) * S.s_q + chain;
-      for (int k = 0; k < B.n; ++k) {
-        const long long g0 = (long long)(B.o + k) * d.S;
-        for (int t = 0; t < d.S * V; ++t) {
-          const long long row = d.off_v + g0 * V + t;
-          pout[row * ld] -= mom_coef * W.Yw[row * ld + chain];
-        }
-      }
-      if (B.ini) {
-        for (int j = 0; j < M::V0; ++j) {
-          const long long row = d.off_v0 + j;
-          pout[row * ld] -= mom_coef * W.Yw[row * ld + chain];
-        }
-        for (int j = 0; j < U; ++j) pout[(long long)j * ld] -= mom_coef * W.Yw[(long long)j * ld + chain];
-      }
-    }
-  }
+  const bool live = t.act && (W.status[t.cix] == 0);
   double rr[1];
   rr[0] = final_norm;
-  block_reduce<1, CPB, true>(rr, smem, nslot, slot, cl);
-  if (slot == 0 && live) {
-    W.iters[mode * ld + chain] = it;
-    W.itsum[chain] += it;
-    if (st) W.status[chain] |= st;
-    if (mode == 1 && st == 0) W.revd[chain] = rr[0];
+  block_reduce<0, 1>(rr, sm_red, t);
+  if (t.slot == 0 && live) {
+    W.iters[mode * d.n_tiles * cpb + t.cix] = it;
+    W.itsum[t.cix] += it;
+    if (st) W.status[t.cix] |= st;
+    if (mode == 1 && st == 0) W.revd[t.cix] = rr[0];
+  }
+}
+
+// commit / reject: successful chains flip to the new slot; reverse check (Mici
+// ConstrainedLeapfrogIntegrator._step_b: reverse_check_norm(...) > reverse_check_tol)
+MMD_D void dev_commit(const Dims& d, const Slots& S, const Work& W, double rev_tol, long long* __restrict__ n_ok,
+                      int cix) {
+  int st = W.status[cix];
+  if (st == 0 && !(W.revd[cix] <= rev_tol)) {
+    st |= ST_NONREV;
+    W.status[cix] = st;
+  }
+  if (st == 0) {
+    S.cur[cix] = 1 - S.cur[cix];
+    n_ok[cix] += 1;
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // standalone launches of the phases (per-op API) and the fused persistent leapfrog kernel
 // ------------------------------------------------------------------------------------------
-template <class M, int CPB, int NRMAX, int RMAX, int UMAX, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-k_point(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* __restrict__ y, int part,
-        int which, int with_grad) {
-  dev_point<M, CPB, NRMAX, RMAX, UMAX>(d, S, W, xobs, y, part, which, with_grad);
+#if defined(__CUDACC__)
+template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB)
+k_point(Dims d, Slots S, Work W, const double* __restrict__ y, int part, int which, int with_grad) {
+  dev_point<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, which, with_grad);
 }
-template <class M, int CPB, int NRMAX, int UMAX, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-k_project(Dims d, Slots S, Work W, int part, int lin_sel, int src_sel, int dst_sel, double h, double qcoef) {
-  dev_project<M, CPB, NRMAX, UMAX>(d, S, W, part, lin_sel, src_sel, dst_sel, h, qcoef);
+template <class M, int NRMAX, int UMAX, int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB)
+k_constr(Dims d, Slots S, Work W, const double* __restrict__ y, int part, double* __restrict__ cout) {
+  dev_constr<M, NRMAX, UMAX>(d, S, W, y, part, cout);
 }
-template <class M, int CPB, int NRMAX, int UMAX, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-k_qn(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* __restrict__ y, int part,
-     int mode, double mom_coef, double ctol, double ptol, double dtol, int max_iters) {
-  dev_qn<M, CPB, NRMAX, UMAX>(d, S, W, xobs, y, part, mode, mom_coef, ctol, ptol, dtol, max_iters);
+template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB)
+k_project(Dims d, Slots S, Work W, int part, int lin_sel, int src_sel, int dst_sel, double h, double qcoef,
+          FlowCoef fl) {
+  dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, lin_sel, src_sel, dst_sel, h, qcoef, fl);
+}
+template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB)
+k_qn(Dims d, Slots S, Work W, const double* __restrict__ y, int part, int mode, double mom_coef, double ctol,
+     double ptol, double dtol, int max_iters) {
+  dev_qn<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, mode, mom_coef, ctol, ptol, dtol, max_iters);
+}
+__global__ void k_commit(Dims d, Slots S, Work W, double rev_tol, long long* __restrict__ n_ok) {
+  const int cix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cix >= d.n_chains) return;
+  dev_commit(d, S, W, rev_tol, n_ok, cix);
 }
 
-// h2_flow for this thread's rows: qw = q(q_sel) + dt * p(p_sel)   (mici_extensions.py:1222-1231)
-template <class M, int CPB>
-MMD_D void dev_flow(const Dims& d, const Slots& S, const Work& W, int part, int q_sel, int p_sel, double dt) {
-  MMD_THREAD_SETUP
-  if (slot >= d.nb[part]) return;
-  const int cur = S.cur[chain];
-  const double* qc = S.q + (q_sel ? 1 - cur : cur) * S.s_q + chain;
-  const double* pc = S.p + (p_sel ? 1 - cur : cur) * S.s_q + chain;
-  double* qw = W.qw + chain;
-  const Blk B = get_block<M>(d, part, slot);
-  const long long r0 = d.off_v + (long long)B.o * d.S * M::V, r1 = r0 + (long long)B.n * d.S * M::V;
-  for (long long r = r0; r < r1; ++r) qw[r * ld] = fma(dt, pc[r * ld], qc[r * ld]);
-  if (d.noisy)
-    for (long long r = d.off_n + B.o; r < d.off_n + B.o + B.n; ++r) qw[r * ld] = fma(dt, pc[r * ld], qc[r * ld]);
-  if (B.ini)
-    for (long long r = 0; r < d.off_v; ++r) qw[r * ld] = fma(dt, pc[r * ld], qc[r * ld]);
-}
+// step-size dependent constants of one leapfrog step (standard / Gaussian splitting, :1186-1238)
+struct StepCoef {
+  double half_dt;    // h1 kick
+  double qcoef;      // 1: h1 contains 1/2 |q|^2 (standard splitting); 0: Gaussian splitting
+  FlowCoef fwd;      // h2_flow(dt) fused into the first projection
+  FlowCoef back;     // h2_flow(-dt) for the reverse check (trial position only)
+  double mom_coef;   // dh2_flow_mom_dmom / (dt or sin dt): momentum update after the projection solve
+};
 
 // One (or n_steps) full ConstrainedLeapfrogIntegrator.step per chain in ONE launch: a CTA carries
-// its CPB chains through every phase with CTA-local barriers only, so chains that need many
+// its tile of chains through every phase with CTA-local barriers only, so chains that need many
 // projection iterations delay just their own small CTA while the other resident CTAs keep the SM busy
 // (the per-chain iteration count is long-tailed: mean ~8, 1 % > 30, max_iters = 50).
 // Step order: Mici ConstrainedLeapfrogIntegrator._step = A(dt/2) B(dt) A(dt/2), SURVEY.md 3.3.
-template <class M, int CPB, int NRMAX, int RMAX, int UMAX, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ xobs, const double* __restrict__ y, int part,
-           double dt, double ctol, double ptol, double dtol, int max_iters, double rev_tol,
-           long long* __restrict__ n_ok, int n_steps, int reset_status) {
-  const int cl = threadIdx.x % CPB, slot = threadIdx.x / CPB;
-  const int chain = blockIdx.x * CPB + cl;
+template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB)
+k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, StepCoef sc, double ctol, double ptol,
+           double dtol, int max_iters, double rev_tol, long long* __restrict__ n_ok, int n_steps,
+           int reset_status) {
+  const Tid t = thread_id(d);
+  const FlowCoef noflow = {0, 1.0, 0.0, 0.0};
   for (int s = 0; s < n_steps; ++s) {
-    if (reset_status && slot == 0) W.status[chain] = 0;
+    if (reset_status && t.slot == 0) W.status[t.cix] = 0;
     __syncthreads();
-    dev_project<M, CPB, NRMAX, UMAX>(d, S, W, part, 0, 0, 1, 0.5 * dt, 1.0);
+    dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 0, PSEL_CUR, PSEL_WORK, sc.half_dt, sc.qcoef, sc.fwd);
     __syncthreads();
-    dev_flow<M, CPB>(d, S, W, part, 0, 1, dt);
+    dev_qn<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, 0, sc.mom_coef, ctol, ptol, dtol, max_iters);
     __syncthreads();
-    dev_qn<M, CPB, NRMAX, UMAX>(d, S, W, xobs, y, part, 0, 1.0 / dt, ctol, ptol, dtol, max_iters);
+    dev_point<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, 1, 1);
     __syncthreads();
-    dev_point<M, CPB, NRMAX, RMAX, UMAX>(d, S, W, xobs, y, part, 1, 1);
+    dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 1, PSEL_OTHER, PSEL_OTHER, 0.0, 0.0, sc.back);
     __syncthreads();
-    dev_project<M, CPB, NRMAX, UMAX>(d, S, W, part, 1, 1, 1, 0.0, 0.0);
+    dev_qn<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, 1, 0.0, ctol, ptol, dtol, max_iters);
     __syncthreads();
-    dev_flow<M, CPB>(d, S, W, part, 1, 1, -dt);
+    dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 1, PSEL_OTHER, PSEL_OTHER, sc.half_dt, sc.qcoef, noflow);
     __syncthreads();
-    dev_qn<M, CPB, NRMAX, UMAX>(d, S, W, xobs, y, part, 1, 0.0, ctol, ptol, dtol, max_iters);
-    __syncthreads();
-    dev_project<M, CPB, NRMAX, UMAX>(d, S, W, part, 1, 1, 1, 0.5 * dt, 1.0);
-    __syncthreads();
-    if (slot == 0 && chain < d.n_chains) {
-      int st = W.status[chain];
-      if (st == 0 && !(W.revd[chain] <= rev_tol)) {
-        st |= ST_NONREV;
-        W.status[chain] = st;
-      }
-      if (st == 0) {
-        S.cur[chain] = 1 - S.cur[chain];
-        n_ok[chain] += 1;
-      }
-    }
+    if (t.slot == 0 && t.act) dev_commit(d, S, W, rev_tol, n_ok, t.cix);
     __syncthreads();
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// elementwise helpers
-// ------------------------------------------------------------------------------------------
-// h2_flow (mici_extensions.py:1222-1231), standard splitting: qw = q(sel_q) + dt * p(sel_p)
-__global__ void k_flow(Dims d, Slots S, Work W, int q_sel, int p_sel, double dt) {
-  const long long n = (long long)d.dim_q * d.ld;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int chain = (int)(i % d.ld);
-    const int cur = S.cur[chain];
-    const int sq = q_sel ? 1 - cur : cur, sp = p_sel ? 1 - cur : cur;
-    W.qw[i] = S.q[sq * S.s_q + i] + dt * S.p[sp * S.s_q + i];
-  }
-}
-
-// commit / reject: successful chains flip to the new slot; reverse check (Mici
-// ConstrainedLeapfrogIntegrator._step_b: reverse_check_norm(...) > reverse_check_tol)
-__global__ void k_commit(Dims d, Slots S, Work W, double rev_tol, long long* __restrict__ n_ok) {
-  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
-  if (chain >= d.n_chains) return;
-  int st = W.status[chain];
-  if (st == 0 && !(W.revd[chain] <= rev_tol)) {
-    st |= ST_NONREV;
-    W.status[chain] = st;
-  }
-  if (st == 0) {
-    S.cur[chain] = 1 - S.cur[chain];
-    n_ok[chain] += 1;
-  }
-}
-
-// Hamiltonian h = h1 + h2 (mici_extensions.py:1186-1202) for the current slot
-template <int CPB>
-__global__ void k_hamiltonian(Dims d, Slots S, Work W, int sel, double* __restrict__ hout) {
-  MMD_THREAD_SETUP
-  const int cur = S.cur[chain];
+// Hamiltonian h = h1 + h2 (mici_extensions.py:1186-1202) for the current slot; both splittings give
+// 1/2 |q|^2 + log det^{1/2} + 1/2 |p|^2 with the identity metric
+template <class M>
+__global__ void k_hamiltonian(Dims d, Slots S, Work W, int part, int sel, double* __restrict__ hout) {
+  const Tid t = thread_id(d);
+  extern __shared__ double smem[];
+  const int cur = S.cur[t.cix];
   const int sl = sel ? 1 - cur : cur;
-  const double* qc = S.q + sl * S.s_q + chain;
-  const double* pc = S.p + sl * S.s_q + chain;
+  const QPtr q = qptr(S.q + sl * S.s_q, d, t);
+  const QPtr p = qptr(S.p + sl * S.s_q, d, t);
   double acc[1];
   acc[0] = 0.0;
-  for (long long r = slot; r < d.dim_q; r += nslot) {
-    const double a = qc[r * ld], b = pc[r * ld];
-    acc[0] += 0.5 * a * a + 0.5 * b * b;
+  if (t.slot < d.nb[part]) {
+    const Blk B = get_block<M>(d, part, t.slot);
+    const int nrow = B.n * d.S * M::V;
+    for (int r = 0; r < nrow; ++r) {
+      const double a = q.body[r * t.nta], b = p.body[r * t.nta];
+      acc[0] += 0.5 * a * a + 0.5 * b * b;
+    }
+    if (d.noisy)
+      for (int k = 0; k < B.n; ++k) {
+        const double a = q.noise[k * t.nta], b = p.noise[k * t.nta];
+        acc[0] += 0.5 * a * a + 0.5 * b * b;
+      }
+    if (B.ini)
+      for (int r = 0; r < d.rows_head; ++r) {
+        const double a = q.head[r * t.cpb], b = p.head[r * t.cpb];
+        acc[0] += 0.5 * a * a + 0.5 * b * b;
+      }
   }
-  block_reduce<1, CPB, false>(acc, smem, nslot, slot, cl);
-  if (slot == 0 && act) hout[chain] = acc[0] + S.ldv[sl * S.s_ld + chain];
+  block_reduce<1, 0>(acc, smem, t);
+  if (t.slot == 0 && t.act) hout[t.cix] = acc[0] + S.ldv[sl * S.s_ld + t.cix];
 }
 
-// [n_chains, rows] row-major (reference per-chain layout) <-> [rows][ld] structure of arrays
-__global__ void k_aos_to_soa(const double* __restrict__ src, double* __restrict__ dst, int n_chains, int rows,
-                             long long ld) {
-  __shared__ double tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int c = c0 + j, r = r0 + threadIdx.x;
-    tile[j][threadIdx.x] = (c < n_chains && r < rows) ? src[(long long)c * rows + r] : 0.0;
+// ------------------------------------------------------------------------------------------
+// layout conversion: reference per-chain layout (canonical, [chain][dim_q] row-major, AoS) <-> tile
+// layout of a q-like vector, for the given partition.  One thread per canonical element.
+// ------------------------------------------------------------------------------------------
+template <class M>
+MMD_D long long tile_index(const Dims& d, int part, int chain, int i) {
+  const int tile = chain >> d.lcpb, cl = chain & (d.cpb - 1);
+  if (i < d.off_v) return ((long long)tile * d.rows_head + i) * d.cpb + cl;
+  int b, row;
+  long long off;
+  int rows;
+  if (i < d.off_n) {
+    const int g = (i - d.off_v) / M::V, j = (i - d.off_v) % M::V;
+    const int o = g / d.S, tt = g % d.S;
+    b = block_of_obs(d, part, o);
+    const Blk B = get_block<M>(d, part, b);
+    row = ((o - B.o) * d.S + tt) * M::V + j;
+    off = d.off_body;
+    rows = d.rows_body;
+  } else {
+    const int o = i - d.off_n;
+    b = block_of_obs(d, part, o);
+    const Blk B = get_block<M>(d, part, b);
+    row = o - B.o;
+    off = d.off_noise;
+    rows = d.rows_noise;
   }
-  __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int r = r0 + j, c = c0 + threadIdx.x;
-    if (r < rows && c < n_chains) dst[(long long)r * ld + c] = tile[threadIdx.x][j];
+  return off + ((long long)tile * rows + row) * d.nta + (b << d.lcpb) + cl;
+}
+// per-chain slot selection: sel 0 cur, 1 other, 2 none (base used as is)
+template <class M>
+__global__ void k_pack(Dims d, int part, const double* __restrict__ canon, double* __restrict__ base,
+                       long long slot_stride, const int* __restrict__ cur, int sel) {
+  const long long n = (long long)d.n_chains * d.dim_q;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int chain = (int)(e / d.dim_q), i = (int)(e % d.dim_q);
+    const int sl = sel == 2 ? 0 : (sel ? 1 - cur[chain] : cur[chain]);
+    base[sl * slot_stride + tile_index<M>(d, part, chain, i)] = canon[e];
   }
 }
-__global__ void k_soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, int n_chains, int rows,
-                             long long ld) {
-  __shared__ double tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int r = r0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (c < n_chains && r < rows) ? src[(long long)r * ld + c] : 0.0;
+template <class M>
+__global__ void k_unpack(Dims d, int part, double* __restrict__ canon, const double* __restrict__ base,
+                         long long slot_stride, const int* __restrict__ cur, int sel) {
+  const long long n = (long long)d.n_chains * d.dim_q;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int chain = (int)(e / d.dim_q), i = (int)(e % d.dim_q);
+    const int sl = sel == 2 ? 0 : (sel ? 1 - cur[chain] : cur[chain]);
+    canon[e] = base[sl * slot_stride + tile_index<M>(d, part, chain, i)];
   }
-  __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int c = c0 + j, r = r0 + threadIdx.x;
-    if (r < rows && c < n_chains) dst[(long long)c * rows + r] = tile[threadIdx.x][j];
+}
+// re-tile the current position from partition `pa` to partition `pb` (SwitchPartitionTransition)
+template <class M>
+__global__ void k_retile(Dims d, int pa, int pb, const double* __restrict__ src, double* __restrict__ dst,
+                         long long slot_stride, const int* __restrict__ cur) {
+  const long long n = (long long)d.n_chains * d.dim_q;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int chain = (int)(e / d.dim_q), i = (int)(e % d.dim_q);
+    dst[tile_index<M>(d, pb, chain, i)] = src[cur[chain] * slot_stride + tile_index<M>(d, pa, chain, i)];
+  }
+}
+// per-chain arrays [chain][rows] (canonical) <-> [tile][rows][cpb]
+__global__ void k_pack_chain(Dims d, int rows, const double* __restrict__ canon, double* __restrict__ dst) {
+  const long long n = (long long)d.n_chains * rows;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int chain = (int)(e / rows), r = (int)(e % rows);
+    dst[((long long)(chain >> d.lcpb) * rows + r) * d.cpb + (chain & (d.cpb - 1))] = canon[e];
+  }
+}
+__global__ void k_unpack_chain(Dims d, int rows, double* __restrict__ canon, const double* __restrict__ src) {
+  const long long n = (long long)d.n_chains * rows;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int chain = (int)(e / rows), r = (int)(e % rows);
+    canon[e] = src[((long long)(chain >> d.lcpb) * rows + r) * d.cpb + (chain & (d.cpb - 1))];
+  }
+}
+// thread-private array (rows per thread, block-local rows) -> [chain][nb][rows] for tests / factor export
+__global__ void k_unpack_tp(Dims d, int part, int rows, double* __restrict__ out, const double* __restrict__ base,
+                            long long slot_stride, const int* __restrict__ cur) {
+  const int nb = d.nb[part];
+  const long long n = (long long)d.n_chains * nb * rows;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e % rows);
+    const int b = (int)((e / rows) % nb);
+    const int chain = (int)(e / ((long long)rows * nb));
+    const int tile = chain >> d.lcpb, cl = chain & (d.cpb - 1);
+    out[e] = base[cur[chain] * slot_stride + ((long long)tile * rows + r) * d.nta + (b << d.lcpb) + cl];
   }
 }
 
-// full forward scan keeping the states at observation times (generate_x_obs_seq :384-397)
+// full forward scan keeping the states at observation times (generate_x_obs_seq :384-397); one
+// thread per chain walks through the blocks of the tile layout of the current position
 template <class M, int UMAX>
-__global__ void k_gen_xobs(Dims d, const double* __restrict__ q, double* __restrict__ xobs) {
+__global__ void k_gen_xobs(Dims d, Slots S, Work W, int part) {
   const int chain = blockIdx.x * blockDim.x + threadIdx.x;
   if (chain >= d.n_chains) return;
-  constexpr int X = M::X, V = M::V, Z = M::Z;
-  const long long ld = d.ld;
-  const double* qc = q + chain;
-  double u[UMAX], z[Z], dzdu[Z * Z], v0[M::V0], x[X];
-  for (int j = 0; j < d.U; ++j) u[j] = qc[(long long)j * ld];
-  M::gen_z(u, z, dzdu);
-  ldcol<M::V0>(qc + (long long)d.off_v0 * ld, ld, v0);
-  M::gen_x0(z, v0, x);
-  for (int k = 0; k < d.T; ++k) {
-    for (int t = 0; t < d.S; ++t) {
-      double v[V], xn[X];
-      ldcol<V>(qc + ((long long)d.off_v + ((long long)k * d.S + t) * V) * ld, ld, v);
-      M::step(z, d.sd, x, v, xn);
+  constexpr int X = M::X, V = M::V;
+  const int tile = chain >> d.lcpb, cl = chain & (d.cpb - 1);
+  const double* base = S.q + S.cur[chain] * S.s_q;
+  const double* head = base + ((long long)tile * d.rows_head) * d.cpb + cl;
+  double u[UMAX], z[M::Z], dzdu[M::Z * M::Z], v0[M::V0], x[X];
 #pragma unroll
-      for (int i = 0; i < X; ++i) x[i] = xn[i];
+  for (int j = 0; j < UMAX; ++j) u[j] = (j < d.U) ? head[j * d.cpb] : 0.0;
+  M::gen_z(u, z, dzdu);
+  typename M::Coef C;
+  M::make_coef(z, d.sd, C);
+  ldcol<M::V0>(head + d.U * d.cpb, d.cpb, v0);
+  M::gen_x0(z, v0, x);
+  double* xo = W.xobs + ((long long)tile * d.T * X) * d.cpb + cl;
+  for (int b = 0; b < d.nb[part]; ++b) {
+    const Blk B = get_block<M>(d, part, b);
+    const double* body = base + d.off_body + ((long long)tile * d.rows_body) * d.nta + (b << d.lcpb) + cl;
+    for (int k = 0; k < B.n; ++k) {
+      for (int tt = 0; tt < d.S; ++tt) {
+        double v[V], xn[X];
+        ldcol<V>(body + (k * d.S + tt) * V * d.nta, d.nta, v);
+        M::step(C, x, v, xn);
+#pragma unroll
+        for (int i = 0; i < X; ++i) x[i] = xn[i];
+      }
+      stcol<X>(xo + (B.o + k) * X * d.cpb, d.cpb, x);
     }
-    stcol<X>(xobs + chain + (long long)k * X * ld, ld, x);
   }
 }
 
 // find_initial_state_by_linear_interpolation (mici_extensions.py:1479-1547), batched: one thread per
-// (chain, observation interval).  Given u, v_0 and the states at observation times, solves per
-// step for the noise vector that makes the discretised path interpolate linearly between them
-// (forward_func is affine in v; d f / d v square and invertible: X == V).
+// (chain, observation block).  Given u, v_0 (already in the head of q) and the states at observation
+// times, solves per step for the noise vector that makes the discretised path interpolate linearly
+// between them (forward_func is affine in v; d f / d v square and invertible: X == V).
 template <class M, int UMAX>
-__global__ void k_init_interp(Dims d, double* __restrict__ q, const double* __restrict__ xobs) {
+__global__ void k_init_interp(Dims d, Slots S, Work W, int part) {
   constexpr int X = M::X, V = M::V, Z = M::Z;
   static_assert(X == V, "linear-interpolation initialiser needs a square noise Jacobian");
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const int chain = (int)(idx % d.ld);
-  const int k = (int)(idx / d.ld);
-  if (k >= d.T || chain >= d.n_chains) return;
-  const long long ld = d.ld;
-  double* qc = q + chain;
-  double u[UMAX], z[Z], dzdu[Z * Z], xa[X], xb[X];
-  for (int j = 0; j < d.U; ++j) u[j] = qc[(long long)j * ld];
+  const Tid t = thread_id(d);
+  if (!t.act || t.slot >= d.nb[part]) return;
+  const QPtr q = qptr(S.q + S.cur[t.cix] * S.s_q, d, t);
+  const double* xoc = pc(W.xobs, d.T * X, t);
+  double u[UMAX], z[Z], dzdu[Z * Z];
+#pragma unroll
+  for (int j = 0; j < UMAX; ++j) u[j] = (j < d.U) ? q.head[j * t.cpb] : 0.0;
   M::gen_z(u, z, dzdu);
-  if (k == 0) {
-    double v0[M::V0];
-    ldcol<M::V0>(qc + (long long)d.off_v0 * ld, ld, v0);
-    M::gen_x0(z, v0, xa);
-  } else {
-    ldcol<X>(xobs + chain + (long long)(k - 1) * X * ld, ld, xa);
-  }
-  ldcol<X>(xobs + chain + (long long)k * X * ld, ld, xb);
-  double dx[X];
-#pragma unroll
-  for (int i = 0; i < X; ++i) dx[i] = (xb[i] - xa[i]) / d.S;
-  for (int s = 0; s < d.S; ++s) {
-    double x[X], vz[V], m[X], Bm[X * V], rhs[X];
-#pragma unroll
-    for (int i = 0; i < X; ++i) x[i] = xa[i] + s * dx[i];
-#pragma unroll
-    for (int j = 0; j < V; ++j) vz[j] = 0.0;
-    M::step(z, d.sd, x, vz, m);
-    M::jac_v(z, d.sd, x, vz, Bm);
-#pragma unroll
-    for (int i = 0; i < X; ++i) rhs[i] = dx[i] - (m[i] - x[i]);
-    // Gaussian elimination with partial pivoting on the X x X system Bm v = rhs
-    for (int c = 0; c < X; ++c) {
-      int piv = c;
-      for (int r = c + 1; r < X; ++r)
-        if (fabs(Bm[r * V + c]) > fabs(Bm[piv * V + c])) piv = r;
-      if (piv != c) {
-        for (int j = 0; j < V; ++j) { double t = Bm[c * V + j]; Bm[c * V + j] = Bm[piv * V + j]; Bm[piv * V + j] = t; }
-        double t = rhs[c]; rhs[c] = rhs[piv]; rhs[piv] = t;
-      }
-      for (int r = c + 1; r < X; ++r) {
-        const double f = Bm[r * V + c] / Bm[c * V + c];
-        for (int j = c; j < V; ++j) Bm[r * V + j] -= f * Bm[c * V + j];
-        rhs[r] -= f * rhs[c];
-      }
+  typename M::Coef C;
+  M::make_coef(z, d.sd, C);
+  const Blk B = get_block<M>(d, part, t.slot);
+  for (int k = 0; k < B.n; ++k) {
+    double xa[X], xb[X];
+    const int o = B.o + k;
+    if (o == 0) {
+      double v0[M::V0];
+      ldcol<M::V0>(q.head + d.U * t.cpb, t.cpb, v0);
+      M::gen_x0(z, v0, xa);
+    } else {
+      ldcol<X>(xoc + (o - 1) * X * t.cpb, t.cpb, xa);
     }
-    double v[V];
-    for (int r = X - 1; r >= 0; --r) {
-      double t = rhs[r];
-      for (int j = r + 1; j < V; ++j) t -= Bm[r * V + j] * v[j];
-      v[r] = t / Bm[r * V + r];
+    ldcol<X>(xoc + o * X * t.cpb, t.cpb, xb);
+    double dx[X];
+#pragma unroll
+    for (int i = 0; i < X; ++i) dx[i] = (xb[i] - xa[i]) / d.S;
+    for (int s = 0; s < d.S; ++s) {
+      double x[X], vz[V], m[X], Bm[X * V], rhs[X];
+#pragma unroll
+      for (int i = 0; i < X; ++i) x[i] = xa[i] + s * dx[i];
+#pragma unroll
+      for (int j = 0; j < V; ++j) vz[j] = 0.0;
+      M::step(C, x, vz, m);
+      M::jac_v(C, x, vz, Bm);
+#pragma unroll
+      for (int i = 0; i < X; ++i) rhs[i] = dx[i] - (m[i] - x[i]);
+      // Gaussian elimination with partial pivoting on the X x X system Bm v = rhs
+      for (int c = 0; c < X; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < X; ++r)
+          if (fabs(Bm[r * V + c]) > fabs(Bm[piv * V + c])) piv = r;
+        if (piv != c) {
+          for (int j = 0; j < V; ++j) { double tw = Bm[c * V + j]; Bm[c * V + j] = Bm[piv * V + j]; Bm[piv * V + j] = tw; }
+          double tw = rhs[c]; rhs[c] = rhs[piv]; rhs[piv] = tw;
+        }
+        for (int r = c + 1; r < X; ++r) {
+          const double f = Bm[r * V + c] / Bm[c * V + c];
+          for (int j = c; j < V; ++j) Bm[r * V + j] -= f * Bm[c * V + j];
+          rhs[r] -= f * rhs[c];
+        }
+      }
+      double v[V];
+      for (int r = X - 1; r >= 0; --r) {
+        double tw = rhs[r];
+        for (int j = r + 1; j < V; ++j) tw -= Bm[r * V + j] * v[j];
+        v[r] = tw / Bm[r * V + r];
+      }
+      stcol<V>(q.body + (k * d.S + s) * V * t.nta, t.nta, v);
     }
-    stcol<V>(qc + ((long long)d.off_v + ((long long)k * d.S + s) * V) * ld, ld, v);
+    if (d.noisy) q.noise[k * t.nta] = 0.0;
   }
-  if (d.noisy) qc[((long long)d.off_n + k) * ld] = 0.0;
+}
+
+// sample_momentum (:1256-1259), draw part: p = standard normals, Philox-4x32-10 keyed by
+// (seed, offset) with counter (chain, canonical element / 2): the stream does not depend on the
+// tile shape, the partition or the number of GPUs.  One thread per (chain, canonical pair).
+template <class M>
+__global__ void k_philox_momentum(Dims d, int part, double* __restrict__ base, long long slot_stride,
+                                  const int* __restrict__ cur, uint64_t seed, uint64_t offset, int chain0) {
+  const int npair = (d.dim_q + 1) / 2;
+  const long long n = (long long)d.n_chains * npair;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int chain = (int)(e / npair), pr = (int)(e % npair);
+    double a, b;
+    philox_normal_pair(seed, offset, ((uint64_t)(chain0 + chain) << 32) | (uint64_t)pr, &a, &b);
+    double* dst = base + cur[chain] * slot_stride;
+    dst[tile_index<M>(d, part, chain, 2 * pr)] = a;
+    if (2 * pr + 1 < d.dim_q) dst[tile_index<M>(d, part, chain, 2 * pr + 1)] = b;
+  }
 }
 
 // Metropolis accept step of a static-trajectory constrained HMC transition, on device.
 // accept iff the trajectory finished without an integrator error, the final Hamiltonian is finite
 // and log(uniform) < h0 - h1 (Mici MetropolisStaticIntegrationTransition semantics; IntegratorError
 // -> reject).  acc_prob is the `accept_stat` statistic min(1, exp(h0 - h1)).
-__global__ void k_decide(Dims d, Work W, const double* __restrict__ h0, const double* __restrict__ h1,
-                         uint64_t seed, uint64_t offset, int* __restrict__ accepted,
-                         double* __restrict__ acc_prob) {
+// A rejected chain returns to the slot it started the transition in (cur0).
+__global__ void k_decide(Dims d, Slots S, Work W, const double* __restrict__ h0, const double* __restrict__ h1,
+                         const int* __restrict__ cur0, uint64_t seed, uint64_t offset, int chain0,
+                         int* __restrict__ accepted, double* __restrict__ acc_prob) {
   const int chain = blockIdx.x * blockDim.x + threadIdx.x;
   if (chain >= d.n_chains) return;
-  double n0, n1;
-  (void)n1;
-  uint32_t c[4] = {(uint32_t)chain, 0u, (uint32_t)offset, (uint32_t)(offset >> 32)};
+  uint32_t c[4] = {(uint32_t)(chain0 + chain), 0u, (uint32_t)offset, (uint32_t)(offset >> 32)};
   philox4x32_10(c, (uint32_t)seed ^ 0x5bd1e995u, (uint32_t)(seed >> 32));
   const double uu = ((double)((((uint64_t)c[1] << 32) | c[0]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
   const int st = W.status[chain];
@@ -1128,17 +1330,56 @@ __global__ void k_decide(Dims d, Work W, const double* __restrict__ h0, const do
   } else if (st == 0) {
     W.status[chain] = ST_NONFINITE;
   }
-  n0 = ap;
   accepted[chain] = acc;
-  acc_prob[chain] = n0;
+  acc_prob[chain] = ap;
+  (void)S; (void)cur0;
 }
+// restore the position of rejected chains from the copy taken at the start of the transition
 __global__ void k_restore(Dims d, Slots S, const int* __restrict__ accepted, const double* __restrict__ qsave) {
-  const long long n = (long long)d.dim_q * d.ld;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int chain = (int)(i % d.ld);
-    if (chain < d.n_chains && !accepted[chain]) S.q[S.cur[chain] * S.s_q + i] = qsave[i];
+  // qsave holds the start-of-transition position in tile layout (same partition); element e of a
+  // q-like vector belongs to chain (tile(e), cl(e)); decode from the section it falls into
+  const long long n = d.qsize;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    int tile, cl;
+    if (e < d.off_body) {
+      tile = (int)(e / ((long long)d.rows_head * d.cpb));
+      cl = (int)(e % d.cpb);
+    } else if (e < d.off_noise) {
+      const long long r = e - d.off_body;
+      tile = (int)(r / ((long long)d.rows_body * d.nta));
+      cl = (int)(r % d.cpb);
+    } else {
+      const long long r = e - d.off_noise;
+      tile = (int)(r / ((long long)d.rows_noise * d.nta));
+      cl = (int)(r % d.cpb);
+    }
+    const int chain = tile * d.cpb + cl;
+    if (chain < d.n_chains && !accepted[chain]) S.q[S.cur[chain] * S.s_q + e] = qsave[e];
   }
 }
+// snapshot of the current position (tile layout) at the start of a transition
+__global__ void k_snapshot(Dims d, Slots S, double* __restrict__ qsave) {
+  const long long n = d.qsize;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    int tile, cl;
+    if (e < d.off_body) {
+      tile = (int)(e / ((long long)d.rows_head * d.cpb));
+      cl = (int)(e % d.cpb);
+    } else if (e < d.off_noise) {
+      const long long r = e - d.off_body;
+      tile = (int)(r / ((long long)d.rows_body * d.nta));
+      cl = (int)(r % d.cpb);
+    } else {
+      const long long r = e - d.off_noise;
+      tile = (int)(r / ((long long)d.rows_noise * d.nta));
+      cl = (int)(r % d.cpb);
+    }
+    const int chain = tile * d.cpb + cl;
+    qsave[e] = S.q[S.cur[chain < d.n_tiles * d.cpb ? chain : 0] * S.s_q + e];
+  }
+}
+#endif  // __CUDACC__
 
 }  // namespace mmd
