@@ -343,7 +343,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   h->X = Mdl::X; h->V = Mdl::V; h->Z = Mdl::Z; h->V0 = Mdl::V0;
   h->nrmax = NRMAX;
   Dims& d = h->d;
-  d.T = T; d.S = S; d.R = R; d.U = cfg->dim_u;
+  d.T = T; d.S = S; d.R = R; d.U = cfg->dim_u; d.X = Mdl::X; d.V = Mdl::V;
   d.noisy = cfg->noise; d.gaussian = cfg->gaussian_splitting; d.sigma_fixed = cfg->sigma_fixed;
   d.delta = cfg->obs_interval / S;
   d.sd = sqrt(d.delta);

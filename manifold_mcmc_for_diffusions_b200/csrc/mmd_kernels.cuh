@@ -34,6 +34,7 @@ namespace mmd {
 struct Dims {
   int T, S, R;        // num_obs, num_steps_per_obs, num_obs_per_subseq  (mici_extensions.py:317-351)
   int U;              // dim_u
+  int X, V;           // dim_x, dim_v of the model
   int noisy;          // 0 noiseless, 1 fixed sigma, 2 sigma = exp(u[Z])   (generate_sigma, :353-358)
   int gaussian;       // use_gaussian_splitting (:303)
   double sigma_fixed;
@@ -60,7 +61,8 @@ struct Dims {
 
 // q-like vector (q, p, grad log det, work position ...) in tile layout: three sections
 //   head  [tile][rows_head][cpb]   (u, v_0: shared by all blocks of the chain)
-//   body  [tile][rows_body][nta]   (v_t of the thread's block: row (k*S + t)*V + j)
+//   body  [tile][step][nta][V]     (v_t of the thread's block, step = k*S + t: one 16-byte record per
+//                                   thread and step, so a warp reads 32 consecutive records)
 //   noise [tile][rows_noise][nta]  (n_k of the thread's block)
 struct QPtr {
   double* head;
@@ -145,10 +147,20 @@ MMD_D double* pc(double* arr, int rows, const Tid& t) { return arr + ((long long
 MMD_D const double* pc(const double* arr, int rows, const Tid& t) {
   return arr + ((long long)t.tile * rows) * t.cpb + t.cl;
 }
+// per-step record arrays [tile][step][nta][W]: record `s` of the thread at tpr<W>(...)[s * W * nta + c]
+template <int W>
+MMD_D double* tpr(double* arr, int rows, const Tid& t) {
+  return arr + ((long long)t.tile * rows) * t.nta + t.tid * W;
+}
+template <int W>
+MMD_D const double* tpr(const double* arr, int rows, const Tid& t) {
+  return arr + ((long long)t.tile * rows) * t.nta + t.tid * W;
+}
+template <class M>
 MMD_D QPtr qptr(double* base, const Dims& d, const Tid& t) {
   QPtr q;
   q.head = pc(base, d.rows_head, t);
-  q.body = tp(base + d.off_body, d.rows_body, t);
+  q.body = tpr<M::V>(base + d.off_body, d.rows_body, t);
   q.noise = tp(base + d.off_noise, d.rows_noise, t);
   return q;
 }
@@ -233,6 +245,31 @@ template <int N>
 MMD_D void stcol(double* g, int ld, const double* r) {
 #pragma unroll
   for (int i = 0; i < N; ++i) g[i * ld] = r[i];
+}
+// contiguous N-double record (16-byte aligned when N is even): vector loads / stores
+template <int N>
+MMD_D void ldrec(const double* g, double* r) {
+  if (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const double2 v = reinterpret_cast<const double2*>(g)[i];
+      r[2 * i] = v.x;
+      r[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = g[i];
+  }
+}
+template <int N>
+MMD_D void strec(double* g, const double* r) {
+  if (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) reinterpret_cast<double2*>(g)[i] = make_double2(r[2 * i], r[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = r[i];
+  }
 }
 MMD_D int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // packed lower index, j <= i
 

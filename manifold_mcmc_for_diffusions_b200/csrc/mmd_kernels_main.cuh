@@ -10,7 +10,7 @@ namespace mmd {
 template <class M, int NRMAX, int UMAX>
 struct SmemPlan {
   static constexpr int NRED = UMAX * (UMAX + 1) / 2 + 1;
-  static constexpr int NRING = (MMD_PREFETCH_STEPS + 1) * (M::V + M::X * M::V);
+  static constexpr int NRING = (MMD_PREFETCH_STEPS + 1) * RingRec<M>::NWP;
   static constexpr int NSCR = NRED > NRING ? NRED : NRING;
   static constexpr int PER_THREAD = NSCR + 2 * NRMAX;  // doubles per thread
 };
@@ -19,7 +19,7 @@ struct SmemPlan {
   extern __shared__ double smem[];                                      \
   const int NT = t.nslot * t.cpb;                                       \
   double* const sm_red = smem;                                          \
-  double* const sm_ring = smem + t.tid;                                 \
+  double* const sm_ring = smem;                                         \
   double* const sm_c = smem + SmemPlan<M, NRMAX, UMAX>::NSCR * NT + t.tid; \
   double* const sm_l = sm_c + NRMAX * NT;                               \
   (void)sm_red; (void)sm_ring; (void)sm_c; (void)sm_l;
@@ -41,9 +41,9 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
   const int cur = S.cur[t.cix];
   const int sl = which ? 1 - cur : cur;
   const bool skip = !t.act || (W.status[t.cix] != 0);
-  const QPtr q = qptr(S.q + sl * S.s_q, d, t);
-  const QPtr gq = qptr(S.gradld + sl * S.s_q, d, t);
-  double* Kc = tp(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
+  const QPtr q = qptr<M>(S.q + sl * S.s_q, d, t);
+  const QPtr gq = qptr<M>(S.gradld + sl * S.s_q, d, t);
+  double* Kc = tpr<XV>(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
   double* Psibc = tp(S.Psib + sl * S.s_Psib, d.rmax * X * X, t);
   double* xendc = tp(S.xend + sl * S.s_xend, d.rmax * X, t);
   double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
@@ -51,7 +51,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
   double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
   double* LCc = pc(S.LC + sl * S.s_LC, UTRI, t);
   const double* xoc = pc(W.xobs, d.T * X, t);
-  double* xsc = tp(W.xs, d.rmax * d.S * X, t);
+  double* xsc = tpr<X>(W.xs, d.rmax * d.S * X, t);
   double* Qc = tp(W.Qk, d.rmax * X * X, t);
   double* Ztc = tp(W.Zt, d.rmax * X * Z, t);
 
@@ -86,9 +86,9 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       const double* vp = q.body + k * d.S * V * nta;
       double* xk = xsc + k * d.S * X * nta;
       for (int tt = 0; tt < d.S; ++tt) {
-        stcol<X>(xk + tt * X * nta, nta, x);
+        strec<X>(xk + tt * X * nta, x);
         double v[V], xn[X];
-        ldcol<V>(vp + tt * V * nta, nta, v);
+        ldrec<V>(vp + tt * V * nta, v);
         M::step(P.C, x, v, xn);
 #pragma unroll
         for (int i = 0; i < X; ++i) x[i] = xn[i];
@@ -102,13 +102,13 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       double* Kk = Kc + k * d.S * XV * nta;
       for (int tt = d.S - 1; tt >= 0; --tt) {
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], tmp[X * X];
-        ldcol<X>(xk + tt * X * nta, nta, xt);
-        ldcol<V>(vp + tt * V * nta, nta, v);
+        ldrec<X>(xk + tt * X * nta, xt);
+        ldrec<V>(vp + tt * V * nta, v);
         M::jac_x(P.C, xt, v, F);
         M::jac_v(P.C, xt, v, Bm);
         M::jac_z(P.C, xt, v, G);
         mm<X, V, X>(Psi, Bm, Kt);
-        stcol<XV>(Kk + tt * XV * nta, nta, Kt);
+        strec<XV>(Kk + tt * XV * nta, Kt);
         // Qk += Kt Kt^T ; Zk += Psi G ; Psi = Psi F
 #pragma unroll
         for (int i = 0; i < X; ++i)
@@ -401,7 +401,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
     for (int i = 0; i < X; ++i) gam[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < Z; ++i) gz[i] = 0.0;
-    double* Ywc = tp(W.Yw, d.rmax * d.S * X * X, t);
+    double* Ywc = tpr<X * X>(W.Yw, d.rmax * d.S * X * X, t);
     for (int k = B.n - 1; k >= 0; --k) {
       const double* vp = q.body + k * d.S * V * nta;
       const double* xk = xsc + k * d.S * X * nta;
@@ -417,11 +417,11 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
         // (handled through obs_hess in the adjoint start below)
       }
       for (int tt = 0; tt < d.S; ++tt) {
-        stcol<X * X>(Yk + tt * X * X * nta, nta, Y);
+        strec<X * X>(Yk + tt * X * X * nta, Y);
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], KM[V * X], Yn[X * X];
-        ldcol<X>(xk + tt * X * nta, nta, xt);
-        ldcol<V>(vp + tt * V * nta, nta, v);
-        ldcol<XV>(Kk + tt * XV * nta, nta, Kt);
+        ldrec<X>(xk + tt * X * nta, xt);
+        ldrec<V>(vp + tt * V * nta, v);
+        ldrec<XV>(Kk + tt * XV * nta, Kt);
         M::jac_x(P.C, xt, v, F);
         M::jac_v(P.C, xt, v, Bm);
         M::jac_z(P.C, xt, v, G);
@@ -437,9 +437,9 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       for (int i = 0; i < X * X; ++i) Psi[i] = (i % (X + 1) == 0) ? 1.0 : 0.0;
       for (int tt = d.S - 1; tt >= 0; --tt) {
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], Yt[X * X];
-        ldcol<X>(xk + tt * X * nta, nta, xt);
-        ldcol<V>(vp + tt * V * nta, nta, v);
-        ldcol<X * X>(Yk + tt * X * X * nta, nta, Yt);
+        ldrec<X>(xk + tt * X * nta, xt);
+        ldrec<V>(vp + tt * V * nta, v);
+        ldrec<X * X>(Yk + tt * X * X * nta, Yt);
         M::jac_x(P.C, xt, v, F);
         M::jac_v(P.C, xt, v, Bm);
         M::jac_z(P.C, xt, v, G);
@@ -454,7 +454,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
         mtv<X, V>(Bm, gam, gv);
 #pragma unroll
         for (int j = 0; j < V; ++j) gv[j] += g[X + j];
-        stcol<V>(gk + tt * V * nta, nta, gv);
+        strec<V>(gk + tt * V * nta, gv);
         mtv<X, Z>(G, gam, tz);
 #pragma unroll
         for (int m = 0; m < Z; ++m) gz[m] += tz[m] + g[X + V + m];
@@ -508,7 +508,7 @@ MMD_D void dev_constr(const Dims& d, const Slots& S, const Work& W, const double
   constexpr int X = M::X;
   if (t.slot >= d.nb[part]) return;
   const int cur = S.cur[t.cix];
-  const QPtr q = qptr(S.q + cur * S.s_q, d, t);
+  const QPtr q = qptr<M>(S.q + cur * S.s_q, d, t);
   ChainPar<M, UMAX> P;
   {
     double u[UMAX];
@@ -521,8 +521,16 @@ MMD_D void dev_constr(const Dims& d, const Slots& S, const Work& W, const double
   double x[X], v0[M::V0];
   ldcol<M::V0>(q.head + d.U * t.cpb, t.cpb, v0);
   block_start<M>(d, B, P.z, v0, xoc, t.cpb, x);
-  constr_sweep<M, false>(d, B, P.C, P.sigy, 0.0, x, q.body, q.noise, xoc, y, nullptr, nullptr, nullptr, t.nta,
-                         t.cpb, NT, sm_c, sm_ring, nullptr);
+  {
+    SweepArgs<M> a;
+    a.C = P.C; a.sigma_y = P.sigy; a.sigma_lin = 0.0;
+#pragma unroll
+    for (int i = 0; i < X; ++i) a.xstart[i] = x[i];
+    a.vb = q.body; a.nzb = q.noise; a.xoc = xoc; a.y = y; a.Kb = nullptr; a.alph = nullptr; a.lamtot = nullptr;
+    a.crow = sm_c; a.ring = sm_ring; a.xend_out = nullptr;
+    a.nta = t.nta; a.cpb = t.cpb; a.NT = NT; a.tid = t.tid;
+    constr_sweep<M, false>(d, B, a);
+  }
   double* co = tp(cout, NRMAX, t);
   for (int r = 0; r < B.nrows; ++r) co[r * t.nta] = sm_c[r * NT];
 }
@@ -558,12 +566,12 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
   auto psel = [&](int sel) -> double* {
     return sel == PSEL_WORK ? W.pw : S.p + (sel == PSEL_OTHER ? 1 - cur : cur) * S.s_q;
   };
-  const QPtr q = qptr(S.q + sl * S.s_q, d, t);
-  const QPtr g = qptr(S.gradld + sl * S.s_q, d, t);
-  const QPtr ps = qptr(psel(src_sel), d, t);
-  const QPtr pd = qptr(psel(dst_sel), d, t);
-  const QPtr qw = qptr(W.qw, d, t);
-  const double* Kc = tp(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
+  const QPtr q = qptr<M>(S.q + sl * S.s_q, d, t);
+  const QPtr g = qptr<M>(S.gradld + sl * S.s_q, d, t);
+  const QPtr ps = qptr<M>(psel(src_sel), d, t);
+  const QPtr pd = qptr<M>(psel(dst_sel), d, t);
+  const QPtr qw = qptr<M>(W.qw, d, t);
+  const double* Kc = tpr<XV>(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
   const double* Psibc = tp(S.Psib + sl * S.s_Psib, d.rmax * X * X, t);
   const double* xendc = tp(S.xend + sl * S.s_xend, d.rmax * X, t);
   const double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
@@ -618,22 +626,23 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
     }
     // pass 1: r = J p'  (lmult_by_jacob_constr :822-877); p' written to dst when it differs from src
     for (int k = 0; k < B.n; ++k) {
-      const int r0 = k * d.S * V;
       double sk[X];
 #pragma unroll
       for (int i = 0; i < X; ++i) sk[i] = 0.0;
-#pragma unroll 5
+#pragma unroll 4
       for (int tt = 0; tt < d.S; ++tt) {
+        const int so = (k * d.S + tt) * nta;
         double Kt[XV], pv[V];
-        ldcol<XV>(Kc + (k * d.S + tt) * XV * nta, nta, Kt);
+        ldrec<XV>(Kc + so * XV, Kt);
+        ldrec<V>(ps.body + so * V, pv);
+        if (kick) {
+          double qv[V], gv[V];
+          ldrec<V>(q.body + so * V, qv);
+          ldrec<V>(g.body + so * V, gv);
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const int row = (r0 + tt * V + j) * nta;
-          double p1 = ps.body[row];
-          if (kick) p1 -= h * (qcoef * q.body[row] + g.body[row]);
-          if (write1) pd.body[row] = p1;
-          pv[j] = p1;
+          for (int j = 0; j < V; ++j) pv[j] -= h * (qcoef * qv[j] + gv[j]);
         }
+        if (write1) strec<V>(pd.body + so * V, pv);
 #pragma unroll
         for (int i = 0; i < X; ++i)
 #pragma unroll
@@ -676,26 +685,29 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
     for (int i = 0; i < NRMAX; ++i) sm_c[i * NT] = rr[i];
     alpha_block<M, NRMAX, RMAXP>(B, rr, Psibc, xendc, nta, alph, a0);
     for (int k = 0; k < B.n; ++k) {
-      const int r0 = k * d.S * V;
       double al[X];
       ldcol<X>(alph + k * X * nta, nta, al);
-#pragma unroll 5
+#pragma unroll 4
       for (int tt = 0; tt < d.S; ++tt) {
-        double Kt[XV];
-        ldcol<XV>(Kc + (k * d.S + tt) * XV * nta, nta, Kt);
+        const int so = (k * d.S + tt) * nta;
+        double Kt[XV], pv[V];
+        ldrec<XV>(Kc + so * XV, Kt);
+        ldrec<V>((write1 ? pd.body : ps.body) + so * V, pv);
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const int row = (r0 + tt * V + j) * nta;
-          double pv = write1 ? pd.body[row] : ps.body[row];
+        for (int j = 0; j < V; ++j)
 #pragma unroll
-          for (int i = 0; i < X; ++i) pv = fma(-Kt[i * V + j], al[i], pv);
-          if (fl.mode) {
-            const double qv = q.body[row];
-            qw.body[row] = fl.fq * qv + fl.fp * pv;
-            if (fl.mode == 2) pv = fl.fq * pv - fl.fpm * qv;
+          for (int i = 0; i < X; ++i) pv[j] = fma(-Kt[i * V + j], al[i], pv[j]);
+        if (fl.mode) {
+          double qv[V], qo[V];
+          ldrec<V>(q.body + so * V, qv);
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            qo[j] = fl.fq * qv[j] + fl.fp * pv[j];
+            if (fl.mode == 2) pv[j] = fl.fq * pv[j] - fl.fpm * qv[j];
           }
-          pd.body[row] = pv;
+          strec<V>(qw.body + so * V, qo);
         }
+        strec<V>(pd.body + so * V, pv);
       }
       if (d.noisy) {
         double pv = write1 ? pd.noise[k * nta] : ps.noise[k * nta];
@@ -755,15 +767,15 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
   const int U = d.U, nta = t.nta, cpb = t.cpb;
   const int cur = S.cur[t.cix];
   const int sl = mode ? 1 - cur : cur;  // linearisation used: forward -> cur (prev point), reverse -> new point
-  const double* Kc = tp(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
+  const double* Kc = tpr<XV>(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
   const double* Psibc = tp(S.Psib + sl * S.s_Psib, d.rmax * X * X, t);
   const double* xendc = tp(S.xend + sl * S.s_xend, d.rmax * X, t);
   const double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
   const double* DinvAc = tp(S.DinvA + sl * S.s_A, NRMAX * U, t);
   const double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
   const double* LCc = pc(S.LC + sl * S.s_LC, UTRI, t);
-  const QPtr qw = qptr(W.qw, d, t);
-  const QPtr qlin = qptr(S.q + sl * S.s_q, d, t);
+  const QPtr qw = qptr<M>(W.qw, d, t);
+  const QPtr qlin = qptr<M>(S.q + sl * S.s_q, d, t);
   const double* xoc = pc(W.xobs, d.T * X, t);
   double* alph = tp(W.alpha, d.rmax * X, t);
   double* alphi = tp(W.alphi, d.rmax * X, t);
@@ -820,8 +832,16 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
         for (int j = 0; j < M::V0; ++j) v0[j] -= t0[j];
       }
       block_start<M>(d, B, P.z, v0, xoc, cpb, x);
-      constr_sweep<M, true>(d, B, P.C, P.sigy, sig_lin, x, qw.body, qw.noise, xoc, y, Kc, alph, sm_l, nta, cpb, NT,
-                            sm_c, sm_ring, nullptr);
+      {
+        SweepArgs<M> a;
+        a.C = P.C; a.sigma_y = P.sigy; a.sigma_lin = sig_lin;
+#pragma unroll
+        for (int i = 0; i < X; ++i) a.xstart[i] = x[i];
+        a.vb = qw.body; a.nzb = qw.noise; a.xoc = xoc; a.y = y; a.Kb = Kc; a.alph = alph; a.lamtot = sm_l;
+        a.crow = sm_c; a.ring = sm_ring; a.xend_out = nullptr;
+        a.nta = nta; a.cpb = cpb; a.NT = NT; a.tid = t.tid;
+        constr_sweep<M, true>(d, B, a);
+      }
     }
     double rr[NRMAX];
     {
@@ -834,6 +854,9 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
       }
       err = e;
     }
+    // the prefetch ring of the sweep and the reduction scratch share shared memory: every thread must have
+    // left its sweep before any thread starts the cross-block reduction
+    __syncthreads();
     inv_gram_block<M, NRMAX, UMAX>(d, B, work, Ac, Lc, DinvAc, LCc, rr, sres, &err, sm_red, t);
     // norm of this iteration's update and (speculative) finalisation when the constraint is met
     const bool check = !done && (err < ctol);
@@ -856,19 +879,21 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
         double a0inc[X];
         alpha_block<M, NRMAX, RMAXP>(B, rr, Psibc, xendc, nta, alphi, a0inc);
         double nm = 0.0, rv = 0.0;
-        const QPtr qout = qptr(S.q + (1 - cur) * S.s_q, d, t);
-        const QPtr pout = qptr(S.p + (1 - cur) * S.s_q, d, t);
-        const QPtr pin = qptr(W.pw, d, t);
-        const QPtr qref = qptr(S.q + cur * S.s_q, d, t);
+        const QPtr qout = qptr<M>(S.q + (1 - cur) * S.s_q, d, t);
+        const QPtr pout = qptr<M>(S.p + (1 - cur) * S.s_q, d, t);
+        const QPtr pin = qptr<M>(W.pw, d, t);
+        const QPtr qref = qptr<M>(S.q + cur * S.s_q, d, t);
         for (int k = 0; k < B.n; ++k) {
-          const int r0 = k * d.S * V;
           double al[X], ai[X];
           ldcol<X>(alph + k * X * nta, nta, al);
           ldcol<X>(alphi + k * X * nta, nta, ai);
-#pragma unroll 5
+#pragma unroll 4
           for (int tt = 0; tt < d.S; ++tt) {
-            double Kt[XV];
-            ldcol<XV>(Kc + (k * d.S + tt) * XV * nta, nta, Kt);
+            const int so = (k * d.S + tt) * nta;
+            double Kt[XV], qv[V], ov[V], pv[V];
+            ldrec<XV>(Kc + so * XV, Kt);
+            ldrec<V>(qw.body + so * V, qv);
+            ldrec<V>((mode == 0 ? pin.body : qref.body) + so * V, ov);
 #pragma unroll
             for (int j = 0; j < V; ++j) {
               double mu = 0.0, inc = 0.0;
@@ -878,14 +903,13 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
                 inc = fma(Kt[i * V + j], ai[i], inc);
               }
               nm = fmax(nm, fabs(inc));
-              const int row = (r0 + tt * V + j) * nta;
-              const double qn = qw.body[row] - mu;
-              if (mode == 0) {
-                qout.body[row] = qn;
-                pout.body[row] = fma(-mom_coef, mu, pin.body[row]);
-              } else {
-                rv = fmax(rv, fabs(qn - qref.body[row]));
-              }
+              qv[j] -= mu;
+              if (mode == 0) pv[j] = fma(-mom_coef, mu, ov[j]);
+              else rv = fmax(rv, fabs(qv[j] - ov[j]));
+            }
+            if (mode == 0) {
+              strec<V>(qout.body + so * V, qv);
+              strec<V>(pout.body + so * V, pv);
             }
           }
           if (d.noisy) {
@@ -1061,16 +1085,19 @@ __global__ void k_hamiltonian(Dims d, Slots S, Work W, int part, int sel, double
   extern __shared__ double smem[];
   const int cur = S.cur[t.cix];
   const int sl = sel ? 1 - cur : cur;
-  const QPtr q = qptr(S.q + sl * S.s_q, d, t);
-  const QPtr p = qptr(S.p + sl * S.s_q, d, t);
+  const QPtr q = qptr<M>(S.q + sl * S.s_q, d, t);
+  const QPtr p = qptr<M>(S.p + sl * S.s_q, d, t);
   double acc[1];
   acc[0] = 0.0;
   if (t.slot < d.nb[part]) {
     const Blk B = get_block<M>(d, part, t.slot);
-    const int nrow = B.n * d.S * M::V;
-    for (int r = 0; r < nrow; ++r) {
-      const double a = q.body[r * t.nta], b = p.body[r * t.nta];
-      acc[0] += 0.5 * a * a + 0.5 * b * b;
+    const int nstep = B.n * d.S;
+    for (int s = 0; s < nstep; ++s) {
+      double a[M::V], b[M::V];
+      ldrec<M::V>(q.body + s * M::V * t.nta, a);
+      ldrec<M::V>(p.body + s * M::V * t.nta, b);
+#pragma unroll
+      for (int j = 0; j < M::V; ++j) acc[0] += 0.5 * a[j] * a[j] + 0.5 * b[j] * b[j];
     }
     if (d.noisy)
       for (int k = 0; k < B.n; ++k) {
@@ -1095,26 +1122,18 @@ template <class M>
 MMD_D long long tile_index(const Dims& d, int part, int chain, int i) {
   const int tile = chain >> d.lcpb, cl = chain & (d.cpb - 1);
   if (i < d.off_v) return ((long long)tile * d.rows_head + i) * d.cpb + cl;
-  int b, row;
-  long long off;
-  int rows;
   if (i < d.off_n) {
     const int g = (i - d.off_v) / M::V, j = (i - d.off_v) % M::V;
     const int o = g / d.S, tt = g % d.S;
-    b = block_of_obs(d, part, o);
+    const int b = block_of_obs(d, part, o);
     const Blk B = get_block<M>(d, part, b);
-    row = ((o - B.o) * d.S + tt) * M::V + j;
-    off = d.off_body;
-    rows = d.rows_body;
-  } else {
-    const int o = i - d.off_n;
-    b = block_of_obs(d, part, o);
-    const Blk B = get_block<M>(d, part, b);
-    row = o - B.o;
-    off = d.off_noise;
-    rows = d.rows_noise;
+    const int s = (o - B.o) * d.S + tt;
+    return d.off_body + ((long long)tile * d.rows_body + s * M::V) * d.nta + ((b << d.lcpb) + cl) * M::V + j;
   }
-  return off + ((long long)tile * rows + row) * d.nta + (b << d.lcpb) + cl;
+  const int o = i - d.off_n;
+  const int b = block_of_obs(d, part, o);
+  const Blk B = get_block<M>(d, part, b);
+  return d.off_noise + ((long long)tile * d.rows_noise + (o - B.o)) * d.nta + (b << d.lcpb) + cl;
 }
 // per-chain slot selection: sel 0 cur, 1 other, 2 none (base used as is)
 template <class M>
@@ -1203,11 +1222,11 @@ __global__ void k_gen_xobs(Dims d, Slots S, Work W, int part) {
   double* xo = W.xobs + ((long long)tile * d.T * X) * d.cpb + cl;
   for (int b = 0; b < d.nb[part]; ++b) {
     const Blk B = get_block<M>(d, part, b);
-    const double* body = base + d.off_body + ((long long)tile * d.rows_body) * d.nta + (b << d.lcpb) + cl;
+    const double* body = base + d.off_body + ((long long)tile * d.rows_body) * d.nta + ((b << d.lcpb) + cl) * V;
     for (int k = 0; k < B.n; ++k) {
       for (int tt = 0; tt < d.S; ++tt) {
         double v[V], xn[X];
-        ldcol<V>(body + (k * d.S + tt) * V * d.nta, d.nta, v);
+        ldrec<V>(body + (k * d.S + tt) * V * d.nta, v);
         M::step(C, x, v, xn);
 #pragma unroll
         for (int i = 0; i < X; ++i) x[i] = xn[i];
@@ -1227,7 +1246,7 @@ __global__ void k_init_interp(Dims d, Slots S, Work W, int part) {
   static_assert(X == V, "linear-interpolation initialiser needs a square noise Jacobian");
   const Tid t = thread_id(d);
   if (!t.act || t.slot >= d.nb[part]) return;
-  const QPtr q = qptr(S.q + S.cur[t.cix] * S.s_q, d, t);
+  const QPtr q = qptr<M>(S.q + S.cur[t.cix] * S.s_q, d, t);
   const double* xoc = pc(W.xobs, d.T * X, t);
   double u[UMAX], z[Z], dzdu[Z * Z];
 #pragma unroll
@@ -1281,7 +1300,7 @@ __global__ void k_init_interp(Dims d, Slots S, Work W, int part) {
         for (int j = r + 1; j < V; ++j) tw -= Bm[r * V + j] * v[j];
         v[r] = tw / Bm[r * V + r];
       }
-      stcol<V>(q.body + (k * d.S + s) * V * t.nta, t.nta, v);
+      strec<V>(q.body + (k * d.S + s) * V * t.nta, v);
     }
     if (d.noisy) q.noise[k * t.nta] = 0.0;
   }
@@ -1348,7 +1367,7 @@ __global__ void k_restore(Dims d, Slots S, const int* __restrict__ accepted, con
     } else if (e < d.off_noise) {
       const long long r = e - d.off_body;
       tile = (int)(r / ((long long)d.rows_body * d.nta));
-      cl = (int)(r % d.cpb);
+      cl = (int)(((r % (d.V * d.nta)) / d.V) % d.cpb);
     } else {
       const long long r = e - d.off_noise;
       tile = (int)(r / ((long long)d.rows_noise * d.nta));
@@ -1370,7 +1389,7 @@ __global__ void k_snapshot(Dims d, Slots S, double* __restrict__ qsave) {
     } else if (e < d.off_noise) {
       const long long r = e - d.off_body;
       tile = (int)(r / ((long long)d.rows_body * d.nta));
-      cl = (int)(r % d.cpb);
+      cl = (int)(((r % (d.V * d.nta)) / d.V) % d.cpb);
     } else {
       const long long r = e - d.off_noise;
       tile = (int)(r / ((long long)d.rows_noise * d.nta));

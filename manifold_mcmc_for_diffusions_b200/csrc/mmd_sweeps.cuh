@@ -36,102 +36,161 @@ MMD_D void block_start(const Dims& d, const Blk& B, const double* z, const doubl
 }
 
 // ------------------------------------------------------------------------------------------
-// asynchronous global -> shared copies (LDGSTS): the sweeps prefetch the rows of future time steps into a
-// thread-private shared-memory ring, so the recursion never waits on HBM and no registers are spent
-// on data in flight
+// asynchronous global -> shared copies (LDGSTS): the sweeps prefetch the records of future time steps
+// into a thread-private shared-memory ring, so the recursion never waits on HBM and no registers are
+// spent on data in flight.  Shared addresses are 32-bit window offsets computed once per sweep.
 // ------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-MMD_D void cp_async8(double* smem_dst, const double* gsrc) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+MMD_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int BYTES>
+MMD_D void cp_async(unsigned sdst, const void* gsrc) {
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst), "l"(gsrc) : "memory");
 }
 MMD_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 MMD_D void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// copy an N-double record (16-byte pieces when N is even)
+template <int N>
+MMD_D void cp_async_rec(unsigned sdst, const double* gsrc) {
+  if (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) cp_async<16>(sdst + 16 * i, gsrc + 2 * i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) cp_async<8>(sdst + 8 * i, gsrc + i);
+  }
+}
+template <int N>
+MMD_D void lds_rec(unsigned saddr, double* r) {
+  if (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i)
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(r[2 * i]), "=d"(r[2 * i + 1]) : "r"(saddr + 16 * i) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(r[i]) : "r"(saddr + 8 * i) : "memory");
+  }
+}
 #endif
+
+// ring record per thread and slot: [v (V) | K (X*V)], padded to an even number of doubles
+template <class M>
+struct RingRec {
+  static constexpr int NW = M::V + M::X * M::V;
+  static constexpr int NWP = (NW + 1) / 2 * 2;
+};
 
 // ------------------------------------------------------------------------------------------
 // forward constraint sweep for one block:  c_b(q)   (generate_y_bar + constr, :399-411, :473-519).
 // With WITH_K the position is the quasi-Newton parametrisation q = qw - J_lin^T lambda_tot, never
 // materialised:   v_t = qw_v[t] - K_t^T alpha_k ,  n_k = qw_n[k] - sigma_lin * lambda_tot[k].
-// The rows of step s + PF are fetched by cp.async into a shared-memory ring while step s is computed
-// (the loads do not depend on the recursion; the sweep would otherwise be bound by global-load
-// latency).  ring: thread-private, word w of ring slot i at ring[(i * NW + w) * NT].
+// The records of step s + PF are fetched by cp.async into a shared-memory ring while step s is
+// computed (the loads do not depend on the recursion; the sweep would otherwise be bound by
+// global-load latency).  ring: CTA ring base; slot i of thread tid at ring[(i * NT + tid) * NWP].
 // crow / lamtot are thread-private columns in shared memory: element r at [r * NT].
+// Not inlined on purpose: the loop gets its own register allocation, independent of what the caller
+// keeps alive across the sweep.
 // ------------------------------------------------------------------------------------------
+template <class M>
+struct SweepArgs {
+  typename M::Coef C;
+  double sigma_y, sigma_lin;
+  double xstart[M::X];
+  const double* vb;      // q-like body records of the block (V per step)
+  const double* nzb;     // noise column
+  const double* xoc;     // per-chain x_obs_seq column
+  const double* y;
+  const double* Kb;      // compressed Jacobian records (X*V per step)
+  const double* alph;    // thread-private alpha column [rmax*X]
+  const double* lamtot;  // shared-memory column
+  double* crow;          // shared-memory column (out)
+  double* ring;          // CTA ring base (shared)
+  double* xend_out;      // thread-private [rmax*X] or null
+  int nta, cpb, NT, tid;
+};
+
 template <class M, bool WITH_K>
-MMD_D void constr_sweep(const Dims& d, const Blk& B, const typename M::Coef& C, double sigma_y, double sigma_lin,
-                        const double* xstart, const double* __restrict__ vb, const double* __restrict__ nzb,
-                        const double* __restrict__ xoc, const double* __restrict__ y,
-                        const double* __restrict__ Kb, const double* __restrict__ alph, const double* lamtot,
-                        int nta, int cpb, int NT, double* crow, double* ring, double* xend_out) {
+__device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const SweepArgs<M>& a) {
   constexpr int X = M::X, V = M::V, XV = M::X * M::V;
-  constexpr int PF = MMD_PREFETCH_STEPS, NSL = PF + 1, NW = V + (WITH_K ? XV : 0);
-  const int ns = B.n * d.S;
+  constexpr int PF = MMD_PREFETCH_STEPS, NSL = PF + 1, NWP = RingRec<M>::NWP;
+  const int ns = B.n * d.S, nta = a.nta, NT = a.NT, S = d.S;
+  const typename M::Coef C = a.C;
   double x[X];
 #pragma unroll
-  for (int i = 0; i < X; ++i) x[i] = xstart[i];
-  auto issue = [&](int s, int slot) {
-    double* dst = ring + slot * NW * NT;
-#pragma unroll
-    for (int j = 0; j < V; ++j) cp_async8(dst + j * NT, vb + (s * V + j) * nta);
-    if (WITH_K) {
-#pragma unroll
-      for (int j = 0; j < XV; ++j) cp_async8(dst + (V + j) * NT, Kb + (s * XV + j) * nta);
-    }
-  };
+  for (int i = 0; i < X; ++i) x[i] = a.xstart[i];
+  const unsigned ring0 = smem_u32(a.ring) + (unsigned)a.tid * (NWP * 8);
+  const unsigned sstride = (unsigned)NT * (NWP * 8);
+  const unsigned ring_end = ring0 + NSL * sstride;
+  const double* vp = a.vb;   // next record to fetch
+  const double* Kp = a.Kb;
+  const int vbump = V * nta, Kbump = XV * nta;
+  unsigned wr = ring0;
 #pragma unroll
   for (int i = 0; i < PF; ++i) {
-    if (i < ns) issue(i, i);
+    if (i < ns) {
+      cp_async_rec<V>(wr, vp);
+      if (WITH_K) cp_async_rec<XV>(wr + V * 8, Kp);
+      vp += vbump;
+      Kp += Kbump;
+    }
     cp_async_commit();
+    wr += sstride;
   }
+  unsigned rd = ring0;
   double al[X];
-  if (WITH_K) ldcol<X>(alph, nta, al);
-  int k = 0, t = 0, slot = 0, fill = PF;
+  if (WITH_K) ldcol<X>(a.alph, nta, al);
+  int k = 0, t = 0;
   for (int s = 0; s < ns; ++s) {
     cp_async_wait<PF - 1>();
-    const double* src = ring + slot * NW * NT;
     double v[V], xn[X];
-#pragma unroll
-    for (int j = 0; j < V; ++j) v[j] = src[j * NT];
+    lds_rec<V>(rd, v);
     if (WITH_K) {
       double Kt[XV];
-#pragma unroll
-      for (int j = 0; j < XV; ++j) Kt[j] = src[(V + j) * NT];
+      lds_rec<XV>(rd + V * 8, Kt);
 #pragma unroll
       for (int j = 0; j < V; ++j)
 #pragma unroll
-        for (int a = 0; a < X; ++a) v[j] = fma(-Kt[a * V + j], al[a], v[j]);
+        for (int i = 0; i < X; ++i) v[j] = fma(-Kt[i * V + j], al[i], v[j]);
     }
-    if (s + PF < ns) issue(s + PF, fill);  // the slot consumed one step ago
+    if (s + PF < ns) {  // refill the slot consumed one step ago
+      cp_async_rec<V>(wr, vp);
+      if (WITH_K) cp_async_rec<XV>(wr + V * 8, Kp);
+      vp += vbump;
+      Kp += Kbump;
+    }
     cp_async_commit();
-    slot = (slot + 1 == NSL) ? 0 : slot + 1;
-    fill = (fill + 1 == NSL) ? 0 : fill + 1;
+    rd += sstride;
+    if (rd == ring_end) rd = ring0;
+    wr += sstride;
+    if (wr == ring_end) wr = ring0;
     M::step(C, x, v, xn);
 #pragma unroll
-    for (int a = 0; a < X; ++a) x[a] = xn[a];
-    if (++t == d.S) {  // end of observation interval k
+    for (int i = 0; i < X; ++i) x[i] = xn[i];
+    if (++t == S) {  // end of observation interval k
       t = 0;
-      if (xend_out) stcol<X>(xend_out + k * X * nta, nta, x);
+      if (a.xend_out) stcol<X>(a.xend_out + k * X * nta, nta, x);
       if (k < B.ny) {
-        double cy = M::obs(x) - y[B.o + k];
+        double cy = M::obs(x) - a.y[B.o + k];
         if (d.noisy) {
-          double nk = nzb[k * nta];
-          if (WITH_K) nk = fma(-sigma_lin, lamtot[k * NT], nk);
-          cy = fma(sigma_y, nk, cy);
+          double nk = a.nzb[k * nta];
+          if (WITH_K) nk = fma(-a.sigma_lin, a.lamtot[k * NT], nk);
+          cy = fma(a.sigma_y, nk, cy);
         }
-        crow[k * NT] = cy;
+        a.crow[k * NT] = cy;
       }
       if (k == B.n - 1 && B.nx > 0) {
         double xo[X];
-        ldcol<X>(xoc + (B.o + k) * X * cpb, cpb, xo);
+        ldcol<X>(a.xoc + (B.o + k) * X * a.cpb, a.cpb, xo);
 #pragma unroll
-        for (int a = 0; a < X; ++a) crow[(B.ny + a) * NT] = x[a] - xo[a];
+        for (int i = 0; i < X; ++i) a.crow[(B.ny + i) * NT] = x[i] - xo[i];
       }
       ++k;
-      if (WITH_K && k < B.n) ldcol<X>(alph + k * X * nta, nta, al);
+      if (WITH_K && k < B.n) ldcol<X>(a.alph + k * X * nta, nta, al);
     }
   }
   cp_async_wait<0>();

@@ -124,3 +124,41 @@ def test_philox_momentum_is_tangent_and_standard(gold):
     assert abs(p1.std() - 1.0) < 0.05 and abs(p1.mean()) < 0.05
     assert np.max(np.abs(bc.normal_space_component(p1))) < 1e-9
     bc.close()
+
+
+@pytest.mark.parametrize("part", [0, 1])
+@pytest.mark.parametrize("via_switch", [False, True])
+def test_full_tiles_agree_with_single_chain(gold, part, via_switch):
+    """Copies of the golden chains filling several CTA tiles (every lane of a tile active, blocks of
+    unequal length in partition 1) must reproduce the single-chain results bit for bit, also when the
+    partition was reached through SwitchPartitionTransition (re-tiling on device)."""
+    from manifold_mcmc_for_diffusions_b200 import BatchedChains
+
+    idx = _chains(gold, part)
+    rep = 20
+    q0 = np.tile(gold["q0"][idx], (rep, 1))
+    xo = np.tile(gold["xobs"][idx], (rep, 1, 1))
+    p = np.tile(gold["p_raw"][idx], (rep, 1))
+    m = len(idx)
+    bc = BatchedChains("fhn", 0.2, int(gold["S"]), int(gold["R"]), gold["y"], 4, rep * m)
+    if via_switch:
+        bc.set_state(q0, xo, 1 - part)
+        bc.switch_partition()
+        bc.set_momentum(p)
+    else:
+        bc.set_state(q0, xo, part, p=p)
+    bc.linearize(True)
+    bc.project_momentum()
+    dt = float(gold["dt"])
+    for s in range(2):
+        bc.leapfrog_step(dt)
+        info = bc.step_info()
+        q, pp, _ = bc.get_state()
+        assert np.all(info["status"] == 0)
+        assert np.array_equal(info["iters_fwd"], np.tile(gold["traj_it"][idx, s, 0], rep))
+        assert np.array_equal(info["iters_rev"], np.tile(gold["traj_it"][idx, s, 1], rep))
+        qr = q.reshape(rep, m, -1)
+        assert np.array_equal(qr, np.broadcast_to(qr[0], qr.shape))
+        # x_obs_seq regenerated on device by the switch differs from the stored one by rounding only
+        assert _rel(qr[0], gold["traj_q"][idx, s]) < (1e-7 if via_switch else 1e-9)
+    bc.close()

@@ -9,6 +9,10 @@ functions: the step, its Jacobians with respect to state / noise / parameters, a
 second-order contraction ``sum_i Hess(f_i)[:, :] @ Theta[:, i]`` that the log-determinant gradient
 sweep needs ("second-order adjoint").
 
+Every sub-expression that depends only on the parameters ``z`` and the step size is hoisted into a
+per-thread coefficient struct (``Coef``), computed once per sweep by ``make_coef``: the time-stepping
+loops then contain no division, no power and no re-evaluation of parameter-only products.
+
 Usage:  python tools/gen_model_code.py   (rewrites manifold_mcmc_for_diffusions_b200/csrc/mmd_model_*.cuh)
 """
 
@@ -25,14 +29,8 @@ OUT_DIR = os.path.join(ROOT, "manifold_mcmc_for_diffusions_b200", "csrc")
 
 
 class _Printer(C99CodePrinter):
-    # symbols whose reciprocal is precomputed once per thread in the model's Coef struct
-    recip = {"epsilon": "ie"}
-
     def _print_Pow(self, expr):
         b, e = expr.base, expr.exp
-        if b.is_Symbol and b.name in self.recip and e.is_Integer and int(e) < 0:
-            r = self.recip[b.name]
-            return r if int(e) == -1 else "(" + "*".join([r] * abs(int(e))) + ")"
         if e.is_Integer and 2 <= abs(int(e)) <= 8:
             s = self._print(b)
             if not b.is_Atom:
@@ -49,13 +47,63 @@ class _Printer(C99CodePrinter):
 _pr = _Printer()
 
 
-def _emit(name, args_sig, outputs, syms_doc):
+class Hoister:
+    """Replaces maximal parameter-only sub-expressions by coefficient symbols k<i>."""
+
+    def __init__(self, dyn_syms, prefix, recip_only=False):
+        self.dyn = set(dyn_syms)
+        self.table = {}
+        self.prefix = prefix
+        self.recip_only = recip_only  # hoist only sub-expressions that contain a division
+
+    def _const(self, e):
+        return not (e.free_symbols & self.dyn)
+
+    def _sym(self, c):
+        if not c.free_symbols:
+            return c
+        if self.recip_only:
+            if not any(isinstance(a, sp.Pow) and a.exp.is_negative for a in sp.preorder_traversal(c)):
+                return c
+            # hoist just the reciprocal factors, keep the rest inline
+            if isinstance(c, sp.Mul):
+                rec = [a for a in c.args if isinstance(a, sp.Pow) and a.exp.is_negative]
+                rest = [a for a in c.args if not (isinstance(a, sp.Pow) and a.exp.is_negative)]
+                if rec and rest:
+                    return sp.Mul(self._sym(sp.Mul(*rec)), *rest)
+            if isinstance(c, sp.Add):
+                return sp.Add(*[self._sym(a) for a in c.args])
+        if c not in self.table:
+            self.table[c] = sp.Symbol(f"{self.prefix}{len(self.table)}")
+        return self.table[c]
+
+    def __call__(self, e):
+        if e.is_Atom:
+            return e
+        if self._const(e):
+            return self._sym(e)
+        if isinstance(e, (sp.Mul, sp.Add)):
+            cargs = [a for a in e.args if self._const(a)]
+            dargs = [self(a) for a in e.args if not self._const(a)]
+            if cargs:
+                return e.func(self._sym(e.func(*cargs)), *dargs)
+            return e.func(*dargs)
+        return e.func(*[self(a) for a in e.args])
+
+
+def _emit(name, args_sig, outputs, unpack, hoister):
     """outputs: list of (lhs string, sympy expr).  Returns C source of one function."""
-    exprs = [e for _, e in outputs]
+    exprs = [hoister(sp.sympify(e)) for _, e in outputs]
     repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("t"), optimizations="basic")
     lines = [f"  MMD_HD static void {name}({args_sig}) {{"]
-    if syms_doc:
-        lines.append(syms_doc)
+    lines.append(unpack)
+    used = set()
+    for _, e in repl:
+        used |= e.free_symbols
+    for e in red:
+        used |= sp.sympify(e).free_symbols
+    for k in sorted((s for s in used if s in set(hoister.table.values())), key=lambda s: int(s.name[len(hoister.prefix):])):
+        lines.append(f"    const double {k} = c.{hoister.prefix}[{k.name[len(hoister.prefix):]}];")
     for s, e in repl:
         lines.append(f"    const double {s} = {_pr.doprint(e)};")
     for (lhs, _), e in zip(outputs, red):
@@ -64,120 +112,144 @@ def _emit(name, args_sig, outputs, syms_doc):
     return "\n".join(lines)
 
 
-def gen_fhn():
-    from oracle.models import derive_fhn_step
-
-    f, sy = derive_fhn_step(simplify=False)
-    x0, x1 = sy["x"]
-    v0, v1 = sy["v"]
-    s, e, g, b = sy["z"]
-    d = sy["delta"]
-    sd = sp.symbols("sd", positive=True)  # sqrt(delta): keeps pow() out of the inner loops
-    f = f.subs(d, sd ** 2)
-    X, V, Z = [x0, x1], [v0, v1], [s, e, g, b]
-    joint = X + V + Z
+def gen_model(struct_name, fname, f, X, V, Z, sd, header, doc):
+    """Emit one model header.  f: sympy column of the step map in terms of X, V, Z symbols and sd."""
+    nx, nv, nz = len(X), len(V), len(Z)
+    dyn = list(X) + list(V)
+    joint = list(X) + list(V) + list(Z)
     unpack = (
-        "    const double x0 = x[0], x1 = x[1], v0 = v[0], v1 = v[1];\n"
-        "    const double sigma = c.z[0], epsilon = c.z[1], gamma = c.z[2], beta = c.z[3], sd = c.sd, ie = c.ie;\n"
-        "    (void)x0; (void)x1; (void)v0; (void)v1; (void)sigma; (void)epsilon; (void)gamma; (void)beta; (void)sd; (void)ie;"
+        "    " + " ".join(f"const double {s} = x[{i}];" for i, s in enumerate(X)) + "\n"
+        "    " + " ".join(f"const double {s} = v[{i}];" for i, s in enumerate(V)) + "\n"
+        "    " + " ".join(f"(void){s};" for s in dyn) + "\n"
+        "    " + " ".join(f"const double {s} = c.z[{i}];" for i, s in enumerate(Z)) + f" const double {sd} = c.sd;\n"
+        "    " + " ".join(f"(void){s};" for s in Z) + f" (void){sd};"
     )
+    hs = Hoister(dyn, "ks")   # coefficients of the step itself (hot in every sweep)
+    hd = Hoister(dyn + [sp.Symbol(f"Th{r}_{c}") for r in range(len(joint)) for c in range(nx)], "kd",
+                 recip_only=True)
     sig = "const Coef& c, const double* x, const double* v, "
     parts = []
-    parts.append(_emit("step", sig + "double* xn", [(f"xn[{i}]", f[i]) for i in range(2)], unpack))
+    parts.append(_emit("step", sig + "double* xn", [(f"xn[{i}]", f[i]) for i in range(nx)], unpack, hs))
     Fx = f.jacobian(X)
-    parts.append(
-        _emit("jac_x", sig + "double* F", [(f"F[{i*2+j}]", Fx[i, j]) for i in range(2) for j in range(2)], unpack)
-    )
+    parts.append(_emit("jac_x", sig + "double* F",
+                       [(f"F[{i*nx+j}]", Fx[i, j]) for i in range(nx) for j in range(nx)], unpack, hd))
     Fv = f.jacobian(V)
-    parts.append(
-        _emit("jac_v", sig + "double* B", [(f"B[{i*2+j}]", Fv[i, j]) for i in range(2) for j in range(2)], unpack)
-    )
+    parts.append(_emit("jac_v", sig + "double* B",
+                       [(f"B[{i*nv+j}]", Fv[i, j]) for i in range(nx) for j in range(nv)], unpack, hd))
     Fz = f.jacobian(Z)
-    parts.append(
-        _emit("jac_z", sig + "double* G", [(f"G[{i*4+j}]", Fz[i, j]) for i in range(2) for j in range(4)], unpack)
-    )
+    parts.append(_emit("jac_z", sig + "double* G",
+                       [(f"G[{i*nz+j}]", Fz[i, j]) for i in range(nx) for j in range(nz)], unpack, hd))
     # second-order contraction: g[a] = sum_i sum_b d2 f_i / d y_a d y_b * Th[b*X + i]
     nj = len(joint)
-    Th = sp.Matrix(nj, 2, lambda r, c: sp.Symbol(f"Th{r}_{c}"))
+    Th = sp.Matrix(nj, nx, lambda r, c: sp.Symbol(f"Th{r}_{c}"))
     gout = []
     for a in range(nj):
         acc = 0
-        for i in range(2):
+        for i in range(nx):
             for bb in range(nj):
                 acc += sp.diff(f[i], joint[a], joint[bb]) * Th[bb, i]
         gout.append(acc)
     th_unpack = unpack + "\n" + "\n".join(
-        f"    const double Th{r}_{c} = Th[{r*2+c}];" for r in range(nj) for c in range(2)
+        "    " + " ".join(f"const double Th{r}_{c} = Th[{r*nx+c}];" for c in range(nx)) for r in range(nj)
     )
-    parts.append(
-        _emit(
-            "hess_contract",
-            sig + "const double* Th, double* g",
-            [(f"g[{a}]", gout[a]) for a in range(nj)],
-            th_unpack,
-        )
-    )
+    parts.append(_emit("hess_contract", sig + "const double* Th, double* g",
+                       [(f"g[{a}]", gout[a]) for a in range(nj)], th_unpack, hd))
+    jv_const = not (Fv.free_symbols & set(X) | Fv.free_symbols & set(V))
+
+    def coef_lines(h):
+        out = []
+        for e, k in sorted(h.table.items(), key=lambda kv: int(kv[1].name[len(h.prefix):])):
+            out.append(f"    c.{h.prefix}[{k.name[len(h.prefix):]}] = {_pr.doprint(e)};")
+        return "\n".join(out)
+
+    zunpack = " ".join(f"const double {s} = z[{i}];" for i, s in enumerate(Z)) + " " + \
+        " ".join(f"(void){s};" for s in Z)
     body = "\n\n".join(parts)
     src = f"""// GENERATED by tools/gen_model_code.py -- do not edit by hand.
-// FitzHugh-Nagumo hypoelliptic diffusion, strong-order-1.5 Taylor step (additive noise).
-// Restates sde/example_models/fhn.py:10-51 and sde/integrators.py:46-63 of the reference; all
-// derivatives are symbolic derivatives of that one expression.
+{doc}
 #pragma once
 #include "mmd_common.cuh"
 
-struct FhnModel {{
-  static constexpr int X = 2;   // dim_x   (fhn.py:10)
+struct {struct_name} {{
+{header}
+  static constexpr bool JV_CONST = {'true' if jv_const else 'false'};  // d f / d v independent of the state
+
+  // per-thread constants of the step map: every parameter-only sub-expression of the generated code,
+  // so no division / power / parameter product is left inside the time-stepping loops
+  struct Coef {{
+    double z[Z];
+    double sd;
+    double ks[{max(len(hs.table), 1)}];   // step
+    double kd[{max(len(hd.table), 1)}];   // derivatives (jac_x, jac_v, jac_z, hess_contract)
+  }};
+  MMD_HD static void make_coef_step(const double* z, double {sd}, Coef& c) {{
+    for (int i = 0; i < Z; ++i) c.z[i] = z[i];
+    c.sd = {sd};
+    {zunpack}
+{coef_lines(hs)}
+  }}
+  MMD_HD static void make_coef(const double* z, double {sd}, Coef& c) {{
+    make_coef_step(z, {sd}, c);
+    {zunpack}
+{coef_lines(hd)}
+  }}
+
+{body}
+}};
+"""
+    path = os.path.join(OUT_DIR, fname)
+    with open(path, "w") as fh:
+        fh.write(src)
+    print("wrote", path, "step coefficients:", len(hs.table), "derivative coefficients:", len(hd.table))
+
+
+FHN_HEADER = """  static constexpr int X = 2;   // dim_x   (fhn.py:10)
   static constexpr int V = 2;   // dim_v   (fhn.py:14)
   static constexpr int Z = 4;   // dim_z   (fhn.py:12)  z = [sigma, epsilon, gamma, beta]
   static constexpr int V0 = 2;  // dim_v_0 (fhn.py:13)
   static constexpr int Y = 1;   // dim_y: obs_func(x) = x[0]  (fhn.py:37-38)
   static constexpr int MODEL_ID = 0;
-  static constexpr bool JV_CONST = true;  // d f / d v does not depend on the state (additive noise)
-
-  // per-thread constants of the step map: parameters, sqrt(delta) and the reciprocals the generated
-  // code needs, so no division is left inside the time-stepping loops
-  struct Coef {{
-    double z[Z];
-    double sd, ie;
-  }};
-  MMD_HD static void make_coef(const double* z, double sd, Coef& c) {{
-    for (int i = 0; i < Z; ++i) c.z[i] = z[i];
-    c.sd = sd;
-    c.ie = 1.0 / z[1];
-  }}
 
   // z = generate_z(u) and dz/du (fhn.py:41-43): z = [exp u0, exp u1, exp u2, u3]
-  MMD_HD static void gen_z(const double* u, double* z, double* dzdu /* Z x Z */) {{
+  MMD_HD static void gen_z(const double* u, double* z, double* dzdu /* Z x Z */) {
     z[0] = exp(u[0]); z[1] = exp(u[1]); z[2] = exp(u[2]); z[3] = u[3];
     for (int i = 0; i < 16; ++i) dzdu[i] = 0.0;
     dzdu[0] = z[0]; dzdu[5] = z[1]; dzdu[10] = z[2]; dzdu[15] = 1.0;
-  }}
-  // extra[j'] = sum_{{m,j}} Gam[m*Z+j] * d2 z_m / du_j du_j'   (second derivative of generate_z)
-  MMD_HD static void gen_z_second(const double* u, const double* z, const double* Gam, double* extra) {{
+  }
+  // extra[j'] = sum_{m,j} Gam[m*Z+j] * d2 z_m / du_j du_j'   (second derivative of generate_z)
+  MMD_HD static void gen_z_second(const double* u, const double* z, const double* Gam, double* extra) {
     extra[0] = Gam[0] * z[0]; extra[1] = Gam[5] * z[1]; extra[2] = Gam[10] * z[2]; extra[3] = 0.0;
-  }}
+  }
   // x_0 = generate_x_0(z, v_0) = v_0 - [0, z3] (fhn.py:50-51); linear: d/dv_0 = I, d/dz = -e1 e3^T
-  MMD_HD static void gen_x0(const double* z, const double* v0, double* x0) {{
+  MMD_HD static void gen_x0(const double* z, const double* v0, double* x0) {
     x0[0] = v0[0]; x0[1] = v0[1] - z[3];
-  }}
-  MMD_HD static void gen_x0_jac(const double* z, double* dx0_dv0 /* X x V0 */, double* dx0_dz /* X x Z */) {{
+  }
+  MMD_HD static void gen_x0_jac(const double* z, double* dx0_dv0 /* X x V0 */, double* dx0_dz /* X x Z */) {
     dx0_dv0[0] = 1.0; dx0_dv0[1] = 0.0; dx0_dv0[2] = 0.0; dx0_dv0[3] = 1.0;
     for (int i = 0; i < 8; ++i) dx0_dz[i] = 0.0;
     dx0_dz[7] = -1.0;
-  }}
+  }
   // observation y = h(x) = x[0]; gradient e0; zero second derivative
-  MMD_HD static double obs(const double* x) {{ return x[0]; }}
-  MMD_HD static void obs_grad(const double* x, double* dh) {{ dh[0] = 1.0; dh[1] = 0.0; }}
-  MMD_HD static void obs_hess_vec(const double* x, const double* d, double* out) {{ out[0] = 0.0; out[1] = 0.0; }}
+  MMD_HD static double obs(const double* x) { return x[0]; }
+  MMD_HD static void obs_grad(const double* x, double* dh) { dh[0] = 1.0; dh[1] = 0.0; }
+  MMD_HD static void obs_hess_vec(const double* x, const double* d, double* out) { out[0] = 0.0; out[1] = 0.0; }
   static constexpr bool OBS_LINEAR = true;
-
-{body}
-}};
 """
-    path = os.path.join(OUT_DIR, "mmd_model_fhn.cuh")
-    with open(path, "w") as fh:
-        fh.write(src)
-    print("wrote", path)
+
+
+def gen_fhn():
+    from oracle.models import derive_fhn_step
+
+    f, sy = derive_fhn_step(simplify=False)
+    d = sy["delta"]
+    sd = sp.symbols("sd", positive=True)  # sqrt(delta): keeps pow() out of the generated code
+    f = f.subs(d, sd ** 2)
+    gen_model(
+        "FhnModel", "mmd_model_fhn.cuh", f, list(sy["x"]), list(sy["v"]), list(sy["z"]), "sd", FHN_HEADER,
+        "// FitzHugh-Nagumo hypoelliptic diffusion, strong-order-1.5 Taylor step (additive noise).\n"
+        "// Restates sde/example_models/fhn.py:10-51 and sde/integrators.py:46-63 of the reference; all\n"
+        "// derivatives are symbolic derivatives of that one expression.",
+    )
 
 
 if __name__ == "__main__":
