@@ -83,13 +83,15 @@ class ClockSampler(threading.Thread):
 # work model (SURVEY.md 8d / DESIGN.md): bytes one quasi-Newton sweep must read per chain
 def leapfrog_bytes_per_chain_step(qn_iters):
     """Algorithmic HBM bytes of one constrained leapfrog step of one chain: doubles
-    per SDE time step summed over the phases (X=V=2: K_t is 4 doubles, v_t / p_t / x_t are 2)."""
-    project = 22 + 14 + 22        # 3 x (h1_flow +) cotangent projection: K twice, p read twice + written
-    flow = 6 + 6                  # 2 x h2_flow into the work position
-    qn = 6 * qn_iters             # one sweep per iteration: K_t + work position
-    qn_final = 10 + 6 + 8         # forward finalise (write q, mu) + momentum update + reverse comparison
-    point = 4 + 8 + 12 + 10       # trajectory, compressed Jacobian, tangent accumulator, adjoint sweep
-    return 8 * T * S * (project + flow + qn + qn_final + point)
+    per SDE time step summed over the phases (X=V=2: a K_t record is 4 doubles, v_t / p_t / x_t records 2)."""
+    # momentum projections (pass 1: J p, pass 2: p - J^T lambda), h1 kick and h2_flow fused in:
+    project = (4 + 2 + 2 + 2 + 2) + (4 + 2 + 2 + 2 + 2)   # A(dt/2) at the old point + flow -> qw, pw
+    project += (4 + 2) + (4 + 2 + 2 + 2 + 2)              # tangent projection at the new point + back flow
+    project += (4 + 2 + 2 + 2 + 2) + (4 + 2 + 2)          # A(dt/2) at the new point
+    qn = 6 * qn_iters                                      # one sweep per iteration: K_t + work position
+    qn_final = (4 + 2 + 2 + 2 + 2) + (4 + 2 + 2)           # forward: write q, p; reverse: compare with q_prev
+    point = 4 + 8 + 12 + 10                                # trajectory, compressed Jacobian, tangent, adjoint sweeps
+    return 8 * T * S * (project + qn + qn_final + point)
 
 
 def run_ours(args):
@@ -109,6 +111,7 @@ def run_ours(args):
     n = args.chains
     y, u, v0, xo = init_inputs(n, rank)
     bc = BatchedChains("fhn", OBS_INTERVAL, S, R, y, 4, n, device=local_rank)
+    bc.set_chain_offset(rank * n)   # disjoint Philox streams per rank
     bc.init_linear_interpolation(u, v0, xo, 0)
     L = args.traj_len
     # untimed burn-in towards the typical set (the linear-interpolation states are far in the tails)
@@ -214,6 +217,7 @@ def run_ours(args):
             "config": {
                 "workload": WORKLOAD,
                 "chains_per_gpu": n,
+                "chains_per_cta_tile": bc.chains_per_tile(),
                 "step_size": args.dt,
                 "traj_len": L,
                 "burnin_transitions": args.burnin,
@@ -346,10 +350,10 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chains", type=int, default=4096, help="chains per GPU")
+    ap.add_argument("--chains", type=int, default=16384, help="chains per GPU")
     ap.add_argument("--dt", type=float, default=0.1)
     ap.add_argument("--traj-len", type=int, default=8)
-    ap.add_argument("--burnin", type=int, default=150)
+    ap.add_argument("--burnin", type=int, default=60)
     ap.add_argument("--burnin-dt", type=float, default=0.05)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)

@@ -84,6 +84,13 @@ class BatchedChains:
     def partition(self):
         return self._L.mmd_get_partition(self._h)
 
+    def set_chain_offset(self, chain0):
+        """Global index of this handle's first chain (keeps Philox streams disjoint across ranks)."""
+        check(self._L.mmd_set_chain_offset(self._h, int(chain0)))
+
+    def chains_per_tile(self):
+        return int(self._L.mmd_chains_per_tile(self._h))
+
     def num_constraints(self, partition=None):
         return self._L.mmd_num_constraints(self._h, self.partition if partition is None else partition)
 

@@ -23,7 +23,10 @@
 #include <stdint.h>
 
 #ifndef MMD_PREFETCH_STEPS
-#define MMD_PREFETCH_STEPS 3
+#define MMD_PREFETCH_STEPS 2      // cp.async ring depth of the recursion sweeps (steps in flight to shared memory)
+#endif
+#ifndef MMD_L2_PREFETCH_STEPS
+#define MMD_L2_PREFETCH_STEPS 8   // additional look-ahead of the HBM -> L2 prefetch (0 = off)
 #endif
 
 namespace mmd {

@@ -49,6 +49,7 @@ MMD_D void cp_async(unsigned sdst, const void* gsrc) {
   else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst), "l"(gsrc) : "memory");
 }
+MMD_D void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(g)); }
 MMD_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 MMD_D void cp_async_wait() {
@@ -160,6 +161,12 @@ __device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const Swe
     if (s + PF < ns) {  // refill the slot consumed one step ago
       cp_async_rec<V>(wr, vp);
       if (WITH_K) cp_async_rec<XV>(wr + V * 8, Kp);
+#if MMD_L2_PREFETCH_STEPS > 0
+      if (s + PF + MMD_L2_PREFETCH_STEPS < ns) {  // pull the records of a later step from HBM into L2
+        prefetch_l2(vp + MMD_L2_PREFETCH_STEPS * vbump);
+        if (WITH_K) prefetch_l2(Kp + MMD_L2_PREFETCH_STEPS * Kbump);
+      }
+#endif
       vp += vbump;
       Kp += Kbump;
     }
