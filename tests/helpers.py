@@ -12,15 +12,21 @@ OBS_INTERVAL = 0.2
 SEED = 20200710
 
 
-def make_fhn_problem(T, S, R, n_chains, nd=1000, seed=SEED):
+def make_fhn_problem(T, S, R, n_chains, nd=1000, seed=SEED, noise=0, sigma=0.1, gaussian=False):
     """Simulated data + oracle system + linear-interpolation initial states for `n_chains` chains
-    (restates fhn_model_noiseless_obs_chmc_experiment.py:84-134 with `nd` fine steps per obs)."""
+    (restates fhn_model_noiseless_obs_chmc_experiment.py:84-134 with `nd` fine steps per obs).
+    noise: 0 noiseless, 1 fixed observation noise scale `sigma`, 2 inferred scale sigma = exp(u[4])
+    (fhn_model_noisy_obs_chmc_experiment.py); gaussian: use_gaussian_splitting."""
     rng = np.random.default_rng(seed)
     v = rng.standard_normal((T * nd, 2))
     y = fhn_simulate_y_seq_numpy(Z_TRUE, X0_TRUE, v, OBS_INTERVAL / nd, nd)
+    if noise:
+        y = y + sigma * rng.standard_normal(y.shape)
+    dim_u = 5 if noise == 2 else 4
+    gen_sigma = None if noise == 0 else (float(sigma) if noise == 1 else fhn.generate_σ_y)
     system = O.OracleSystem(
-        OBS_INTERVAL, S, R, y, 4, 2, 2, fhn.forward_func, fhn.generate_x_0, fhn.generate_z, fhn.obs_func,
-        None, False, dim_v_0=2,
+        OBS_INTERVAL, S, R, y, dim_u, 2, 2, fhn.forward_func, fhn.generate_x_0, fhn.generate_z, fhn.obs_func,
+        gen_sigma, gaussian, dim_v_0=2,
     )
 
     def gen_init(rng_):
@@ -29,19 +35,24 @@ def make_fhn_problem(T, S, R, n_chains, nd=1000, seed=SEED):
     qs, xs = [], []
     for c in range(n_chains):
         crng = np.random.default_rng([seed, c])
-        u = crng.standard_normal(4) * 0.5
+        u = crng.standard_normal(dim_u) * 0.5
+        if noise == 2:
+            u[4] = np.log(sigma) + 0.3 * u[4]
         v0 = crng.standard_normal(2)
         q, xo = O.find_initial_state_by_linear_interpolation(system, crng, gen_init, u=u, v_0=v0)
         qs.append(q.numpy())
         xs.append(xo.numpy())
-    return dict(T=T, S=S, R=R, y=y, system=system, q=np.stack(qs), xobs=np.stack(xs))
+    return dict(T=T, S=S, R=R, y=y, system=system, q=np.stack(qs), xobs=np.stack(xs), noise=noise, sigma=sigma,
+                gaussian=gaussian, dim_u=dim_u)
 
 
 def make_batched(prob, n_chains=None):
     from manifold_mcmc_for_diffusions_b200 import BatchedChains
 
     n = prob["q"].shape[0] if n_chains is None else n_chains
-    return BatchedChains("fhn", OBS_INTERVAL, prob["S"], prob["R"], prob["y"], 4, n)
+    return BatchedChains("fhn", OBS_INTERVAL, prob["S"], prob["R"], prob["y"], prob.get("dim_u", 4), n,
+                         noise=prob.get("noise", 0), sigma_fixed=prob.get("sigma", 0.0),
+                         use_gaussian_splitting=prob.get("gaussian", False))
 
 
 def oracle_momentum(prob, q, xobs, part, seed):
