@@ -62,6 +62,7 @@ class BatchedChains:
         self._h = C.c_void_p()
         check(self._L.mmd_create(C.byref(cfg), C.byref(self._h)))
         self.n_chains = int(n_chains)
+        self._sigma_fixed = float(sigma_fixed)
         self.dim_q = self._L.mmd_dim_q(self._h)
         self.num_partition = self._L.mmd_num_partition(self._h)
         self.num_obs = cfg.num_obs

@@ -644,9 +644,10 @@ int mmd_get_factor(mmd_handle h, const char* name, double* out, int* rows_out) {
   long long stride = 0;
   int rows = 0;
   bool per_chain = false;
+  int W = 1;
   const int NTRI = h->nrmax * (h->nrmax + 1) / 2;
   std::string nm(name);
-  if (nm == "K") { arr = h->S.K; stride = h->S.s_K; rows = d.rmax * d.S * h->X * h->V; }
+  if (nm == "K") { arr = h->S.K; stride = h->S.s_K; rows = d.rmax * d.S * h->X * h->V; W = h->X * h->V; }
   else if (nm == "Psib") { arr = h->S.Psib; stride = h->S.s_Psib; rows = d.rmax * h->X * h->X; }
   else if (nm == "xend") { arr = h->S.xend; stride = h->S.s_xend; rows = d.rmax * h->X; }
   else if (nm == "A") { arr = h->S.A; stride = h->S.s_A; rows = h->nrmax * d.U; }
@@ -675,7 +676,7 @@ int mmd_get_factor(mmd_handle h, const char* name, double* out, int* rows_out) {
   const size_t n = (size_t)d.n_chains * d.nb[h->partition] * rows;
   double* tmp = nullptr;
   CK(cudaMalloc((void**)&tmp, n * sizeof(double)));
-  k_unpack_tp<<<592, 256, 0, h->stream>>>(d, h->partition, rows, tmp, arr, stride, h->S.cur);
+  k_unpack_tp<<<592, 256, 0, h->stream>>>(d, h->partition, rows, W, tmp, arr, stride, h->S.cur);
   h->launches++;
   int rc = d2h_sync(h, out, tmp, n);
   cudaFree(tmp);

@@ -1186,9 +1186,10 @@ __global__ void k_unpack_chain(Dims d, int rows, double* __restrict__ canon, con
     canon[e] = src[((long long)(chain >> d.lcpb) * rows + r) * d.cpb + (chain & (d.cpb - 1))];
   }
 }
-// thread-private array (rows per thread, block-local rows) -> [chain][nb][rows] for tests / factor export
-__global__ void k_unpack_tp(Dims d, int part, int rows, double* __restrict__ out, const double* __restrict__ base,
-                            long long slot_stride, const int* __restrict__ cur) {
+// thread-private array (rows per thread, block-local rows; records of width W, W = 1 for plain columns)
+// -> [chain][nb][rows] for tests / factor export
+__global__ void k_unpack_tp(Dims d, int part, int rows, int W, double* __restrict__ out,
+                            const double* __restrict__ base, long long slot_stride, const int* __restrict__ cur) {
   const int nb = d.nb[part];
   const long long n = (long long)d.n_chains * nb * rows;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
@@ -1197,7 +1198,9 @@ __global__ void k_unpack_tp(Dims d, int part, int rows, double* __restrict__ out
     const int b = (int)((e / rows) % nb);
     const int chain = (int)(e / ((long long)rows * nb));
     const int tile = chain >> d.lcpb, cl = chain & (d.cpb - 1);
-    out[e] = base[cur[chain] * slot_stride + ((long long)tile * rows + r) * d.nta + (b << d.lcpb) + cl];
+    const int tid = (b << d.lcpb) + cl;
+    const int s = r / W, c = r % W;
+    out[e] = base[cur[chain] * slot_stride + ((long long)tile * rows + s * W) * d.nta + tid * W + c];
   }
 }
 

@@ -1,0 +1,403 @@
+"""Drop-in for the constrained-HMC part of ``sde.mici_extensions`` (reference ``sde/mici_extensions.py``):
+the same names, signatures and error behaviour, with every numerical operation executed by the CUDA
+library through the C ABI (``include/mmd_b200.h``).  Mici samplers / integrators call it unchanged.
+
+    ConditionedDiffusionConstrainedSystem   :208-1259
+    SwitchPartitionTransition               :1262-1282
+    ConditionedDiffusionHamiltonianState    :1285-1320
+    jitted_solve_projection_onto_manifold_quasi_newton   :1323-1402
+    jitted_solve_projection_onto_manifold_newton         :1405-1476
+    find_initial_state_by_linear_interpolation           :1479-1547
+    split, split_and_reshape                :31-53
+
+This module is the *compatibility* path: one Mici chain = one resident chain on the device, one C
+call per system method (the way Mici drives the reference's jitted JAX functions).  The throughput
+path is :class:`manifold_mcmc_for_diffusions_b200.BatchedChains`, which keeps thousands of chains
+resident and runs whole leapfrog steps / transitions per launch.  There is no CPU fallback: model
+callables must be the tagged functions of :mod:`.example_models` (arbitrary Python callables cannot
+be compiled into device functors and raise ``NotImplementedError``).
+"""
+
+from numbers import Number
+
+import numpy as np
+
+try:  # prefer the real Mici when it is installed
+    from mici.errors import ConvergenceError
+    from mici.matrices import IdentityMatrix
+    from mici.states import ChainState, _cache_key_func
+    from mici.systems import System, cache_in_state, cache_in_state_with_aux
+    from mici.transitions import Transition
+except ImportError:  # pragma: no cover - exercised in this environment
+    from .mici_compat.errors import ConvergenceError
+    from .mici_compat.matrices import IdentityMatrix
+    from .mici_compat.states import ChainState, _cache_key_func, cache_in_state, cache_in_state_with_aux
+    from .mici_compat.systems import System
+    from .mici_compat.transitions import Transition
+
+from .batched import BatchedChains
+
+SOLVER_QUASI_NEWTON, SOLVER_NEWTON = 0, 1
+
+
+def split(v, lengths):
+    """Split an array along first dimension into slices of specified lengths (:31-40)."""
+    i = 0
+    parts = []
+    for length in lengths:
+        parts.append(v[i: i + length])
+        i += length
+    if i < len(v):
+        parts.append(v[i:])
+    return parts
+
+
+def split_and_reshape(array, shapes):
+    """Split an array along first dimension into subarrays of specified shapes (:43-53)."""
+    array = np.asarray(array)
+    lengths = [int(np.prod(shape)) for shape in shapes]
+    return tuple(part.reshape(shape + array.shape[1:]) for part, shape in
+                 zip(split(array, lengths), shapes))
+
+
+def standard_normal_neg_log_dens(q):
+    """Unnormalised negative log density of standard normal vector (:56-58)."""
+    return 0.5 * float(np.sum(np.square(q)))
+
+
+def standard_normal_grad_neg_log_dens(q):
+    """Gradient and value of negative log density of standard normal vector (:61-63)."""
+    return q, 0.5 * float(np.sum(np.square(q)))
+
+
+def _model_tag(*funcs):
+    tags = {getattr(f, "_mmd_model", None) for f in funcs}
+    if None in tags or len(tags) != 1:
+        raise NotImplementedError(
+            "ConditionedDiffusionConstrainedSystem runs on generated CUDA device functors: forward_func, "
+            "generate_x_0, generate_z, obs_func (and a callable generate_σ) must be the functions of "
+            "manifold_mcmc_for_diffusions_b200.example_models.<model>; arbitrary callables are not supported "
+            "and there is no CPU fallback")
+    return tags.pop()
+
+
+class ConditionedDiffusionConstrainedSystem(System):
+    """Specialised mici system class for conditioned diffusion problems (reference :208-1259),
+    identity metric, evaluated on the GPU."""
+
+    def __init__(self, obs_interval, num_steps_per_obs, num_obs_per_subseq, y_seq, dim_u, dim_x, dim_v,
+                 forward_func, generate_x_0, generate_z, obs_func, generate_σ=None,
+                 use_gaussian_splitting=False, metric=None, dim_v_0=None, device=0):
+        if use_gaussian_splitting and metric is not None:
+            raise ValueError("Only identity matrix metric can be used with Gaussian splitting.")  # :293-297
+        if metric is not None and not isinstance(metric, IdentityMatrix):
+            raise NotImplementedError("Only the identity metric is implemented on the device path.")  # :305-315
+        super().__init__(neg_log_dens=standard_normal_neg_log_dens,
+                         grad_neg_log_dens=standard_normal_grad_neg_log_dens)
+        self.use_gaussian_splitting = use_gaussian_splitting
+        self.metric = IdentityMatrix()
+        funcs = [forward_func, generate_x_0, generate_z, obs_func]
+        if generate_σ is None:
+            noise, sigma = 0, 0.0
+        elif isinstance(generate_σ, Number):
+            noise, sigma = 1, float(generate_σ)
+        else:
+            noise, sigma = 2, 0.0
+            funcs.append(generate_σ)
+        model = _model_tag(*funcs)
+        y_seq = np.asarray(y_seq, dtype=np.float64)
+        num_obs, dim_y = y_seq.shape
+        dim_v_0 = dim_x if dim_v_0 is None else dim_v_0
+        self._bc = BatchedChains(model, obs_interval, num_steps_per_obs, num_obs_per_subseq, y_seq, dim_u, 1,
+                                 noise=noise, sigma_fixed=sigma, use_gaussian_splitting=use_gaussian_splitting,
+                                 device=device)
+        self.num_partition = self._bc.num_partition
+        self.dim_q = self._bc.dim_q
+        self.model_dict = {
+            "dim_u": dim_u, "dim_v": dim_v, "dim_v_0": dim_v_0, "dim_x": dim_x, "dim_y": dim_y,
+            "num_obs": num_obs, "num_steps_per_obs": num_steps_per_obs, "δ": obs_interval / num_steps_per_obs,
+            "generate_z": generate_z, "generate_x_0": generate_x_0, "generate_σ": generate_σ,
+            "forward_func": forward_func, "obs_func": obs_func, "y_seq": y_seq,
+        }
+        self._dims = (num_obs, num_steps_per_obs, num_obs_per_subseq, dim_u, dim_x, dim_v, dim_v_0, noise)
+        self._resident = None     # (pos bytes, x_obs bytes, partition) of the chain resident on the device
+        self._linearised = False
+        self._grad = self._ld = None
+
+    # ---- device residency ----------------------------------------------------------------------
+    def _upload(self, state):
+        key = (np.asarray(state.pos).tobytes(), np.asarray(state.x_obs_seq).tobytes(), int(state.partition))
+        if key != self._resident:
+            self._bc.set_state(np.asarray(state.pos, dtype=np.float64)[None],
+                               np.asarray(state.x_obs_seq, dtype=np.float64)[None], int(state.partition))
+            self._resident = key
+            self._linearised = False
+
+    def _linearise(self, state):
+        """jacob_constr_blocks + chol_gram_blocks + log_det_sqrt_gram + grad_log_det_sqrt_gram in one
+        device pass (the reference also computes them together, :1173-1184)."""
+        self._upload(state)
+        if not self._linearised:
+            self._bc.linearize(True)
+            self._ld = float(self._bc.log_det_sqrt_gram()[0])
+            self._grad = self._bc.grad_log_det_sqrt_gram()[0]
+            self._linearised = True
+
+    # ---- cached system functions (:1151-1184) ----------------------------------------------------
+    @cache_in_state("pos", "x_obs_seq", "partition")
+    def constr(self, state):
+        self._upload(state)
+        return self._bc.constr()[0]
+
+    @cache_in_state("pos", "x_obs_seq", "partition")
+    def jacob_constr_blocks(self, state):
+        """Dense ``(dc_du_blocks, dc_dv_blocks, dc_dn_blocks)`` rebuilt on the host from the compressed
+        device factors (only tests / diagnostics need them: the device solvers use the factors directly)."""
+        self._linearise(state)
+        return _dense_jacobian_blocks(self, int(state.partition))
+
+    @cache_in_state("pos", "x_obs_seq", "partition")
+    def chol_gram_blocks(self, state):
+        """``(chol_C, chol_D_blocks)`` (lower Cholesky factors, reference layout) from the device factors."""
+        self._linearise(state)
+        return _dense_cholesky_blocks(self, int(state.partition))
+
+    @cache_in_state("pos", "x_obs_seq", "partition")
+    def log_det_sqrt_gram(self, state):
+        self._linearise(state)
+        return self._ld
+
+    @cache_in_state_with_aux(("pos", "x_obs_seq", "partition"), ("log_det_sqrt_gram",))
+    def grad_log_det_sqrt_gram(self, state):
+        self._linearise(state)
+        return np.array(self._grad, copy=True), self._ld
+
+    # ---- Hamiltonian components (:1186-1238) -----------------------------------------------------
+    def h1(self, state):
+        if self.use_gaussian_splitting:
+            return self.log_det_sqrt_gram(state)
+        return self.neg_log_dens(state) + self.log_det_sqrt_gram(state)
+
+    def dh1_dpos(self, state):
+        if self.use_gaussian_splitting:
+            return self.grad_log_det_sqrt_gram(state)
+        return self.grad_neg_log_dens(state) + self.grad_log_det_sqrt_gram(state)
+
+    def h2(self, state):
+        if self.use_gaussian_splitting:
+            return 0.5 * state.pos @ state.pos + 0.5 * state.mom @ state.mom
+        return 0.5 * state.mom @ state.mom
+
+    def dh2_dmom(self, state):
+        return state.mom
+
+    def dh2_dpos(self, state):
+        return state.pos if self.use_gaussian_splitting else 0 * state.pos
+
+    def dh_dpos(self, state):
+        if self.use_gaussian_splitting:
+            return self.dh1_dpos(state) + self.dh2_dpos(state)
+        return self.dh1_dpos(state)
+
+    def h2_flow(self, state, dt):
+        if self.use_gaussian_splitting:
+            sin_dt, cos_dt = np.sin(dt), np.cos(dt)
+            pos = state.pos.copy()
+            state.pos = cos_dt * pos + sin_dt * state.mom
+            state.mom = cos_dt * state.mom - sin_dt * pos
+        else:
+            state.pos = state.pos + dt * self.dh2_dmom(state)
+
+    def dh2_flow_dmom(self, dt):
+        if self.use_gaussian_splitting:
+            return np.sin(dt) * IdentityMatrix(), np.cos(dt) * IdentityMatrix()
+        return dt * IdentityMatrix(), IdentityMatrix()
+
+    # ---- :1240-1259 ----------------------------------------------------------------------------------
+    def update_x_obs_seq(self, state):
+        self._upload(state)
+        self._bc.update_x_obs_seq()
+        _, _, x = self._bc.get_state()
+        state.x_obs_seq = x[0]
+        self._resident = None   # x_obs_seq changed on the device: refresh the key on next use
+
+    def normal_space_component(self, state, vct):
+        self._linearise(state)
+        return self._bc.normal_space_component(np.asarray(vct, dtype=np.float64)[None])[0]
+
+    def project_onto_cotangent_space(self, mom, state):
+        mom = mom - self.normal_space_component(state, mom)
+        return mom
+
+    def sample_momentum(self, state, rng):
+        mom = rng.standard_normal(state.pos.shape)
+        return self.project_onto_cotangent_space(mom, state)
+
+    # ---- projection solves on the device ----------------------------------------------------------
+    def _project(self, state_prev, q_in, solver, constraint_tol, position_tol, divergence_tol, max_iters):
+        self._linearise(state_prev)
+        o = self._bc.opts
+        o.solver, o.constraint_tol, o.position_tol = solver, constraint_tol, position_tol
+        o.divergence_tol, o.max_iters = divergence_tol, int(max_iters)
+        q_out, status, iters = self._bc.project_quasi_newton(np.asarray(q_in, dtype=np.float64)[None])
+        return q_out[0], int(status[0]), int(iters[0])
+
+
+def _solve_projection(state, state_prev, dt, system, solver, name, constraint_tol, position_tol, divergence_tol,
+                      max_iters):
+    q_in = np.array(state.pos, dtype=np.float64, copy=True)
+    q_out, status, iters = system._project(state_prev, q_in, solver, constraint_tol, position_tol, divergence_tol,
+                                           max_iters)
+    if state._call_counts is not None:  # :1382-1387
+        key = _cache_key_func(system, system.constr)
+        state._call_counts[key] = state._call_counts.get(key, 0) + iters
+    if status == 0:
+        state.pos = q_out
+        if state.mom is not None:
+            # mu = dq for the identity metric; returned as mu / dt (or mu / sin dt), then
+            # state.mom -= dh2_flow_mom_dmom @ mu   (:1060-1063, :1388-1392)
+            scale = (np.cos(dt) / np.sin(dt)) if system.use_gaussian_splitting else 1.0 / dt
+            state.mom = state.mom - scale * (q_in - q_out)
+        return state
+    if status & 2:
+        raise ConvergenceError(f"{name} iteration diverged on iteration {iters}.")
+    raise ConvergenceError(f"{name} iteration did not converge (status {status}) after {iters} iterations.")
+
+
+def jitted_solve_projection_onto_manifold_quasi_newton(
+        state, state_prev, dt, system, constraint_tol=1e-8, position_tol=1e-8, divergence_tol=1e10, max_iters=50):
+    """Symmetric quasi-Newton solver for projecting points onto manifold (:1323-1402), on device."""
+    return _solve_projection(state, state_prev, dt, system, SOLVER_QUASI_NEWTON, "Quasi-Newton",
+                             constraint_tol, position_tol, divergence_tol, max_iters)
+
+
+def jitted_solve_projection_onto_manifold_newton(
+        state, state_prev, dt, system, constraint_tol=1e-8, position_tol=1e-8, divergence_tol=1e10, max_iters=50):
+    """Newton solver for projecting points onto manifold (:1405-1476), on device."""
+    return _solve_projection(state, state_prev, dt, system, SOLVER_NEWTON, "Newton",
+                             constraint_tol, position_tol, divergence_tol, max_iters)
+
+
+class SwitchPartitionTransition(Transition):
+    """Markov transition that deterministically switches conditioned partition (:1262-1282)."""
+
+    def __init__(self, system):
+        self.system = system
+        self.num_partition = system.num_partition
+
+    state_variables = {"partition", "x_obs_seq"}
+    statistic_types = None
+
+    def sample(self, state, rng):
+        state.partition = (state.partition + 1) % self.num_partition
+        self.system.update_x_obs_seq(state)
+        return state, None
+
+
+class ConditionedDiffusionHamiltonianState(ChainState):
+    """Markov chain state for conditioned diffusion Hamiltonian system (:1285-1320)."""
+
+    def __init__(self, pos, x_obs_seq, partition=0, mom=None, dir=1, _call_counts=None, _dependencies=None,
+                 _cache=None, _read_only=False):
+        if _call_counts is None:
+            _call_counts = {}
+        super().__init__(pos=pos, x_obs_seq=x_obs_seq, partition=partition, mom=mom, dir=dir,
+                         _call_counts=_call_counts, _dependencies=_dependencies, _cache=_cache,
+                         _read_only=_read_only)
+
+
+def find_initial_state_by_linear_interpolation(system, rng, generate_x_obs_seq_init, u=None, v_0=None,
+                                               **model_dict):
+    """Find an initial constraint satisfying state linearly interpolating noise sequence (:1479-1547):
+    the per-step linear solves run on the device (k_init_interp)."""
+    md = system.model_dict if not model_dict else model_dict
+    u = rng.standard_normal(md["dim_u"]) if u is None else np.asarray(u, dtype=np.float64)
+    v_0 = rng.standard_normal(md["dim_v_0"]) if v_0 is None else np.asarray(v_0, dtype=np.float64)
+    x_obs_seq = np.asarray(generate_x_obs_seq_init(rng), dtype=np.float64)
+    bc = system._bc
+    bc.init_linear_interpolation(u[None], v_0[None], x_obs_seq[None], 0)
+    q, _, _ = bc.get_state()
+    system._resident = None
+    state = ConditionedDiffusionHamiltonianState(pos=q[0], x_obs_seq=x_obs_seq)
+    state.mom = system.sample_momentum(state, rng)
+    return state
+
+
+# ---------------------------------------------------------------------------------------------------
+# dense blocks in the reference's layout, rebuilt from the compressed device factors (host, NumPy)
+# ---------------------------------------------------------------------------------------------------
+def _block_shapes(system, partition):
+    T, S, R, U, X, V, V0, noise = system._dims
+    if system.num_partition == 1:
+        return [(0, T, True, True)]
+    init = R if partition == 0 else R // 2
+    out = [(0, init, True, False)]
+    o = init
+    while T - o > R:
+        out.append((o, R, False, False))
+        o += R
+    out.append((o, T - o, False, True))
+    return out
+
+
+def _dense_jacobian_blocks(system, partition):
+    """Per block (first, middle..., last): dc_du [rows, U], dc_dv [rows, (V0 +) n*S*V], dc_dn [rows, n] or None.
+    Row r of d c / d v_t inside interval k is H_r Phi(t_kr, t_k) K_t."""
+    T, S, R, U, X, V, V0, noise = system._dims
+    bc = system._bc
+    K = bc.get_factor("K")[0]
+    Psib = bc.get_factor("Psib")[0]
+    A = bc.get_factor("A")[0]
+    q = np.frombuffer(system._resident[0], dtype=np.float64)
+    sigma = 0.0 if noise == 0 else (bc._sigma_fixed if noise == 1 else float(np.exp(q[U - 1])))
+    dc_du, dc_dv, dc_dn = [], [], []
+    for b, (o, n, ini, fin) in enumerate(_block_shapes(system, partition)):
+        ny = n if (fin or noise) else n - 1
+        nx = 0 if fin else X
+        nrows = ny + nx
+        Kb = K[b].reshape(-1, S, X, V)[:n]
+        Pb = Psib[b].reshape(-1, X, X)[:n]
+        Ab = A[b].reshape(-1, U)[:nrows]
+        Jv = np.zeros((nrows, (V0 if ini else 0) + n * S * V))
+        off = V0 if ini else 0
+        for r in range(nrows):
+            kr = r if r < ny else n - 1
+            h = np.zeros(X)
+            if r < ny:
+                h[0] = 1.0  # obs_func gradient of the FHN model (x[0]); nonlinear models use xend
+            else:
+                h[r - ny] = 1.0
+            vec = h
+            for k in range(kr, -1, -1):
+                if k < kr:
+                    vec = Pb[k + 1].T @ vec
+                Jv[r, off + k * S * V: off + (k + 1) * S * V] = np.einsum("i,tij->tj", vec, Kb[k]).reshape(-1)
+            if ini:
+                Jv[r, :V0] = (Pb[0].T @ vec)[:V0]  # d x_0 / d v_0 = I for the registered models
+        Jn = None
+        if noise:
+            Jn = np.zeros((nrows, n))
+            Jn[np.arange(ny), np.arange(ny)] = sigma
+        dc_du.append(Ab.copy())
+        dc_dv.append(Jv)
+        dc_dn.append(Jn)
+    return tuple(dc_du), tuple(dc_dv), tuple(dc_dn)
+
+
+def _dense_cholesky_blocks(system, partition):
+    T, S, R, U, X, V, V0, noise = system._dims
+    bc = system._bc
+    L = bc.get_factor("L")[0]
+    LC = bc.get_factor("LC")[0]
+
+    def unpack(packed, n):
+        M = np.zeros((n, n))
+        M[np.tril_indices(n)] = packed[: n * (n + 1) // 2]
+        M[np.diag_indices(n)] = 1.0 / np.diag(M)   # the device stores the diagonal inverted
+        return M
+
+    chol_D = []
+    for b, (o, n, ini, fin) in enumerate(_block_shapes(system, partition)):
+        nrows = (n if (fin or noise) else n - 1) + (0 if fin else X)
+        chol_D.append(unpack(L[b], nrows))
+    return unpack(LC, U), tuple(chol_D)
