@@ -140,8 +140,11 @@ int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_pa
 int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, int* status);
 /* per-chain status / diagnostics of the last step (any pointer may be NULL) */
 int mmd_get_step_info(mmd_handle h, int* status, int* iters_fwd, int* iters_rev, double* rev_dist);
-/* jitted_solve_projection_onto_manifold_quasi_newton (:1323-1402) on host inputs: projects
- * q [n][dim_q] using the linearisation at the resident position; returns projected q and mu. */
+/* jitted_solve_projection_onto_manifold_quasi_newton (:1323-1402) or, with opts->solver ==
+ * MMD_SOLVER_NEWTON, jitted_solve_projection_onto_manifold_newton (:1405-1476; per iteration the
+ * constraint is re-linearised at the iterate and the non-symmetric block products J(q) J(q_prev)^T are
+ * LU-factorised, :689-763, :944-981) on host inputs: projects q [n][dim_q] using the linearisation at
+ * the resident position; returns the projected q, per-chain status bits and iteration counts. */
 int mmd_project_quasi_newton(mmd_handle h, const double* q_in, double dt, const mmd_integrator_opts* opts,
                              double* q_out, int* status, int* iters);
 

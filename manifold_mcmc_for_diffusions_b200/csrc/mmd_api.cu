@@ -181,9 +181,10 @@ struct Ops {
     CK(cudaGetLastError());
     return 0;
   }
-  static int qn(mmd_handle h, int mode, double mom_coef, const mmd_integrator_opts* o) {
+  template <bool NEWTON>
+  static int qn_t(mmd_handle h, int mode, double mom_coef, const mmd_integrator_opts* o) {
     ProfScope ps(h, KID_QN);
-    auto kern = k_qn<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
+    auto kern = k_qn<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB, NEWTON>;
     const int n = nt(h);
     if (prep(kern, smem(n))) return -2;
     kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, mode, mom_coef,
@@ -193,9 +194,13 @@ struct Ops {
     CK(cudaGetLastError());
     return 0;
   }
-  static int leapfrog(mmd_handle h, double dt, const mmd_integrator_opts* o, int n_steps, int reset_status) {
+  static int qn(mmd_handle h, int mode, double mom_coef, const mmd_integrator_opts* o) {
+    return o->solver == MMD_SOLVER_NEWTON ? qn_t<true>(h, mode, mom_coef, o) : qn_t<false>(h, mode, mom_coef, o);
+  }
+  template <bool NEWTON>
+  static int leapfrog_t(mmd_handle h, double dt, const mmd_integrator_opts* o, int n_steps, int reset_status) {
     ProfScope ps(h, KID_LEAPFROG);
-    auto kern = k_leapfrog<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
+    auto kern = k_leapfrog<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB, NEWTON>;
     const int n = nt(h);
     if (prep(kern, smem(n))) return -2;
     kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, step_coef(h->d, dt),
@@ -205,6 +210,10 @@ struct Ops {
     h->launches++;
     CK(cudaGetLastError());
     return 0;
+  }
+  static int leapfrog(mmd_handle h, double dt, const mmd_integrator_opts* o, int n_steps, int reset_status) {
+    return o->solver == MMD_SOLVER_NEWTON ? leapfrog_t<true>(h, dt, o, n_steps, reset_status)
+                                          : leapfrog_t<false>(h, dt, o, n_steps, reset_status);
   }
   static int hamiltonian(mmd_handle h, int sel, double* out) {
     const int n = nt(h);
@@ -687,7 +696,7 @@ static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opt
                          int n_steps = 1) {
   mmd_integrator_opts o;
   if (opts) o = *opts; else mmd_default_integrator_opts(&o);
-  if (o.solver != MMD_SOLVER_QUASI_NEWTON) FAIL("only the quasi-Newton projection solver is built");
+  if (o.solver != MMD_SOLVER_QUASI_NEWTON && o.solver != MMD_SOLVER_NEWTON) FAIL("unknown projection solver");
   if (!h->lin_valid) {
     int rc0 = mmd_linearize(h, 1);
     if (rc0) return rc0;

@@ -527,7 +527,7 @@ MMD_D void dev_constr(const Dims& d, const Slots& S, const Work& W, const double
 #pragma unroll
     for (int i = 0; i < X; ++i) a.xstart[i] = x[i];
     a.vb = q.body; a.nzb = q.noise; a.xoc = xoc; a.y = y; a.Kb = nullptr; a.alph = nullptr; a.lamtot = nullptr;
-    a.crow = sm_c; a.ring = sm_ring; a.xend_out = nullptr;
+    a.crow = sm_c; a.ring = sm_ring; a.xend_out = nullptr; a.xs_out = nullptr;
     a.nta = t.nta; a.cpb = t.cpb; a.NT = NT; a.tid = t.tid;
     constr_sweep<M, false>(d, B, a);
   }
@@ -749,6 +749,227 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
 }
 
 // ------------------------------------------------------------------------------------------
+// Newton iteration body (newton_projection :1065-1135, lu_jacob_product_blocks :689-763,
+// lmult_by_inv_jacob_product :944-981): linearise the constraint at the CURRENT iterate, form the
+// non-symmetric block products D_b = J_v(q) J_v(q_lin)^T by the cross-covariance recursion
+//   P_k = Psib_k(q) P_{k-1} Psib_k(q_lin)^T + sum_t K_t(q) K_t(q_lin)^T ,
+// LU-factorise them with partial pivoting, and solve
+//   (J(q) J(q_lin)^T) lam = c   via   C = I + sum_b A_b(q_lin)^T D_b^{-1} A_b(q)   (Woodbury).
+// On entry the forward sweep has stored the trajectory in W.xs and c in `rr`; on return rr = lam_b.
+// ------------------------------------------------------------------------------------------
+template <class M, int NRMAX, int RMAX, int UMAX>
+MMD_D void newton_solve_block(const Dims& d, const Blk& B, bool work, const ChainPar<M, UMAX>& P, double sig_lin,
+                              const double* dx0_dv0_lin, const QPtr& qw, const double* __restrict__ Kc,
+                              const double* __restrict__ Psibc, const double* __restrict__ xendc,
+                              const double* __restrict__ Ac, const double* __restrict__ alph, const double* lamtot,
+                              const Work& W, double* rr, double* s_out, double* extra_max, double* sm_red,
+                              const Tid& t, int NT) {
+  constexpr int X = M::X, V = M::V, Z = M::Z, XV = M::X * M::V;
+  const int U = d.U, nta = t.nta;
+  double Cb[UMAX * UMAX], gb[UMAX + 1];
+#pragma unroll
+  for (int i = 0; i < UMAX * UMAX; ++i) Cb[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < UMAX; ++i) gb[i] = 0.0;
+  gb[UMAX] = extra_max ? *extra_max : 0.0;
+  double Dm[NRMAX * NRMAX], DiA[NRMAX * UMAX], Am[NRMAX * UMAX];
+  int piv[NRMAX];
+  const int nr = work ? B.nrows : 0;
+  if (work) {
+    const double* xsc = tpr<X>(W.xs, d.rmax * d.S * X, t);
+    double* Pcc = tp(W.Mk, d.rmax * X * X, t);   // Psib at the current iterate
+    double* Qc = tp(W.Qk, d.rmax * X * X, t);    // cross sums  sum_t K_t(q) K_t(q_lin)^T
+    double* Ztc = tp(W.Zt, d.rmax * X * Z, t);
+    double dx0_dv0[X * M::V0], dx0_dz[X * Z];
+    M::gen_x0_jac(P.z, dx0_dv0, dx0_dz);
+    // ---- backward sweeps per interval at the current iterate
+    for (int k = 0; k < B.n; ++k) {
+      double al[X];
+      ldcol<X>(alph + k * X * nta, nta, al);
+      double Psi[X * X], Qk[X * X], Zk[X * Z];
+#pragma unroll
+      for (int i = 0; i < X * X; ++i) { Psi[i] = (i % (X + 1) == 0) ? 1.0 : 0.0; Qk[i] = 0.0; }
+#pragma unroll
+      for (int i = 0; i < X * Z; ++i) Zk[i] = 0.0;
+      for (int tt = d.S - 1; tt >= 0; --tt) {
+        const int so = (k * d.S + tt) * nta;
+        double xt[X], v[V], Kp[XV], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], tmp[X * X];
+        ldrec<X>(xsc + so * X, xt);
+        ldrec<V>(qw.body + so * V, v);
+        ldrec<XV>(Kc + so * XV, Kp);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+#pragma unroll
+          for (int i = 0; i < X; ++i) v[j] = fma(-Kp[i * V + j], al[i], v[j]);
+        M::jac_x(P.C, xt, v, F);
+        M::jac_v(P.C, xt, v, Bm);
+        M::jac_z(P.C, xt, v, G);
+        mm<X, V, X>(Psi, Bm, Kt);
+#pragma unroll
+        for (int i = 0; i < X; ++i)
+#pragma unroll
+          for (int j = 0; j < X; ++j) {
+            double sv = Qk[i * X + j];
+#pragma unroll
+            for (int l = 0; l < V; ++l) sv = fma(Kt[i * V + l], Kp[j * V + l], sv);
+            Qk[i * X + j] = sv;
+          }
+        mm_acc<X, Z, X>(Psi, G, Zk);
+        mm<X, X, X>(Psi, F, tmp);
+#pragma unroll
+        for (int i = 0; i < X * X; ++i) Psi[i] = tmp[i];
+      }
+      stcol<X * X>(Pcc + k * X * X * nta, nta, Psi);
+      stcol<X * X>(Qc + k * X * X * nta, nta, Qk);
+      stcol<X * Z>(Ztc + k * X * Z * nta, nta, Zk);
+    }
+    // ---- per-observation algebra: A_b(q) rows and the full (non-symmetric) D_b
+    double Su[X * Z], Pm[X * X], wc[NRMAX * X], wp[NRMAX * X];
+#pragma unroll
+    for (int i = 0; i < X * Z; ++i) Su[i] = B.ini ? dx0_dz[i] : 0.0;
+    if (B.ini) {
+      mmt<X, X, M::V0>(dx0_dv0, dx0_dv0_lin, Pm);
+    } else {
+#pragma unroll
+      for (int i = 0; i < X * X; ++i) Pm[i] = 0.0;
+    }
+    int nrow_done = 0;
+    for (int k = 0; k < B.n; ++k) {
+      double Pc[X * X], Pp[X * X], Qk[X * X], Zk[X * Z], t1[X * Z], t2[X * X], t3[X * X];
+      ldcol<X * X>(Pcc + k * X * X * nta, nta, Pc);
+      ldcol<X * X>(Psibc + k * X * X * nta, nta, Pp);
+      ldcol<X * X>(Qc + k * X * X * nta, nta, Qk);
+      ldcol<X * Z>(Ztc + k * X * Z * nta, nta, Zk);
+      mm<X, Z, X>(Pc, Su, t1);
+#pragma unroll
+      for (int i = 0; i < X * Z; ++i) Su[i] = t1[i] + Zk[i];
+      mm<X, X, X>(Pc, Pm, t2);
+      mmt<X, X, X>(t2, Pp, t3);
+#pragma unroll
+      for (int i = 0; i < X * X; ++i) Pm[i] = t3[i] + Qk[i];
+      for (int r = 0; r < nrow_done; ++r) {
+        double tw[X];
+        mv<X, X>(Pc, &wc[r * X], tw);       // Phi_c(k, k_r) P_{k_r} h_r(lin)
+#pragma unroll
+        for (int i = 0; i < X; ++i) wc[r * X + i] = tw[i];
+        mv<X, X>(Pp, &wp[r * X], tw);       // Phi_lin(k, k_r) P_{k_r}^T h_r(cur)
+#pragma unroll
+        for (int i = 0; i < X; ++i) wp[r * X + i] = tw[i];
+      }
+      const int n_new = (k < B.ny ? 1 : 0) + ((k == B.n - 1) ? B.nx : 0);
+      const int first_new = nrow_done;
+      for (int a = 0; a < n_new; ++a) {
+        double hc[X], hp[X];
+        const bool yrow = (k < B.ny) && a == 0;
+        if (yrow) {
+          double xe[X];
+          // current iterate: state at the end of the interval = start of the next one (or recomputed)
+          if (!M::OBS_LINEAR) ldcol<X>(tp(W.Yb, d.rmax * X * X, t) + k * X * nta, nta, xe);
+          M::obs_grad(xe, hc);
+          if (!M::OBS_LINEAR) ldcol<X>(xendc + k * X * nta, nta, xe);
+          M::obs_grad(xe, hp);
+        } else {
+          const int comp = a - ((k < B.ny) ? 1 : 0);
+#pragma unroll
+          for (int i = 0; i < X; ++i) hc[i] = hp[i] = (i == comp) ? 1.0 : 0.0;
+        }
+        const int r = nrow_done;
+        mv<X, X>(Pm, hp, &wc[r * X]);       // P_k h_r(lin)
+        mtv<X, X>(Pm, hc, &wp[r * X]);      // P_k^T h_r(cur)
+        for (int j = 0; j < first_new; ++j) {
+          double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < X; ++i) {
+            s1 = fma(hc[i], wc[j * X + i], s1);   // D[r][j], k_r > k_j
+            s2 = fma(wp[j * X + i], hp[i], s2);   // D[j][r]
+          }
+          Dm[r * NRMAX + j] = s1;
+          Dm[j * NRMAX + r] = s2;
+        }
+        double az[Z];
+        mtv<X, Z>(Su, hc, az);
+        for (int j = 0; j < U; ++j) {
+          double sv = 0.0;
+          if (j < Z) {
+#pragma unroll
+            for (int m = 0; m < Z; ++m) sv = fma(az[m], P.dzdu[m * Z + j], sv);
+          }
+          Am[r * UMAX + j] = sv;
+        }
+        if (d.noisy == 2 && yrow) {
+          const double nk = qw.noise[k * nta] - sig_lin * lamtot[k * NT];
+          Am[r * UMAX + Z] = P.sigy * nk;
+        }
+        nrow_done++;
+      }
+      // rows created at the same observation: D[r][j] = h_r(cur) . P_k h_j(lin)
+      for (int r = first_new; r < nrow_done; ++r)
+        for (int j = first_new; j < nrow_done; ++j) {
+          double hc[X];
+          const bool yr = (k < B.ny) && r == first_new;
+          if (yr) {
+            double xe[X];
+            if (!M::OBS_LINEAR) ldcol<X>(tp(W.Yb, d.rmax * X * X, t) + k * X * nta, nta, xe);
+            M::obs_grad(xe, hc);
+          } else {
+            const int comp = (r - first_new) - ((k < B.ny) ? 1 : 0);
+#pragma unroll
+            for (int i = 0; i < X; ++i) hc[i] = (i == comp) ? 1.0 : 0.0;
+          }
+          double sv = 0.0;
+#pragma unroll
+          for (int i = 0; i < X; ++i) sv = fma(hc[i], wc[j * X + i], sv);
+          if (d.noisy && yr && j == r) sv += P.sigy * sig_lin;
+          Dm[r * NRMAX + j] = sv;
+        }
+    }
+    lu_factor<NRMAX>(Dm, piv, nr);
+    lu_solve<NRMAX>(Dm, piv, nr, rr);       // t_b = D_b^{-1} c_b
+    for (int j = 0; j < U; ++j) {
+      double col[NRMAX];
+      for (int r = 0; r < nr; ++r) col[r] = Am[r * UMAX + j];
+      lu_solve<NRMAX>(Dm, piv, nr, col);
+      for (int r = 0; r < nr; ++r) DiA[r * UMAX + j] = col[r];
+    }
+    for (int r = 0; r < nr; ++r) {
+      for (int i = 0; i < U; ++i) {
+        const double ap = Ac[(r * U + i) * nta];        // A_b(q_lin)
+        gb[i] = fma(ap, rr[r], gb[i]);
+        for (int j = 0; j < U; ++j) Cb[i * UMAX + j] = fma(ap, DiA[r * UMAX + j], Cb[i * UMAX + j]);
+      }
+    }
+  }
+  // cross-block sums: C (UMAX^2 values, in chunks that fit the reduction scratch) and [g | max |c|]
+  constexpr int CH = 8;
+#pragma unroll
+  for (int c0 = 0; c0 < UMAX * UMAX; c0 += CH) {
+    double chunk[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) chunk[i] = (c0 + i < UMAX * UMAX) ? Cb[c0 + i] : 0.0;
+    block_reduce<CH, 0>(chunk, sm_red, t);
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (c0 + i < UMAX * UMAX) Cb[c0 + i] = chunk[i];
+  }
+  block_reduce<UMAX, 1>(gb, sm_red, t);
+  if (extra_max) *extra_max = gb[UMAX];
+  for (int i = 0; i < U; ++i) Cb[i * UMAX + i] += 1.0;   // M_0 = I
+  int pivC[UMAX];
+  lu_factor<UMAX>(Cb, pivC, U);
+  lu_solve<UMAX>(Cb, pivC, U, gb);
+#pragma unroll
+  for (int j = 0; j < UMAX; ++j) s_out[j] = gb[j];
+  if (work) {
+    // lam_b = D_b^{-1} (c_b - A_b(q) s) = t_b - (D_b^{-1} A_b(q)) s
+    for (int r = 0; r < nr; ++r) {
+      double tv = rr[r];
+      for (int j = 0; j < U; ++j) tv = fma(-DiA[r * UMAX + j], gb[j], tv);
+      rr[r] = tv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // dev_qn: on-device symmetric quasi-Newton projection loop (quasi_newton_projection :1009-1063 and
 // its host wrapper :1323-1402) for a tile of chains, masked per chain, no host round trips.
 //   iterate:  c = constr(q) ; err = |c|_inf ; lam = G_lin^{-1} c ; q -= J_lin^T lam
@@ -756,7 +977,7 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
 // mode 0 (forward):  linearisation = cur; on convergence q(other) = q_new, p(other) = pw - mom_coef * mu
 // mode 1 (reverse):  linearisation = other; compare q_back with q(cur) -> revd, no writes (Mici reverse check)
 // ------------------------------------------------------------------------------------------
-template <class M, int NRMAX, int RMAXP, int UMAX>
+template <class M, int NRMAX, int RMAXP, int UMAX, bool NEWTON>
 MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ y, int part, int mode,
                   double mom_coef, double ctol, double ptol, double dtol, int max_iters) {
   const Tid t = thread_id(d);
@@ -811,6 +1032,7 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
     for (int r = 0; r < NRMAX; ++r) sm_l[r * NT] = 0.0;
   }
   double final_norm = 0.0;
+  ChainPar<M, UMAX> Pkeep;
   while (true) {
     if (__syncthreads_and(done ? 1 : 0)) break;
     const bool work = in_blk && !done;
@@ -839,9 +1061,12 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
         for (int i = 0; i < X; ++i) a.xstart[i] = x[i];
         a.vb = qw.body; a.nzb = qw.noise; a.xoc = xoc; a.y = y; a.Kb = Kc; a.alph = alph; a.lamtot = sm_l;
         a.crow = sm_c; a.ring = sm_ring; a.xend_out = nullptr;
+        a.xs_out = NEWTON ? tpr<X>(W.xs, d.rmax * d.S * X, t) : nullptr;
+        if (NEWTON && !M::OBS_LINEAR) a.xend_out = tp(W.Yb, d.rmax * X * X, t);
         a.nta = nta; a.cpb = cpb; a.NT = NT; a.tid = t.tid;
         constr_sweep<M, true>(d, B, a);
       }
+      if (NEWTON) Pkeep = P;
     }
     double rr[NRMAX];
     {
@@ -857,7 +1082,11 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
     // the prefetch ring of the sweep and the reduction scratch share shared memory: every thread must have
     // left its sweep before any thread starts the cross-block reduction
     __syncthreads();
-    inv_gram_block<M, NRMAX, UMAX>(d, B, work, Ac, Lc, DinvAc, LCc, rr, sres, &err, sm_red, t);
+    if (NEWTON)
+      newton_solve_block<M, NRMAX, RMAXP, UMAX>(d, B, work, Pkeep, sig_lin, dx0_dv0, qw, Kc, Psibc, xendc, Ac, alph,
+                                                sm_l, W, rr, sres, &err, sm_red, t, NT);
+    else
+      inv_gram_block<M, NRMAX, UMAX>(d, B, work, Ac, Lc, DinvAc, LCc, rr, sres, &err, sm_red, t);
     // norm of this iteration's update and (speculative) finalisation when the constraint is met
     const bool check = !done && (err < ctol);
     double nrm[1];
@@ -1024,11 +1253,11 @@ k_project(Dims d, Slots S, Work W, int part, int lin_sel, int src_sel, int dst_s
           FlowCoef fl) {
   dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, lin_sel, src_sel, dst_sel, h, qcoef, fl);
 }
-template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB>
+template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB, bool NEWTON>
 __global__ void __launch_bounds__(NTMAX, MINB)
 k_qn(Dims d, Slots S, Work W, const double* __restrict__ y, int part, int mode, double mom_coef, double ctol,
      double ptol, double dtol, int max_iters) {
-  dev_qn<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, mode, mom_coef, ctol, ptol, dtol, max_iters);
+  dev_qn<M, NRMAX, RMAX, UMAX, NEWTON>(d, S, W, y, part, mode, mom_coef, ctol, ptol, dtol, max_iters);
 }
 __global__ void k_commit(Dims d, Slots S, Work W, double rev_tol, long long* __restrict__ n_ok) {
   const int cix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1050,7 +1279,7 @@ struct StepCoef {
 // projection iterations delay just their own small CTA while the other resident CTAs keep the SM busy
 // (the per-chain iteration count is long-tailed: mean ~8, 1 % > 30, max_iters = 50).
 // Step order: Mici ConstrainedLeapfrogIntegrator._step = A(dt/2) B(dt) A(dt/2), SURVEY.md 3.3.
-template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB>
+template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB, bool NEWTON>
 __global__ void __launch_bounds__(NTMAX, MINB)
 k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, StepCoef sc, double ctol, double ptol,
            double dtol, int max_iters, double rev_tol, long long* __restrict__ n_ok, int n_steps,
@@ -1062,13 +1291,13 @@ k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, Step
     __syncthreads();
     dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 0, PSEL_CUR, PSEL_WORK, sc.half_dt, sc.qcoef, sc.fwd);
     __syncthreads();
-    dev_qn<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, 0, sc.mom_coef, ctol, ptol, dtol, max_iters);
+    dev_qn<M, NRMAX, RMAX, UMAX, NEWTON>(d, S, W, y, part, 0, sc.mom_coef, ctol, ptol, dtol, max_iters);
     __syncthreads();
     dev_point<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, 1, 1);
     __syncthreads();
     dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 1, PSEL_OTHER, PSEL_OTHER, 0.0, 0.0, sc.back);
     __syncthreads();
-    dev_qn<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, 1, 0.0, ctol, ptol, dtol, max_iters);
+    dev_qn<M, NRMAX, RMAX, UMAX, NEWTON>(d, S, W, y, part, 1, 0.0, ctol, ptol, dtol, max_iters);
     __syncthreads();
     dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 1, PSEL_OTHER, PSEL_OTHER, sc.half_dt, sc.qcoef, noflow);
     __syncthreads();

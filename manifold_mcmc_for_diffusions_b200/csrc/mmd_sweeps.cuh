@@ -112,6 +112,7 @@ struct SweepArgs {
   double* crow;          // shared-memory column (out)
   double* ring;          // CTA ring base (shared)
   double* xend_out;      // thread-private [rmax*X] or null
+  double* xs_out;        // thread-private trajectory records [rmax*S][X] (state BEFORE each step) or null
   int nta, cpb, NT, tid;
 };
 
@@ -149,6 +150,7 @@ __device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const Swe
   for (int s = 0; s < ns; ++s) {
     cp_async_wait<PF - 1>();
     double v[V], xn[X];
+    if (a.xs_out) strec<X>(a.xs_out + s * X * nta, x);
     lds_rec<V>(rd, v);
     if (WITH_K) {
       double Kt[XV];
@@ -201,6 +203,46 @@ __device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const Swe
     }
   }
   cp_async_wait<0>();
+}
+
+// in-place LU factorisation with partial pivoting of a dense n x n matrix (row-major, leading dimension
+// LD), as scipy.linalg.lu_factor does for the reference's Newton solver (mici_extensions.py:745-763)
+template <int LD>
+MMD_D void lu_factor(double* A, int* piv, int n) {
+  for (int c = 0; c < n; ++c) {
+    int p = c;
+    double best = fabs(A[c * LD + c]);
+    for (int r = c + 1; r < n; ++r) {
+      const double a = fabs(A[r * LD + c]);
+      if (a > best) { best = a; p = r; }
+    }
+    piv[c] = p;
+    if (p != c)
+      for (int j = 0; j < n; ++j) { const double tv = A[c * LD + j]; A[c * LD + j] = A[p * LD + j]; A[p * LD + j] = tv; }
+    const double inv = 1.0 / A[c * LD + c];
+    for (int r = c + 1; r < n; ++r) {
+      const double f = A[r * LD + c] * inv;
+      A[r * LD + c] = f;
+      for (int j = c + 1; j < n; ++j) A[r * LD + j] = fma(-f, A[c * LD + j], A[r * LD + j]);
+    }
+  }
+}
+template <int LD>
+MMD_D void lu_solve(const double* A, const int* piv, int n, double* x) {
+  for (int c = 0; c < n; ++c) {
+    const int p = piv[c];
+    if (p != c) { const double tv = x[c]; x[c] = x[p]; x[p] = tv; }
+  }
+  for (int i = 1; i < n; ++i) {
+    double sv = x[i];
+    for (int k = 0; k < i; ++k) sv = fma(-A[i * LD + k], x[k], sv);
+    x[i] = sv;
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double sv = x[i];
+    for (int k = i + 1; k < n; ++k) sv = fma(-A[i * LD + k], x[k], sv);
+    x[i] = sv / A[i * LD + i];
+  }
 }
 
 // obs-level backward recursion: alpha_k = H_k^T lambda_k + Psib_{k+1}^T alpha_{k+1}  (J^T lambda in
