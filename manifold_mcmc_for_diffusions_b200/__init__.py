@@ -22,6 +22,7 @@ def install_reference_aliases(force_mici_compat=False):
     sys.modules["sde.mici_extensions"] = mici_extensions
     sys.modules["sde.example_models"] = example_models
     sys.modules["sde.example_models.fhn"] = example_models.fhn
+    sys.modules["sde.example_models.sir"] = example_models.sir
     have_mici = False
     if not force_mici_compat:
         try:

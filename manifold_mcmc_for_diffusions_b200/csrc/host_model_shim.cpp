@@ -24,3 +24,23 @@ void philox_normal_pair(unsigned long long seed, unsigned long long offset, unsi
   mmd::philox_normal_pair(seed, offset, idx, a, b);
 }
 }
+
+#include "mmd_model_sir.cuh"
+namespace {
+SirModel::Coef scoef(const double* z, double sd) {
+  SirModel::Coef c;
+  SirModel::make_coef(z, sd, c);
+  return c;
+}
+}  // namespace
+extern "C" {
+void sir_step(const double* z, double sd, const double* x, const double* v, double* xn) { SirModel::step(scoef(z, sd), x, v, xn); }
+void sir_jac_x(const double* z, double sd, const double* x, const double* v, double* F) { SirModel::jac_x(scoef(z, sd), x, v, F); }
+void sir_jac_v(const double* z, double sd, const double* x, const double* v, double* B) { SirModel::jac_v(scoef(z, sd), x, v, B); }
+void sir_jac_z(const double* z, double sd, const double* x, const double* v, double* G) { SirModel::jac_z(scoef(z, sd), x, v, G); }
+void sir_hess_contract(const double* z, double sd, const double* x, const double* v, const double* Th, double* g) {
+  SirModel::hess_contract(scoef(z, sd), x, v, Th, g);
+}
+void sir_gen_z(const double* u, double* z, double* dzdu) { SirModel::gen_z(u, z, dzdu); }
+void sir_gen_z_second(const double* u, const double* z, const double* Gam, double* extra) { SirModel::gen_z_second(u, z, Gam, extra); }
+}

@@ -1,89 +1,15 @@
 // C ABI (include/mmd_b200.h) over the CHMC kernels.  Host-side orchestration only: allocation,
 // layout conversion, kernel sequencing of one constrained leapfrog step.  No CPU compute path:
 // every entry point fails with an error if CUDA is unavailable.
-#include "../../include/mmd_b200.h"
-
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdio.h>
-#include <string.h>
-#include <stdlib.h>
-
-#include <string>
-#include <vector>
-
+#include "mmd_host.h"
 #include "mmd_kernels_main.cuh"
-#include "mmd_model_fhn.cuh"
-#include "mmd_philox.cuh"
 
 using namespace mmd;
 
-namespace {
-
-thread_local std::string g_err;
-
-#define CK(call)                                                                              \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess) {                                                                  \
-      char buf_[512];                                                                         \
-      snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-      g_err = buf_;                                                                           \
-      return -2;                                                                              \
-    }                                                                                         \
-  } while (0)
-
-#define FAIL(msg)    \
-  do {               \
-    g_err = (msg);   \
-    return -1;       \
-  } while (0)
-
-constexpr int UMAX = 5;      // max dim_u
-#ifndef MMD_NTMAX
-#define MMD_NTMAX 192         // max threads per CTA (= chains per tile x observation blocks)
-#endif
-constexpr int NTMAX = MMD_NTMAX;
-#ifndef MMD_MINB
-#define MMD_MINB 3           // __launch_bounds__ min resident CTAs per SM for the phase kernels
-#endif
-
-}  // namespace
-
-struct mmd_handle_s {
-  Dims d;
-  Slots S;
-  Work W;
-  int model;
-  int X, V, Z, V0;
-  int nrmax;      // constraint rows per block the kernels are instantiated for
-  double* y;      // [T]
-  double* stage;  // [n_chains * dim_q] canonical staging (device)
-  double* stage2;
-  double* tpbuf;  // thread-private scratch [n_tiles][nrmax][nta] (constraint values)
-  double* hbuf;   // [chains]
-  double* h0buf;  // [chains]
-  double* qsave;  // q-like
-  double* qtmp;   // q-like (re-tiling at a partition switch)
-  double* accp;   // [chains]
-  int* accepted;  // [chains]
-  int* cur0;
-  int partition;
-  int ncmax, nbmax;
-  int chain0;     // global index of this handle's first chain (Philox stream offset)
-  bool fused;
-  cudaStream_t stream;
-  cudaEvent_t ev0, ev1;
-  long long launches;
-  bool lin_valid;
-  std::vector<void*> allocs;
-  // optional per-kernel event timing (bench.py's roofline leg)
-  bool prof_on;
-  std::vector<cudaEvent_t> prof_ev;   // pairs
-  std::vector<int> prof_kid;
-  size_t prof_used;
-  long long* n_ok;   // [chains] successful leapfrog steps per chain (device counter)
-};
+std::string& mmd_err() {
+  thread_local std::string e;
+  return e;
+}
 
 namespace {
 
@@ -104,183 +30,8 @@ void partition_shapes(int T, int R, int init, int* nb, int* fin) {
   *nb = 2 + (num_middle > 0 ? num_middle : 0);
 }
 
-enum { KID_POINT = 0, KID_PROJECT = 1, KID_QN = 2, KID_LEAPFROG = 3, KID_OTHER = 4, KID_COUNT = 5 };
 
-struct ProfScope {
-  mmd_handle h;
-  size_t idx;
-  bool on;
-  ProfScope(mmd_handle h_, int kid) : h(h_), idx(0), on(false) {
-    if (h->prof_on && h->prof_used + 2 <= h->prof_ev.size()) {
-      on = true;
-      idx = h->prof_used;
-      h->prof_used += 2;
-      h->prof_kid.push_back(kid);
-      cudaEventRecord(h->prof_ev[idx], h->stream);
-    }
-  }
-  ~ProfScope() {
-    if (on) cudaEventRecord(h->prof_ev[idx + 1], h->stream);
-  }
-};
-
-StepCoef step_coef(const Dims& d, double dt) {
-  StepCoef sc;
-  sc.half_dt = 0.5 * dt;
-  if (d.gaussian) {
-    // h2_flow = exact rotation by dt; dh2_flow_dmom = (sin dt, cos dt) (mici_extensions.py:1222-1238)
-    sc.qcoef = 0.0;
-    sc.fwd = FlowCoef{2, cos(dt), sin(dt), sin(dt)};
-    sc.back = FlowCoef{1, cos(dt), -sin(dt), -sin(dt)};
-    sc.mom_coef = cos(dt) / sin(dt);
-  } else {
-    sc.qcoef = 1.0;
-    sc.fwd = FlowCoef{2, 1.0, dt, 0.0};
-    sc.back = FlowCoef{1, 1.0, -dt, 0.0};
-    sc.mom_coef = 1.0 / dt;
-  }
-  return sc;
-}
-
-// kernel launchers for one model / block-size instantiation
-template <class Mdl, int NRMAX, int RMAX>
-struct Ops {
-  static size_t smem(int nt) { return (size_t)SmemPlan<Mdl, NRMAX, UMAX>::PER_THREAD * nt * sizeof(double); }
-  static int nt(mmd_handle h) { return h->d.nb[h->partition] * h->d.cpb; }
-  template <class Kern>
-  static int prep(Kern kern, size_t bytes) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return 0;
-  }
-  static int point(mmd_handle h, int which, int with_grad) {
-    ProfScope ps(h, KID_POINT);
-    auto kern = k_point<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
-    const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, which, with_grad);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  static int constr(mmd_handle h) {
-    auto kern = k_constr<Mdl, NRMAX, UMAX, NTMAX, MMD_MINB>;
-    const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, h->tpbuf);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  static int project(mmd_handle h, int lin, int src, int dst, double hh, double qcoef, FlowCoef fl) {
-    ProfScope ps(h, KID_PROJECT);
-    auto kern = k_project<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
-    const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->partition, lin, src, dst, hh, qcoef, fl);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  template <bool NEWTON>
-  static int qn_t(mmd_handle h, int mode, double mom_coef, const mmd_integrator_opts* o) {
-    ProfScope ps(h, KID_QN);
-    auto kern = k_qn<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB, NEWTON>;
-    const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, mode, mom_coef,
-                                                   o->constraint_tol, o->position_tol, o->divergence_tol,
-                                                   o->max_iters);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  static int qn(mmd_handle h, int mode, double mom_coef, const mmd_integrator_opts* o) {
-    return o->solver == MMD_SOLVER_NEWTON ? qn_t<true>(h, mode, mom_coef, o) : qn_t<false>(h, mode, mom_coef, o);
-  }
-  template <bool NEWTON>
-  static int leapfrog_t(mmd_handle h, double dt, const mmd_integrator_opts* o, int n_steps, int reset_status) {
-    ProfScope ps(h, KID_LEAPFROG);
-    auto kern = k_leapfrog<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB, NEWTON>;
-    const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, step_coef(h->d, dt),
-                                                   o->constraint_tol, o->position_tol, o->divergence_tol,
-                                                   o->max_iters, o->reverse_check_tol, h->n_ok, n_steps,
-                                                   reset_status);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  static int leapfrog(mmd_handle h, double dt, const mmd_integrator_opts* o, int n_steps, int reset_status) {
-    return o->solver == MMD_SOLVER_NEWTON ? leapfrog_t<true>(h, dt, o, n_steps, reset_status)
-                                          : leapfrog_t<false>(h, dt, o, n_steps, reset_status);
-  }
-  static int hamiltonian(mmd_handle h, int sel, double* out) {
-    const int n = nt(h);
-    k_hamiltonian<Mdl><<<h->d.n_tiles, n, (size_t)n * sizeof(double), h->stream>>>(h->d, h->S, h->W, h->partition,
-                                                                                   sel, out);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  // canonical [n_chains][dim_q] (device) -> tile layout of a q-like vector
-  static int pack(mmd_handle h, const double* canon_dev, double* base, long long stride, int sel) {
-    k_pack<Mdl><<<1184, 256, 0, h->stream>>>(h->d, h->partition, canon_dev, base, stride, h->S.cur, sel);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  static int unpack(mmd_handle h, double* canon_dev, const double* base, long long stride, int sel) {
-    k_unpack<Mdl><<<1184, 256, 0, h->stream>>>(h->d, h->partition, canon_dev, base, stride, h->S.cur, sel);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  static int retile(mmd_handle h, int pa, int pb) {
-    // q(cur) in the tiling of partition pa -> qtmp in the tiling of pb -> slot 0; cur := 0
-    k_retile<Mdl><<<1184, 256, 0, h->stream>>>(h->d, pa, pb, h->S.q, h->qtmp, h->S.s_q, h->S.cur);
-    h->launches++;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->S.q, h->qtmp, (size_t)h->d.qsize * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemsetAsync(h->S.cur, 0, (size_t)h->d.n_tiles * h->d.cpb * sizeof(int), h->stream));
-    return 0;
-  }
-  static int gen_xobs(mmd_handle h) {
-    k_gen_xobs<Mdl, UMAX><<<(h->d.n_chains + 63) / 64, 64, 0, h->stream>>>(h->d, h->S, h->W, h->partition);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  static int init_interp(mmd_handle h) {
-    k_init_interp<Mdl, UMAX><<<h->d.n_tiles, nt(h), 0, h->stream>>>(h->d, h->S, h->W, h->partition);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  static int philox(mmd_handle h, uint64_t seed, uint64_t offset) {
-    k_philox_momentum<Mdl><<<1184, 256, 0, h->stream>>>(h->d, h->partition, h->S.p, h->S.s_q, h->S.cur, seed, offset,
-                                                        h->chain0);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-  }
-  static void constr_rows(mmd_handle h, const std::vector<double>& buf, double* c_out) {
-    // thread-private [tile][NRMAX][nta] -> [chain][n_c]: rows of block b start at its row0
-    const Dims& d = h->d;
-    const int part = h->partition, nc = d.n_c[part];
-    for (int c = 0; c < d.n_chains; ++c) {
-      const int tile = c / d.cpb, cl = c % d.cpb;
-      for (int b = 0; b < d.nb[part]; ++b) {
-        const Blk B = get_block<Mdl>(d, part, b);
-        for (int r = 0; r < B.nrows; ++r)
-          c_out[(size_t)c * nc + B.row0 + r] = buf[((size_t)tile * NRMAX + r) * d.nta + b * d.cpb + cl];
-      }
-    }
-  }
-};
-
-// dispatch on the model chosen at create time
-#define DISPATCH(h, CALL) (Ops<FhnModel, 8, 8>::CALL)
+#define DISPATCH(h, CALL) ((h)->ops->CALL)
 
 int h2d_stage(mmd_handle h, const double* host, double* stage, size_t n) {
   CK(cudaMemcpyAsync(stage, host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -314,7 +65,7 @@ int reset_flags(mmd_handle h) {
 
 extern "C" {
 
-const char* mmd_last_error_string(void) { return g_err.c_str(); }
+const char* mmd_last_error_string(void) { return mmd_err().c_str(); }
 
 void mmd_default_integrator_opts(mmd_integrator_opts* o) {
   // scripts/utils.py:124-166 defaults
@@ -331,33 +82,34 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     FAIL("no CUDA device: this library has no CPU path");
-  if (cfg->model != MMD_MODEL_FHN) FAIL("model not supported in this build (FHN only)");
+  const mmd_ops* ops = cfg->model == MMD_MODEL_FHN ? mmd_ops_fhn() : (cfg->model == MMD_MODEL_SIR ? mmd_ops_sir() : nullptr);
+  if (!ops) FAIL("unknown model id");
   if (cfg->device < 0 || cfg->device >= ndev) FAIL("bad device ordinal");
   CK(cudaSetDevice(cfg->device));
-  using Mdl = FhnModel;
-  constexpr int NRMAX = 8, RMAX = 8;
+  const int NRMAX = ops->nrmax, RMAX = ops->rmax;
   const int T = cfg->num_obs, S = cfg->num_steps_per_obs;
   int R = cfg->num_obs_per_subseq;
   if (T <= 0 || S <= 0 || cfg->n_chains <= 0) FAIL("bad sizes");
   if (R <= 0 || R >= T) R = T;
   const int nz = cfg->noise != MMD_NOISE_NONE;
-  if (cfg->dim_u != Mdl::Z + (cfg->noise == MMD_NOISE_PARAM ? 1 : 0)) FAIL("dim_u inconsistent with model/noise");
+  if (cfg->dim_u != ops->Z + (cfg->noise == MMD_NOISE_PARAM ? 1 : 0)) FAIL("dim_u inconsistent with model/noise");
   if (cfg->dim_u > UMAX) FAIL("dim_u too large");
-  if (R - 1 + nz + Mdl::X > NRMAX || R > RMAX) FAIL("num_obs_per_subseq too large for this build");
-  if (R == T && T * Mdl::Y > NRMAX) FAIL("unblocked problem too large for this build");
+  if (R - 1 + nz + ops->X > NRMAX || R > RMAX) FAIL("num_obs_per_subseq too large for this build");
+  if (R == T && (T * ops->Y > NRMAX || T > RMAX)) FAIL("unblocked problem too large for this build");
 
   mmd_handle h = new mmd_handle_s();
   memset(&h->d, 0, sizeof(Dims));
   h->model = cfg->model;
-  h->X = Mdl::X; h->V = Mdl::V; h->Z = Mdl::Z; h->V0 = Mdl::V0;
+  h->ops = ops;
+  h->X = ops->X; h->V = ops->V; h->Z = ops->Z; h->V0 = ops->V0;
   h->nrmax = NRMAX;
   Dims& d = h->d;
-  d.T = T; d.S = S; d.R = R; d.U = cfg->dim_u; d.X = Mdl::X; d.V = Mdl::V;
+  d.T = T; d.S = S; d.R = R; d.U = cfg->dim_u; d.X = ops->X; d.V = ops->V;
   d.noisy = cfg->noise; d.gaussian = cfg->gaussian_splitting; d.sigma_fixed = cfg->sigma_fixed;
   d.delta = cfg->obs_interval / S;
   d.sd = sqrt(d.delta);
-  d.off_v0 = d.U; d.off_v = d.U + Mdl::V0; d.off_n = d.off_v + T * S * Mdl::V;
-  d.dim_q = d.off_n + (nz ? T * Mdl::Y : 0);
+  d.off_v0 = d.U; d.off_v = d.U + ops->V0; d.off_n = d.off_v + T * S * ops->V;
+  d.dim_q = d.off_n + (nz ? T * ops->Y : 0);
   if (R == T) {
     d.num_partition = 1;
     d.nb[0] = d.nb[1] = 1;
@@ -373,9 +125,9 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
     }
   }
   for (int p = 0; p < 2; ++p) {
-    if (d.nb[p] == 1) d.n_c[p] = T * Mdl::Y;
+    if (d.nb[p] == 1) d.n_c[p] = T * ops->Y;
     else
-      d.n_c[p] = (d.init_size[p] - 1 + nz + Mdl::X) + (d.nb[p] - 2) * (R - 1 + nz + Mdl::X) + d.fin_size[p];
+      d.n_c[p] = (d.init_size[p] - 1 + nz + ops->X) + (d.nb[p] - 2) * (R - 1 + nz + ops->X) + d.fin_size[p];
   }
   d.n_chains = cfg->n_chains;
   h->ncmax = d.n_c[0] > d.n_c[1] ? d.n_c[0] : d.n_c[1];
@@ -396,9 +148,9 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   d.nslot = h->nbmax;
   d.nta = d.nslot * cpb;
   d.rmax = R;
-  d.rows_body = d.rmax * S * Mdl::V;
+  d.rows_body = d.rmax * S * ops->V;
   d.rows_noise = nz ? d.rmax : 0;
-  d.rows_head = d.U + Mdl::V0;
+  d.rows_head = d.U + ops->V0;
   d.off_body = (long long)d.n_tiles * d.rows_head * cpb;
   d.off_noise = d.off_body + (long long)d.n_tiles * d.rows_body * d.nta;
   d.qsize = d.off_noise + (long long)d.n_tiles * d.rows_noise * d.nta;
@@ -414,8 +166,8 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   h->partition = 0;
   h->chain0 = 0;
 
-  const size_t X = Mdl::X, V = Mdl::V, Z = Mdl::Z;
-  const size_t NTRI = NRMAX * (NRMAX + 1) / 2, UTRI = UMAX * (UMAX + 1) / 2;
+  const size_t X = ops->X, V = ops->V, Z = ops->Z;
+  const size_t NTRI = (size_t)NRMAX * (NRMAX + 1) / 2, UTRI = UMAX * (UMAX + 1) / 2;
   const size_t tpu = (size_t)d.n_tiles * d.nta;         // elements per thread-private row
   const size_t nc = (size_t)d.n_tiles * cpb;            // padded chain count
   const size_t RS = (size_t)d.rmax * S;
@@ -458,7 +210,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   rc |= dalloc(h, &W.iters, 2 * nc);
   rc |= dalloc(h, &W.revd, nc);
   rc |= dalloc(h, &W.itsum, nc);
-  rc |= dalloc(h, &h->y, (size_t)T * Mdl::Y);
+  rc |= dalloc(h, &h->y, (size_t)T * ops->Y);
   const size_t stage_n = (size_t)d.n_chains * (size_t)(d.dim_q > (int)(T * X) ? d.dim_q : T * X);
   rc |= dalloc(h, &h->stage, stage_n);
   rc |= dalloc(h, &h->stage2, stage_n);
@@ -472,7 +224,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   rc |= dalloc(h, &h->cur0, nc);
   rc |= dalloc(h, &h->n_ok, nc);
   if (rc) { mmd_destroy(h); return -2; }
-  CK(cudaMemcpyAsync(h->y, cfg->y_seq, (size_t)T * Mdl::Y * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->y, cfg->y_seq, (size_t)T * ops->Y * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   *out = h;
   return 0;

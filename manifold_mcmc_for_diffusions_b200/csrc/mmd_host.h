@@ -1,0 +1,142 @@
+// Host-side declarations shared by the translation units of libmmd_b200.so: the handle, the error
+// plumbing and the per-model table of kernel launchers (one translation unit per model, so the
+// models compile in parallel and every kernel is instantiated exactly once).
+#pragma once
+#include "../../include/mmd_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+
+#include <string>
+#include <vector>
+
+#include "mmd_kernels.cuh"
+
+std::string& mmd_err();   // thread-local last error text (defined in mmd_api.cu)
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char buf_[512];                                                                         \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      mmd_err() = buf_;                                                                       \
+      return -2;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+#define FAIL(msg)      \
+  do {                 \
+    mmd_err() = (msg); \
+    return -1;         \
+  } while (0)
+
+constexpr int UMAX = 5;      // max dim_u
+#ifndef MMD_NTMAX
+#define MMD_NTMAX 192         // max threads per CTA (= chains per tile x observation blocks)
+#endif
+constexpr int NTMAX = MMD_NTMAX;
+#ifndef MMD_MINB
+#define MMD_MINB 3           // __launch_bounds__ min resident CTAs per SM for the phase kernels
+#endif
+
+struct mmd_ops;
+
+struct mmd_handle_s {
+  mmd::Dims d;
+  mmd::Slots S;
+  mmd::Work W;
+  int model;
+  int X, V, Z, V0;
+  int nrmax;      // constraint rows per block the kernels are instantiated for
+  double* y;      // [T]
+  double* stage;  // [n_chains * dim_q] canonical staging (device)
+  double* stage2;
+  double* tpbuf;  // thread-private scratch [n_tiles][nrmax][nta] (constraint values)
+  double* hbuf;   // [chains]
+  double* h0buf;  // [chains]
+  double* qsave;  // q-like
+  double* qtmp;   // q-like (re-tiling at a partition switch)
+  double* accp;   // [chains]
+  int* accepted;  // [chains]
+  int* cur0;
+  int partition;
+  int ncmax, nbmax;
+  int chain0;     // global index of this handle's first chain (Philox stream offset)
+  bool fused;
+  const mmd_ops* ops;  // kernel launchers of the handle's model
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  long long launches;
+  bool lin_valid;
+  std::vector<void*> allocs;
+  // optional per-kernel event timing (bench.py's roofline leg)
+  bool prof_on;
+  std::vector<cudaEvent_t> prof_ev;   // pairs
+  std::vector<int> prof_kid;
+  size_t prof_used;
+  long long* n_ok;   // [chains] successful leapfrog steps per chain (device counter)
+};
+
+
+enum { KID_POINT = 0, KID_PROJECT = 1, KID_QN = 2, KID_LEAPFROG = 3, KID_OTHER = 4, KID_COUNT = 5 };
+
+struct ProfScope {
+  mmd_handle h;
+  size_t idx;
+  bool on;
+  ProfScope(mmd_handle h_, int kid) : h(h_), idx(0), on(false) {
+    if (h->prof_on && h->prof_used + 2 <= h->prof_ev.size()) {
+      on = true;
+      idx = h->prof_used;
+      h->prof_used += 2;
+      h->prof_kid.push_back(kid);
+      cudaEventRecord(h->prof_ev[idx], h->stream);
+    }
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(h->prof_ev[idx + 1], h->stream);
+  }
+};
+
+inline mmd::StepCoef step_coef(const mmd::Dims& d, double dt) {
+  mmd::StepCoef sc;
+  sc.half_dt = 0.5 * dt;
+  if (d.gaussian) {
+    // h2_flow = exact rotation by dt; dh2_flow_dmom = (sin dt, cos dt) (mici_extensions.py:1222-1238)
+    sc.qcoef = 0.0;
+    sc.fwd = mmd::FlowCoef{2, cos(dt), sin(dt), sin(dt)};
+    sc.back = mmd::FlowCoef{1, cos(dt), -sin(dt), -sin(dt)};
+    sc.mom_coef = cos(dt) / sin(dt);
+  } else {
+    sc.qcoef = 1.0;
+    sc.fwd = mmd::FlowCoef{2, 1.0, dt, 0.0};
+    sc.back = mmd::FlowCoef{1, 1.0, -dt, 0.0};
+    sc.mom_coef = 1.0 / dt;
+  }
+  return sc;
+}
+
+
+// model dimensions and the launcher table the C ABI dispatches through
+struct mmd_ops {
+  int X, V, Z, V0, Y, nrmax, rmax;
+  int (*point)(mmd_handle, int, int);
+  int (*constr)(mmd_handle);
+  int (*project)(mmd_handle, int, int, int, double, double, mmd::FlowCoef);
+  int (*qn)(mmd_handle, int, double, const mmd_integrator_opts*);
+  int (*leapfrog)(mmd_handle, double, const mmd_integrator_opts*, int, int);
+  int (*hamiltonian)(mmd_handle, int, double*);
+  int (*pack)(mmd_handle, const double*, double*, long long, int);
+  int (*unpack)(mmd_handle, double*, const double*, long long, int);
+  int (*retile)(mmd_handle, int, int);
+  int (*gen_xobs)(mmd_handle);
+  int (*init_interp)(mmd_handle);
+  int (*philox)(mmd_handle, uint64_t, uint64_t);
+  void (*constr_rows)(mmd_handle, const std::vector<double>&, double*);
+};
+const mmd_ops* mmd_ops_fhn();
+const mmd_ops* mmd_ops_sir();

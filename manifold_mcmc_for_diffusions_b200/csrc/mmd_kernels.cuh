@@ -111,6 +111,21 @@ struct Work {
   long long* itsum;  // [chains] total projection iterations executed (both directions)
 };
 
+struct FlowCoef {
+  int mode;
+  double fq, fp, fpm;
+};
+
+// step-size dependent constants of one leapfrog step (standard / Gaussian splitting, :1186-1238)
+struct StepCoef {
+  double half_dt;    // h1 kick
+  double qcoef;      // 1: h1 contains 1/2 |q|^2 (standard splitting); 0: Gaussian splitting
+  FlowCoef fwd;      // h2_flow(dt) fused into the first projection
+  FlowCoef back;     // h2_flow(-dt) for the reverse check (trial position only)
+  double mom_coef;   // dh2_flow_mom_dmom / (dt or sin dt): momentum update after the projection solve
+};
+
+
 enum : int { ST_NOTCONV = 1, ST_DIVERGED = 2, ST_NONREV = 4, ST_NONFINITE = 8 };
 enum : int { PSEL_CUR = 0, PSEL_OTHER = 1, PSEL_WORK = 2 };
 

@@ -339,6 +339,8 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       }
     }
     double Suz[X * Z], Gam[Z * UMAX];
+    double gobs[M::OBS_LINEAR ? 1 : RMAX * X];
+    (void)gobs;
 #pragma unroll
     for (int i = 0; i < X * Z; ++i) Suz[i] = B.ini ? dx0_dz[i] : 0.0;
     for (int i = 0; i < Z * UMAX; ++i) Gam[i] = 0.0;
@@ -381,6 +383,12 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #pragma unroll
         for (int i = 0; i < X; ++i) dprev[r * X + i] = t1[i] + t2[i] + t3[i];
       }
+      if (!M::OBS_LINEAR && k < B.ny) {
+        // tangent of the state at observation time k in the direction that weights row k: the observation
+        // curvature enters the adjoint there (d H_k = Hess h(x_k) d x_k)
+#pragma unroll
+        for (int i = 0; i < X; ++i) gobs[k * X + i] = dprev[k * X + i];
+      }
       double ts[X * Z];
       mm<X, Z, X>(Ps, Suz, ts);
 #pragma unroll
@@ -412,9 +420,13 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       ldcol<X * X>(Mkc + k * X * X * nta, nta, Mk);
       ldcol<Z * X>(LamZc + k * Z * X * nta, nta, Lam);
       ldcol<X * X>(Ybc + k * X * X * nta, nta, Y);
-      if (!M::OBS_LINEAR) {
-        // curvature of the observation function enters the adjoint at the observation time
-        // (handled through obs_hess in the adjoint start below)
+      if (!M::OBS_LINEAR && k < B.ny) {
+        // curvature of the observation function: adjoint source at the observation time t_k
+        double xe[X], hv[X];
+        ldcol<X>(xendc + k * X * nta, nta, xe);
+        M::obs_hess_vec(xe, &gobs[k * X], hv);
+#pragma unroll
+        for (int i = 0; i < X; ++i) gam[i] += hv[i];
       }
       for (int tt = 0; tt < d.S; ++tt) {
         strec<X * X>(Yk + tt * X * X * nta, Y);
@@ -546,10 +558,6 @@ MMD_D void dev_constr(const Dims& d, const Slots& S, const Work& W, const double
 // where (fq, fp, fpm) = (1, dt, 0) for the standard splitting and (cos dt, sin dt, sin dt) for the
 // Gaussian splitting.  lin/src/dst select slots relative to cur (PSEL_*).
 // ------------------------------------------------------------------------------------------
-struct FlowCoef {
-  int mode;
-  double fq, fp, fpm;
-};
 
 template <class M, int NRMAX, int RMAXP, int UMAX>
 MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, int lin_sel, int src_sel,
@@ -1259,20 +1267,11 @@ k_qn(Dims d, Slots S, Work W, const double* __restrict__ y, int part, int mode, 
      double ptol, double dtol, int max_iters) {
   dev_qn<M, NRMAX, RMAX, UMAX, NEWTON>(d, S, W, y, part, mode, mom_coef, ctol, ptol, dtol, max_iters);
 }
-__global__ void k_commit(Dims d, Slots S, Work W, double rev_tol, long long* __restrict__ n_ok) {
+static __global__ void k_commit(Dims d, Slots S, Work W, double rev_tol, long long* __restrict__ n_ok) {
   const int cix = blockIdx.x * blockDim.x + threadIdx.x;
   if (cix >= d.n_chains) return;
   dev_commit(d, S, W, rev_tol, n_ok, cix);
 }
-
-// step-size dependent constants of one leapfrog step (standard / Gaussian splitting, :1186-1238)
-struct StepCoef {
-  double half_dt;    // h1 kick
-  double qcoef;      // 1: h1 contains 1/2 |q|^2 (standard splitting); 0: Gaussian splitting
-  FlowCoef fwd;      // h2_flow(dt) fused into the first projection
-  FlowCoef back;     // h2_flow(-dt) for the reverse check (trial position only)
-  double mom_coef;   // dh2_flow_mom_dmom / (dt or sin dt): momentum update after the projection solve
-};
 
 // One (or n_steps) full ConstrainedLeapfrogIntegrator.step per chain in ONE launch: a CTA carries
 // its tile of chains through every phase with CTA-local barriers only, so chains that need many
@@ -1399,7 +1398,7 @@ __global__ void k_retile(Dims d, int pa, int pb, const double* __restrict__ src,
   }
 }
 // per-chain arrays [chain][rows] (canonical) <-> [tile][rows][cpb]
-__global__ void k_pack_chain(Dims d, int rows, const double* __restrict__ canon, double* __restrict__ dst) {
+static __global__ void k_pack_chain(Dims d, int rows, const double* __restrict__ canon, double* __restrict__ dst) {
   const long long n = (long long)d.n_chains * rows;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
@@ -1407,7 +1406,7 @@ __global__ void k_pack_chain(Dims d, int rows, const double* __restrict__ canon,
     dst[((long long)(chain >> d.lcpb) * rows + r) * d.cpb + (chain & (d.cpb - 1))] = canon[e];
   }
 }
-__global__ void k_unpack_chain(Dims d, int rows, double* __restrict__ canon, const double* __restrict__ src) {
+static __global__ void k_unpack_chain(Dims d, int rows, double* __restrict__ canon, const double* __restrict__ src) {
   const long long n = (long long)d.n_chains * rows;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
@@ -1417,7 +1416,7 @@ __global__ void k_unpack_chain(Dims d, int rows, double* __restrict__ canon, con
 }
 // thread-private array (rows per thread, block-local rows; records of width W, W = 1 for plain columns)
 // -> [chain][nb][rows] for tests / factor export
-__global__ void k_unpack_tp(Dims d, int part, int rows, int W, double* __restrict__ out,
+static __global__ void k_unpack_tp(Dims d, int part, int rows, int W, double* __restrict__ out,
                             const double* __restrict__ base, long long slot_stride, const int* __restrict__ cur) {
   const int nb = d.nb[part];
   const long long n = (long long)d.n_chains * nb * rows;
@@ -1562,7 +1561,7 @@ __global__ void k_philox_momentum(Dims d, int part, double* __restrict__ base, l
 // and log(uniform) < h0 - h1 (Mici MetropolisStaticIntegrationTransition semantics; IntegratorError
 // -> reject).  acc_prob is the `accept_stat` statistic min(1, exp(h0 - h1)).
 // A rejected chain returns to the slot it started the transition in (cur0).
-__global__ void k_decide(Dims d, Slots S, Work W, const double* __restrict__ h0, const double* __restrict__ h1,
+static __global__ void k_decide(Dims d, Slots S, Work W, const double* __restrict__ h0, const double* __restrict__ h1,
                          const int* __restrict__ cur0, uint64_t seed, uint64_t offset, int chain0,
                          int* __restrict__ accepted, double* __restrict__ acc_prob) {
   const int chain = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1586,7 +1585,7 @@ __global__ void k_decide(Dims d, Slots S, Work W, const double* __restrict__ h0,
   (void)S; (void)cur0;
 }
 // restore the position of rejected chains from the copy taken at the start of the transition
-__global__ void k_restore(Dims d, Slots S, const int* __restrict__ accepted, const double* __restrict__ qsave) {
+static __global__ void k_restore(Dims d, Slots S, const int* __restrict__ accepted, const double* __restrict__ qsave) {
   // qsave holds the start-of-transition position in tile layout (same partition); element e of a
   // q-like vector belongs to chain (tile(e), cl(e)); decode from the section it falls into
   const long long n = d.qsize;
@@ -1610,7 +1609,7 @@ __global__ void k_restore(Dims d, Slots S, const int* __restrict__ accepted, con
   }
 }
 // snapshot of the current position (tile layout) at the start of a transition
-__global__ void k_snapshot(Dims d, Slots S, double* __restrict__ qsave) {
+static __global__ void k_snapshot(Dims d, Slots S, double* __restrict__ qsave) {
   const long long n = d.qsize;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {

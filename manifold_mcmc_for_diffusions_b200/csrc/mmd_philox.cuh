@@ -34,7 +34,7 @@ MMD_HD static void philox_normal_pair(uint64_t seed, uint64_t offset, uint64_t i
 }
 
 #if defined(__CUDACC__)
-__global__ void k_philox_normal(double* out, long long n, uint64_t seed, uint64_t offset) {
+static __global__ void k_philox_normal(double* out, long long n, uint64_t seed, uint64_t offset) {
   const long long npair = (n + 1) / 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npair;
        i += (long long)gridDim.x * blockDim.x) {

@@ -132,3 +132,22 @@ def test_reference_aliases():
     assert sde.example_models.fhn.dim_x == 2
     for k in [k for k in sys.modules if k == "mici" or k.startswith("mici.") or k == "sde" or k.startswith("sde.")]:
         del sys.modules[k]
+
+
+def test_sir_numpy_model_matches_oracle():
+    from oracle.models import sir as osir
+
+    rng = np.random.default_rng(4)
+    m = example_models.sir
+    for _ in range(5):
+        u = 0.3 * rng.standard_normal(5)
+        z = m.generate_z(u)
+        assert np.allclose(z, osir.generate_z(torch.tensor(u)).numpy(), rtol=1e-15)
+        x = np.array([6.5, 2.0, 0.5]) + 0.2 * rng.standard_normal(3)
+        v = rng.standard_normal(3)
+        ref = osir.forward_func(torch.tensor(z), torch.tensor(x), torch.tensor(v), 0.05).numpy()
+        assert np.max(np.abs(m.forward_func(z, x, v, 0.05) - ref)) < 1e-13
+        assert np.allclose(m.generate_x_0(z, np.array([0.3])), osir.generate_x_0(torch.tensor(z), torch.tensor([0.3], dtype=torch.float64)).numpy())
+    xc = np.array([-600.0, 1.0, 0.2])
+    ref = osir.forward_func(torch.tensor(z), torch.tensor(xc), torch.tensor(v), 0.05).numpy()
+    assert np.allclose(m.forward_func(z, xc, v, 0.05), ref) and m.forward_func(z, xc, v, 0.05)[0] == -500.0

@@ -88,3 +88,52 @@ def test_philox_normals_are_standard_normal_and_reproducible(shim):
     assert a.value == vals[10] and b.value == vals[11]
     # Philox-4x32-10 known-answer test (Random123 kat_vectors: counter=0, key=0)
     # checked through the raw block function in test_abi-level C shim is overkill; moments + determinism suffice here.
+
+
+def test_sir_functor_matches_autodiff(shim):
+    from oracle.models import sir
+
+    rng = np.random.default_rng(12)
+    dl = 0.05
+    sd = np.sqrt(dl)
+    for _ in range(10):
+        u = 0.3 * rng.standard_normal(4)
+        z = sir.generate_z(torch.tensor(u)).numpy()
+        x = np.array([np.log(700.0), np.log(20.0), 0.3]) + 0.2 * rng.standard_normal(3)
+        v = rng.standard_normal(3)
+        zt, xt, vt = torch.tensor(z), torch.tensor(x), torch.tensor(v)
+        f = lambda z_, x_, v_: sir.forward_func(z_, x_, v_, dl)  # noqa: E731
+        xn = np.zeros(3)
+        shim.sir_step(_p(z), C.c_double(sd), _p(x), _p(v), _p(xn))
+        assert np.max(np.abs(xn - f(zt, xt, vt).numpy())) < 1e-13
+        Jz, Jx, Jv = torch.func.jacrev(f, argnums=(0, 1, 2))(zt, xt, vt)
+        F, B, G = np.zeros(9), np.zeros(9), np.zeros(12)
+        shim.sir_jac_x(_p(z), C.c_double(sd), _p(x), _p(v), _p(F))
+        shim.sir_jac_v(_p(z), C.c_double(sd), _p(x), _p(v), _p(B))
+        shim.sir_jac_z(_p(z), C.c_double(sd), _p(x), _p(v), _p(G))
+        assert np.max(np.abs(F.reshape(3, 3) - Jx.numpy())) < 1e-12 * max(1, np.abs(Jx.numpy()).max())
+        assert np.max(np.abs(B.reshape(3, 3) - Jv.numpy())) < 1e-13 * max(1, np.abs(Jv.numpy()).max())
+        assert np.max(np.abs(G.reshape(3, 4) - Jz.numpy())) < 1e-12 * max(1, np.abs(Jz.numpy()).max())
+        Th = rng.standard_normal((10, 3))
+
+        def fj(yv):
+            return sir.forward_func(yv[6:10], yv[0:3], yv[3:6], dl)
+
+        H = torch.func.jacfwd(torch.func.jacrev(fj))(torch.tensor(np.concatenate([x, v, z]))).numpy()
+        ref = np.einsum("iab,bi->a", H, Th)
+        g = np.zeros(10)
+        Thc = np.ascontiguousarray(Th)
+        shim.sir_hess_contract(_p(z), C.c_double(sd), _p(x), _p(v), _p(Thc), _p(g))
+        assert np.max(np.abs(g - ref)) < 1e-10 * max(1.0, np.abs(ref).max())
+        # generate_z: Jacobian and the second-derivative contraction used by the log-det gradient
+        zz, dz = np.zeros(4), np.zeros(16)
+        shim.sir_gen_z(_p(u), _p(zz), _p(dz))
+        J = torch.func.jacrev(sir.generate_z)(torch.tensor(u)).numpy()
+        assert np.allclose(zz, z, rtol=1e-15) and np.allclose(dz.reshape(4, 4), J, rtol=1e-14, atol=1e-16)
+        Gam = rng.standard_normal((4, 4))
+        H2 = torch.func.jacfwd(torch.func.jacrev(sir.generate_z))(torch.tensor(u)).numpy()  # [m, j, j']
+        ref2 = np.einsum("mj,mjk->k", Gam, H2)
+        ex = np.zeros(4)
+        Gc = np.ascontiguousarray(Gam)
+        shim.sir_gen_z_second(_p(u), _p(zz), _p(Gc), _p(ex))
+        assert np.max(np.abs(ex - ref2)) < 1e-13 * max(1.0, np.abs(ref2).max())

@@ -112,7 +112,7 @@ def _emit(name, args_sig, outputs, unpack, hoister):
     return "\n".join(lines)
 
 
-def gen_model(struct_name, fname, f, X, V, Z, sd, header, doc):
+def gen_model(struct_name, fname, f, X, V, Z, sd, header, doc, extra_methods="", step_name="step"):
     """Emit one model header.  f: sympy column of the step map in terms of X, V, Z symbols and sd."""
     nx, nv, nz = len(X), len(V), len(Z)
     dyn = list(X) + list(V)
@@ -129,7 +129,7 @@ def gen_model(struct_name, fname, f, X, V, Z, sd, header, doc):
                  recip_only=True)
     sig = "const Coef& c, const double* x, const double* v, "
     parts = []
-    parts.append(_emit("step", sig + "double* xn", [(f"xn[{i}]", f[i]) for i in range(nx)], unpack, hs))
+    parts.append(_emit(step_name, sig + "double* xn", [(f"xn[{i}]", f[i]) for i in range(nx)], unpack, hs))
     Fx = f.jacobian(X)
     parts.append(_emit("jac_x", sig + "double* F",
                        [(f"F[{i*nx+j}]", Fx[i, j]) for i in range(nx) for j in range(nx)], unpack, hd))
@@ -195,8 +195,11 @@ struct {struct_name} {{
   }}
 
 {body}
+{extra_methods}
 }};
 """
+    if step_name != "step":
+        src = src.replace("MMD_HD static void step_clipped(", "MMD_HD static void step(")
     path = os.path.join(OUT_DIR, fname)
     with open(path, "w") as fh:
         fh.write(src)
@@ -252,5 +255,76 @@ def gen_fhn():
     )
 
 
+SIR_HEADER = """  static constexpr int X = 3;   // dim_x   (sir.py:9)   state [log S, log I, log contact rate]
+  static constexpr int V = 3;   // dim_v = dim_w (sir.py:10-13)
+  static constexpr int Z = 4;   // dim_z   z = [beta, gamma, zeta, epsilon]
+  static constexpr int V0 = 1;  // dim_v_0
+  static constexpr int Y = 1;   // dim_y: obs_func(x) = exp(x[1])  (sir.py:73-74)
+  static constexpr int MODEL_ID = 1;
+
+  // z = generate_z(u) (sir.py:77-85): [exp u0, exp u1, u2, exp(sqrt(.75) u3 + .5 u1 - 3)] and dz/du
+  MMD_HD static void gen_z(const double* u, double* z, double* dzdu /* Z x Z */) {
+    z[0] = exp(u[0]); z[1] = exp(u[1]); z[2] = u[2];
+    z[3] = exp(0.8660254037844386 * u[3] + 0.5 * u[1] - 3.0);
+    for (int i = 0; i < 16; ++i) dzdu[i] = 0.0;
+    dzdu[0] = z[0]; dzdu[5] = z[1]; dzdu[10] = 1.0;
+    dzdu[13] = 0.5 * z[3]; dzdu[15] = 0.8660254037844386 * z[3];
+  }
+  // extra[j'] = sum_{m,j} Gam[m*Z+j] * d2 z_m / du_j du_j'
+  MMD_HD static void gen_z_second(const double* u, const double* z, const double* Gam, double* extra) {
+    const double a = 0.5, b = 0.8660254037844386;
+    extra[0] = Gam[0] * z[0];
+    extra[1] = Gam[5] * z[1] + z[3] * (Gam[13] * a * a + Gam[15] * a * b);
+    extra[2] = 0.0;
+    extra[3] = z[3] * (Gam[13] * a * b + Gam[15] * b * b);
+  }
+  // x_0 = generate_x_0(z, v_0) = [log 762, log 1, v_0[0]] (sir.py:88-89)
+  MMD_HD static void gen_x0(const double* z, const double* v0, double* x0) {
+    x0[0] = 6.635946555686647; x0[1] = 0.0; x0[2] = v0[0];
+  }
+  MMD_HD static void gen_x0_jac(const double* z, double* dx0_dv0 /* X x V0 */, double* dx0_dz /* X x Z */) {
+    dx0_dv0[0] = 0.0; dx0_dv0[1] = 0.0; dx0_dv0[2] = 1.0;
+    for (int i = 0; i < 12; ++i) dx0_dz[i] = 0.0;
+  }
+  // observation y = h(x) = exp(x[1])
+  MMD_HD static double obs(const double* x) { return exp(x[1]); }
+  MMD_HD static void obs_grad(const double* x, double* dh) { dh[0] = 0.0; dh[1] = exp(x[1]); dh[2] = 0.0; }
+  MMD_HD static void obs_hess_vec(const double* x, const double* d, double* out) {
+    out[0] = 0.0; out[1] = exp(x[1]) * d[1]; out[2] = 0.0;
+  }
+  static constexpr bool OBS_LINEAR = false;
+"""
+
+
+def gen_sir():
+    from oracle.models import derive_sir_step
+
+    f, sy = derive_sir_step(simplify=False)
+    d = sy["delta"]
+    sd = sp.symbols("sd", positive=True)
+    f = f.subs(d, sd ** 2)
+    gen_model(
+        "SirModel", "mmd_model_sir.cuh", f, list(sy["x"]), list(sy["v"]), list(sy["z"]), "sd", SIR_HEADER,
+        "// SIR epidemic model with an Ornstein-Uhlenbeck log contact rate, Euler-Maruyama step of the\n"
+        "// log-transformed SDE.  Restates sde/example_models/sir.py:9-93, sde/integrators.py:8-14 and\n"
+        "// sde/transforms.py:9-63 of the reference (the clip of the first two state components at -500,\n"
+        "// sir.py:54-70, is applied by `step_clipped`); all derivatives are symbolic.",
+        extra_methods='''
+  // forward_func with the reference's guards (sir.py:54-70): clip the first two components below at -500
+  // before the step and keep them there afterwards
+  MMD_HD static void step_clipped(const Coef& c, const double* x, const double* v, double* xn) {
+    double xc[3] = {x[0] < -500.0 ? -500.0 : x[0], x[1] < -500.0 ? -500.0 : x[1], x[2]};
+    double xr[3];
+    step_raw(c, xc, v, xr);
+    xn[0] = xc[0] > -500.0 ? xr[0] : xc[0];
+    xn[1] = xc[1] > -500.0 ? xr[1] : xc[1];
+    xn[2] = xr[2];
+  }
+''',
+        step_name="step_raw",
+    )
+
+
 if __name__ == "__main__":
     gen_fhn()
+    gen_sir()
