@@ -9,6 +9,7 @@ n = int(os.environ.get("NCH", 4096)); burn = int(os.environ.get("BURN", 20)); dt
 y = np.load(os.path.join(ROOT, "tests/golden/fhn_yseq_T100.npy"))
 T, S, R = 100, 25, 5
 bc = BatchedChains("fhn", 0.2, S, R, y, 4, n)
+bc.opts.solver = int(os.environ.get("SOLVER", 0))   # 0 quasi-Newton, 1 Newton
 rng = np.random.default_rng([20200710, 0])
 u = rng.standard_normal((n, 4)); v0 = rng.standard_normal((n, 2))
 xo = np.concatenate((np.broadcast_to(y, (n, T, 1)), 0.5 * rng.standard_normal((n, T, 1))), -1)
