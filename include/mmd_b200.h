@@ -32,7 +32,8 @@ extern "C" {
 
 typedef struct mmd_handle_s* mmd_handle;
 
-enum { MMD_MODEL_FHN = 0, MMD_MODEL_SIR = 1 };
+enum { MMD_MODEL_FHN = 0, MMD_MODEL_SIR = 1,
+       MMD_MODEL_FHN_NOTEBOOK = 2 /* FHN with the prior parametrisation of FitzHugh-Nagumo_example.ipynb */ };
 enum { MMD_NOISE_NONE = 0, MMD_NOISE_FIXED = 1, MMD_NOISE_PARAM = 2 };
 enum { MMD_SOLVER_QUASI_NEWTON = 0, MMD_SOLVER_NEWTON = 1 };
 

@@ -12,7 +12,7 @@ import numpy as np
 
 from ._lib import MmdConfig, MmdIntegratorOpts, check, lib
 
-MODEL_IDS = {"fhn": 0, "sir": 1}
+MODEL_IDS = {"fhn": 0, "sir": 1, "fhn_notebook": 2}
 STATUS_NOT_CONVERGED, STATUS_DIVERGED, STATUS_NON_REVERSIBLE, STATUS_NON_FINITE = 1, 2, 4, 8
 
 

@@ -82,7 +82,9 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     FAIL("no CUDA device: this library has no CPU path");
-  const mmd_ops* ops = cfg->model == MMD_MODEL_FHN ? mmd_ops_fhn() : (cfg->model == MMD_MODEL_SIR ? mmd_ops_sir() : nullptr);
+  const mmd_ops* ops = cfg->model == MMD_MODEL_FHN ? mmd_ops_fhn()
+                       : cfg->model == MMD_MODEL_SIR ? mmd_ops_sir()
+                       : cfg->model == MMD_MODEL_FHN_NOTEBOOK ? mmd_ops_fhn_notebook() : nullptr;
   if (!ops) FAIL("unknown model id");
   if (cfg->device < 0 || cfg->device >= ndev) FAIL("bad device ordinal");
   CK(cudaSetDevice(cfg->device));

@@ -140,3 +140,4 @@ struct mmd_ops {
 };
 const mmd_ops* mmd_ops_fhn();
 const mmd_ops* mmd_ops_sir();
+const mmd_ops* mmd_ops_fhn_notebook();

@@ -2,4 +2,4 @@
 simulation, trace functions, initial states.  Every callable carries a ``_mmd_model`` tag; the
 constrained system recognises the tag and maps the model to its generated device functor -- arbitrary
 Python callables cannot be traced into CUDA and are rejected, never run on a CPU fallback."""
-from . import fhn, sir  # noqa: F401
+from . import fhn, fhn_notebook, sir  # noqa: F401
