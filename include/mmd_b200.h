@@ -137,6 +137,17 @@ int mmd_hmc_transition(mmd_handle h, double dt, int n_leapfrog, uint64_t seed, u
 int mmd_transition_begin(mmd_handle h, uint64_t seed, uint64_t iter);
 int mmd_transition_steps(mmd_handle h, double dt, int n_steps, const mmd_integrator_opts* opts);
 int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_partition);
+/* Per-chain step sizes [n_chains] (host): used by the leapfrog / transition entry points instead of their
+ * scalar `dt` argument, whose sign still gives the integration direction; NULL switches back to the scalar. */
+int mmd_set_step_sizes(mmd_handle h, const double* dt);
+int mmd_get_step_sizes(mmd_handle h, double* dt);
+/* mici.adapters.DualAveragingStepSizeAdapter (scripts/utils.py:303-306: target 0.8, regularisation coefficient
+ * 0.1; Mici defaults decay 0.75, offset 10) run per chain on device: after every transition the chain's step
+ * size is updated from its accept_stat.  mmd_adapt_stop = finalize: step size <- exp(smoothed log step size)
+ * per chain, or (pool != 0) the mean over chains as Mici does for several chains. */
+int mmd_adapt_start(mmd_handle h, double init_step_size, double target, double reg_coefficient, double iter_decay,
+                    double iter_offset);
+int mmd_adapt_stop(mmd_handle h, int pool);
 /* accepted flag, accept_stat = min(1, exp(h0 - h1)), integrator status of the last transition */
 int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, int* status);
 /* per-chain status / diagnostics of the last step (any pointer may be NULL) */

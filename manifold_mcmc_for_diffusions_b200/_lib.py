@@ -93,6 +93,10 @@ SIGNATURES = {
     "mmd_transition_begin": (C.c_int, [_H, C.c_uint64, C.c_uint64]),
     "mmd_transition_steps": (C.c_int, [_H, C.c_double, C.c_int, C.POINTER(MmdIntegratorOpts)]),
     "mmd_transition_end": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int]),
+    "mmd_set_step_sizes": (C.c_int, [_H, _dp]),
+    "mmd_get_step_sizes": (C.c_int, [_H, _dp]),
+    "mmd_adapt_start": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "mmd_adapt_stop": (C.c_int, [_H, C.c_int]),
     "mmd_successful_steps": (C.c_longlong, [_H, C.c_int]),
     "mmd_total_qn_iterations": (C.c_longlong, [_H, C.c_int]),
     "mmd_profile_enable": (C.c_int, [_H, C.c_int, C.c_int]),

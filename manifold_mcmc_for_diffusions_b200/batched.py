@@ -192,6 +192,23 @@ class BatchedChains:
     def transition_end(self, seed, it, switch_partition=True):
         check(self._L.mmd_transition_end(self._h, int(seed), int(it), int(switch_partition)))
 
+    def set_step_sizes(self, dt):
+        """Per-chain step sizes (array [n_chains]) or None to return to the scalar step size."""
+        check(self._L.mmd_set_step_sizes(self._h, None if dt is None else _dp(_c(np.broadcast_to(dt, (self.n_chains,))))))
+
+    def get_step_sizes(self):
+        out = np.empty(self.n_chains)
+        check(self._L.mmd_get_step_sizes(self._h, _dp(out)))
+        return out
+
+    def adapt_start(self, init_step_size, target=0.8, reg_coefficient=0.05, iter_decay=0.75, iter_offset=10):
+        """On-device per-chain DualAveragingStepSizeAdapter (Mici defaults; scripts use target 0.8, reg 0.1)."""
+        check(self._L.mmd_adapt_start(self._h, float(init_step_size), float(target), float(reg_coefficient),
+                                      float(iter_decay), float(iter_offset)))
+
+    def adapt_stop(self, pool=False):
+        check(self._L.mmd_adapt_stop(self._h, int(pool)))
+
     def successful_steps(self, reset=False):
         return int(self._L.mmd_successful_steps(self._h, int(reset)))
 

@@ -212,6 +212,10 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   rc |= dalloc(h, &W.iters, 2 * nc);
   rc |= dalloc(h, &W.revd, nc);
   rc |= dalloc(h, &W.itsum, nc);
+  rc |= dalloc(h, &W.dt_chain, nc);
+  W.use_dt_chain = 0;
+  rc |= dalloc(h, &h->ad_state, 4 * nc);
+  h->adapting = false;
   rc |= dalloc(h, &h->y, (size_t)T * ops->Y);
   const size_t stage_n = (size_t)d.n_chains * (size_t)(d.dim_q > (int)(T * X) ? d.dim_q : T * X);
   rc |= dalloc(h, &h->stage, stage_n);
@@ -455,7 +459,7 @@ static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opt
     int rc0 = mmd_linearize(h, 1);
     if (rc0) return rc0;
   }
-  if (h->fused) return DISPATCH(h, leapfrog(h, dt, &o, n_steps, reset_status ? 1 : 0));
+  if (h->fused || h->W.use_dt_chain) return DISPATCH(h, leapfrog(h, dt, &o, n_steps, reset_status ? 1 : 0));
   if (reset_status)
     CK(cudaMemsetAsync(h->W.status, 0, (size_t)h->d.n_tiles * h->d.cpb * sizeof(int), h->stream));
   const StepCoef sc = step_coef(h->d, dt);
@@ -505,8 +509,55 @@ int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_pa
   k_restore<<<1184, 256, 0, h->stream>>>(h->d, h->S, h->accepted, h->qsave);
   h->launches++;
   CK(cudaGetLastError());
+  if (h->adapting) {
+    const long long nc = (long long)h->d.n_tiles * h->d.cpb;
+    k_dual_averaging<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->ad_state, nc, h->accp, h->ad_target,
+                                                                        h->ad_reg_coef, h->ad_decay, h->ad_offset,
+                                                                        h->W.dt_chain);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
   h->lin_valid = false;
   if (switch_partition) return mmd_switch_partition(h);
+  return 0;
+}
+
+int mmd_set_step_sizes(mmd_handle h, const double* dt) {
+  if (!dt) { h->W.use_dt_chain = 0; return 0; }
+  CK(cudaMemcpyAsync(h->W.dt_chain, dt, h->d.n_chains * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->W.use_dt_chain = 1;
+  return 0;
+}
+
+int mmd_get_step_sizes(mmd_handle h, double* dt) {
+  CK(cudaMemcpyAsync(dt, h->W.dt_chain, h->d.n_chains * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int mmd_adapt_start(mmd_handle h, double init_step_size, double target, double reg_coefficient, double iter_decay,
+                    double iter_offset) {
+  if (!(init_step_size > 0.0)) FAIL("initial step size must be positive");
+  const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
+  std::vector<double> st(4 * nc, 0.0), dt(nc, init_step_size);
+  for (size_t c = 0; c < nc; ++c) st[3 * nc + c] = log(10.0 * init_step_size);   // log_step_size_reg_target
+  CK(cudaMemcpyAsync(h->ad_state, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->W.dt_chain, dt.data(), nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->ad_target = target; h->ad_reg_coef = reg_coefficient; h->ad_decay = iter_decay; h->ad_offset = iter_offset;
+  h->adapting = true;
+  h->W.use_dt_chain = 1;
+  return 0;
+}
+
+int mmd_adapt_stop(mmd_handle h, int pool) {
+  if (!h->adapting) FAIL("mmd_adapt_start was not called");
+  const long long nc = (long long)h->d.n_tiles * h->d.cpb;
+  k_dual_averaging_finalize<<<1, 256, 0, h->stream>>>(h->d, h->ad_state, nc, pool, h->W.dt_chain);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->adapting = false;
   return 0;
 }
 

@@ -79,6 +79,10 @@ struct mmd_handle_s {
   std::vector<int> prof_kid;
   size_t prof_used;
   long long* n_ok;   // [chains] successful leapfrog steps per chain (device counter)
+  // on-device dual-averaging step-size adaptation (DualAveragingStepSizeAdapter, scripts/utils.py:303-306)
+  bool adapting;
+  double ad_target, ad_reg_coef, ad_decay, ad_offset;
+  double* ad_state;  // [4][chains]: iteration count, smoothed log step size, adapt-stat error, reg target
 };
 
 
@@ -102,24 +106,7 @@ struct ProfScope {
   }
 };
 
-inline mmd::StepCoef step_coef(const mmd::Dims& d, double dt) {
-  mmd::StepCoef sc;
-  sc.half_dt = 0.5 * dt;
-  if (d.gaussian) {
-    // h2_flow = exact rotation by dt; dh2_flow_dmom = (sin dt, cos dt) (mici_extensions.py:1222-1238)
-    sc.qcoef = 0.0;
-    sc.fwd = mmd::FlowCoef{2, cos(dt), sin(dt), sin(dt)};
-    sc.back = mmd::FlowCoef{1, cos(dt), -sin(dt), -sin(dt)};
-    sc.mom_coef = cos(dt) / sin(dt);
-  } else {
-    sc.qcoef = 1.0;
-    sc.fwd = mmd::FlowCoef{2, 1.0, dt, 0.0};
-    sc.back = mmd::FlowCoef{1, 1.0, -dt, 0.0};
-    sc.mom_coef = 1.0 / dt;
-  }
-  return sc;
-}
-
+inline mmd::StepCoef step_coef(const mmd::Dims& d, double dt) { return mmd::make_step_coef(d.gaussian, dt); }
 
 // model dimensions and the launcher table the C ABI dispatches through
 struct mmd_ops {

@@ -109,6 +109,8 @@ struct Work {
   int* iters;     // [2][chains] projection iterations (forward, reverse) of the last step
   double* revd;   // [chains] reverse-check distance of the last step
   long long* itsum;  // [chains] total projection iterations executed (both directions)
+  double* dt_chain;  // [chains] per-chain step sizes (used instead of the scalar step size when use_dt_chain)
+  int use_dt_chain;
 };
 
 struct FlowCoef {
@@ -125,6 +127,27 @@ struct StepCoef {
   double mom_coef;   // dh2_flow_mom_dmom / (dt or sin dt): momentum update after the projection solve
 };
 
+
+// step-size dependent constants for the signed step dt (host and device: with per-chain step sizes every
+// thread derives its own)
+MMD_HD StepCoef make_step_coef(int gaussian, double dt) {
+  StepCoef sc;
+  sc.half_dt = 0.5 * dt;
+  if (gaussian) {
+    // h2_flow = exact rotation by dt; dh2_flow_dmom = (sin dt, cos dt) (mici_extensions.py:1222-1238)
+    const double c = cos(dt), sn = sin(dt);
+    sc.qcoef = 0.0;
+    sc.fwd = FlowCoef{2, c, sn, sn};
+    sc.back = FlowCoef{1, c, -sn, -sn};
+    sc.mom_coef = c / sn;
+  } else {
+    sc.qcoef = 1.0;
+    sc.fwd = FlowCoef{2, 1.0, dt, 0.0};
+    sc.back = FlowCoef{1, 1.0, -dt, 0.0};
+    sc.mom_coef = 1.0 / dt;
+  }
+  return sc;
+}
 
 enum : int { ST_NOTCONV = 1, ST_DIVERGED = 2, ST_NONREV = 4, ST_NONFINITE = 8 };
 enum : int { PSEL_CUR = 0, PSEL_OTHER = 1, PSEL_WORK = 2 };

@@ -1280,11 +1280,13 @@ static __global__ void k_commit(Dims d, Slots S, Work W, double rev_tol, long lo
 // Step order: Mici ConstrainedLeapfrogIntegrator._step = A(dt/2) B(dt) A(dt/2), SURVEY.md 3.3.
 template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB, bool NEWTON>
 __global__ void __launch_bounds__(NTMAX, MINB)
-k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, StepCoef sc, double ctol, double ptol,
+k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, double dt, double ctol, double ptol,
            double dtol, int max_iters, double rev_tol, long long* __restrict__ n_ok, int n_steps,
            int reset_status) {
   const Tid t = thread_id(d);
   const FlowCoef noflow = {0, 1.0, 0.0, 0.0};
+  // per-chain step sizes keep the sign (integration direction) of the scalar argument
+  const StepCoef sc = make_step_coef(d.gaussian, W.use_dt_chain ? copysign(W.dt_chain[t.cix], dt) : dt);
   for (int s = 0; s < n_steps; ++s) {
     if (reset_status && t.slot == 0) W.status[t.cix] = 0;
     __syncthreads();
@@ -1584,6 +1586,45 @@ static __global__ void k_decide(Dims d, Slots S, Work W, const double* __restric
   acc_prob[chain] = ap;
   (void)S; (void)cur0;
 }
+// DualAveragingStepSizeAdapter.update (Mici 0.1.10) per chain, on device:
+//   w = 1/(offset + n); err <- (1-w) err + w (target - accept_stat); log eps = reg_target - err sqrt(n) / reg_coef;
+//   smoothed <- (1 - n^-decay) smoothed + n^-decay log eps; step size <- exp(log eps)
+// state: [4][nc] = iteration, smoothed log step size, adapt-stat error, regularisation target
+static __global__ void k_dual_averaging(Dims d, double* __restrict__ state, long long nc,
+                                        const double* __restrict__ accept_stat, double target, double reg_coef,
+                                        double decay, double offset, double* __restrict__ dt_chain) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.n_chains) return;
+  const double n = state[c] + 1.0;
+  state[c] = n;
+  const double w = 1.0 / (offset + n);
+  const double err = (1.0 - w) * state[2 * nc + c] + w * (target - accept_stat[c]);
+  state[2 * nc + c] = err;
+  const double log_eps = state[3 * nc + c] - err * sqrt(n) / reg_coef;
+  const double sw = pow(n, -decay);
+  state[nc + c] = (1.0 - sw) * state[nc + c] + sw * log_eps;
+  dt_chain[c] = exp(log_eps);
+}
+// DualAveragingStepSizeAdapter.finalize: step size = exp(smoothed log step size) per chain, or (pool) the mean
+// over chains like Mici's finalize with several chains
+static __global__ void k_dual_averaging_finalize(Dims d, const double* __restrict__ state, long long nc, int pool,
+                                                 double* __restrict__ dt_chain) {
+  __shared__ double red[256];
+  double mean = 0.0;
+  if (pool) {
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < d.n_chains; c += blockDim.x) acc += exp(state[nc + c]);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
+      if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+      __syncthreads();
+    }
+    mean = red[0] / d.n_chains;
+  }
+  for (int c = threadIdx.x; c < d.n_chains; c += blockDim.x) dt_chain[c] = pool ? mean : exp(state[nc + c]);
+}
+
 // restore the position of rejected chains from the copy taken at the start of the transition
 static __global__ void k_restore(Dims d, Slots S, const int* __restrict__ accepted, const double* __restrict__ qsave) {
   // qsave holds the start-of-transition position in tile layout (same partition); element e of a

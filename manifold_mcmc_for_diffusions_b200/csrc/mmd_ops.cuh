@@ -68,7 +68,7 @@ struct Ops {
     auto kern = k_leapfrog<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB, NEWTON>;
     const int n = nt(h);
     if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, step_coef(h->d, dt),
+    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, dt,
                                                    o->constraint_tol, o->position_tol, o->divergence_tol,
                                                    o->max_iters, o->reverse_check_tol, h->n_ok, n_steps,
                                                    reset_status);

@@ -57,6 +57,10 @@ def main():
     # randomly chosen moving chain (a valid re-initialisation: burn-in continues afterwards and the per-chain
     # Philox momentum streams decorrelate the copies at once).
     n_restarted = 0
+    adapt = int(os.environ.get("ADAPT", 0))
+    if adapt:
+        # per-chain dual averaging on device (target 0.8, reg 0.1 as in scripts/utils.py:303-306), pooled at the end
+        bc.adapt_start(dt / 4, target=0.8, reg_coefficient=0.1)
     for frac, step in ((0.25, dt / 4), (0.25, dt / 2), (0.5, dt)):
         acc, moved = [], np.zeros(n)
         for _ in range(int(frac * n_burn)):
@@ -75,6 +79,11 @@ def main():
             n_restarted += len(stuck)
         log.append({"dt": step, "transitions": len(acc), "accept_stat": float(np.mean(acc[-20:])),
                     "restarted_chains": int(len(stuck))})
+    if adapt:
+        per_chain = bc.get_step_sizes()
+        bc.adapt_stop(pool=True)
+        log.append({"adapted_step_size_quantiles": [round(float(v), 4) for v in np.quantile(per_chain, [0.05, 0.5, 0.95])],
+                    "pooled_step_size": float(bc.get_step_sizes()[0])})
     names = ["σ", "ϵ", "γ", "β", "x_0[0]", "x_0[1]"]
     draws = np.empty((n, n_main, 6))
     acc, fail = [], []
