@@ -96,7 +96,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   const int nz = cfg->noise != MMD_NOISE_NONE;
   if (cfg->dim_u != ops->Z + (cfg->noise == MMD_NOISE_PARAM ? 1 : 0)) FAIL("dim_u inconsistent with model/noise");
   if (cfg->dim_u > UMAX) FAIL("dim_u too large");
-  if (R - 1 + nz + ops->X > NRMAX || R > RMAX) FAIL("num_obs_per_subseq too large for this build");
+  if (R < T && (R - 1 + nz + ops->X > NRMAX || R > RMAX)) FAIL("num_obs_per_subseq too large for this build");
   if (R == T && (T * ops->Y > NRMAX || T > RMAX)) FAIL("unblocked problem too large for this build");
 
   mmd_handle h = new mmd_handle_s();

@@ -135,3 +135,36 @@ def test_leapfrog_steps(prob, solver):
                 assert _rel(pg[i], p.numpy()) < 1e-8
                 assert abs(hg[i] - sysm.h(q, p, pt)) < 1e-9 * abs(hg[i])
         bc.close()
+
+
+def test_sir_script_shape_golden():
+    """The reference's SIR experiment shape (14 observations x 20 steps, one block, inferred noise scale,
+    dim_q = 860; boarding-school data) against committed oracle-frozen vectors (tests/golden/make_golden_sir.py)."""
+    import os
+
+    from manifold_mcmc_for_diffusions_b200 import BatchedChains
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sir_T14_S20_golden.npz"))
+    n = g["q0"].shape[0]
+    for solver, sid in (("quasi_newton", 0), ("newton", 1)):
+        bc = BatchedChains("sir", 1.0, int(g["S"]), int(g["T"]), g["y"], 5, n, noise=2)
+        assert bc.dim_q == 860 and bc.num_partition == 1
+        bc.opts.solver = sid
+        bc.set_state(g["q0"], g["xobs"], 0, p=g["p_raw"])
+        assert np.max(np.abs(bc.constr() - g["c"])) < 1e-9
+        bc.linearize(True)
+        assert np.max(np.abs(bc.log_det_sqrt_gram() - g["ld"])) < 1e-9 * np.max(np.abs(g["ld"]))
+        assert _rel(bc.grad_log_det_sqrt_gram(), g["grad_ld"]) < 1e-9
+        assert _rel(bc.normal_space_component(g["p_raw"]), g["nsc"]) < 1e-9
+        bc.project_momentum()
+        bc.leapfrog_step(float(g["dt"]))
+        info = bc.step_info()
+        q, p, _ = bc.get_state()
+        assert np.all(info["status"] == 0)
+        assert np.array_equal(info["iters_fwd"], g[f"{solver}_it"][:, 0])
+        assert np.array_equal(info["iters_rev"], g[f"{solver}_it"][:, 1])
+        assert _rel(q, g[f"{solver}_q"]) < 1e-9
+        assert _rel(p, g[f"{solver}_p"]) < 1e-8
+        h = bc.hamiltonian()
+        assert np.max(np.abs(h - g[f"{solver}_h"]) / np.abs(h)) < 1e-9
+        bc.close()
