@@ -3,6 +3,14 @@
 #pragma once
 #include "mmd_kernels.cuh"
 
+// the per-iteration block solves: fully unrolled (factor loads issued up front: lowest latency for a lone
+// CTA) or rolled (fewer registers: higher throughput with all SMs busy)
+#if defined(MMD_ROLLED_SOLVES)
+#define MMD_SOLVE_UNROLL _Pragma("unroll 1")
+#else
+#define MMD_SOLVE_UNROLL _Pragma("unroll")
+#endif
+
 namespace mmd {
 
 // per-thread parameters of the chain at some value of u
@@ -257,7 +265,7 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
   double al[X];
 #pragma unroll
   for (int i = 0; i < X; ++i) al[i] = 0.0;
-#pragma unroll
+  MMD_SOLVE_UNROLL
   for (int k = RMAX - 1; k >= 0; --k) {
     if (k < B.n) {
       if (k < B.n - 1) {
@@ -313,26 +321,26 @@ MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const doubl
   g[UMAX] = extra_max ? *extra_max : 0.0;
   if (has_blk) {
     // forward / backward substitution with the packed factor (diagonal stored inverted)
-#pragma unroll
+    MMD_SOLVE_UNROLL
     for (int i = 0; i < NRMAX; ++i) {
       if (i < n) {
         double s = r[i];
-#pragma unroll
+        MMD_SOLVE_UNROLL
         for (int k = 0; k < i; ++k) s = fma(-Lc[tri(i, k) * nta], r[k], s);
         r[i] = s * Lc[tri(i, i) * nta];
       }
     }
-#pragma unroll
+    MMD_SOLVE_UNROLL
     for (int i = NRMAX - 1; i >= 0; --i) {
       if (i < n) {
         double s = r[i];
-#pragma unroll
+        MMD_SOLVE_UNROLL
         for (int k = i + 1; k < NRMAX; ++k)
           if (k < n) s = fma(-Lc[tri(k, i) * nta], r[k], s);
         r[i] = s * Lc[tri(i, i) * nta];
       }
     }
-#pragma unroll
+    MMD_SOLVE_UNROLL
     for (int i = 0; i < NRMAX; ++i) {
       if (i < n) {
 #pragma unroll
@@ -350,7 +358,7 @@ MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const doubl
 #pragma unroll
   for (int j = 0; j < UMAX; ++j) s_out[j] = g[j];
   if (has_blk) {
-#pragma unroll
+    MMD_SOLVE_UNROLL
     for (int i = 0; i < NRMAX; ++i) {
       if (i < n) {
         double ti = r[i];

@@ -103,3 +103,47 @@ def summary(traces):
         v = np.asarray(v, dtype=np.float64)
         out[k] = {"mean": float(v.mean()), "sd": float(v.std(ddof=1)), "ess_bulk": ess_bulk(v), "r_hat": rhat(v)}
     return out
+
+
+def save_and_print_summary(output_dir, traces, summary_vars, sampling_time, step_size, call_counts=None,
+                           verbose=True):
+    """Output format of the reference's experiment scripts (``scripts/utils.py:368-381``): ``summary.json`` in
+    the column-major layout of ``arviz.summary(...).to_dict()`` ({statistic: {variable: value}}) plus the totals the
+    plotting / cost-per-ESS code reads (``load_summary_data``, ``utils.py:484-523``), and one
+    ``trace_{chain}_{var}.npy`` per chain and variable (the names ``load_traces`` globs for, ``utils.py:555-556``).
+
+    traces[var]: array [n_chains, n_iter] (scalar variables) or [n_chains, n_iter, k] (vectors, written as
+    ``var[i]`` like ArviZ does)."""
+    import json
+    import os
+
+    os.makedirs(output_dir, exist_ok=True)
+    flat = {}
+    for var in summary_vars:
+        v = np.asarray(traces[var], dtype=np.float64)
+        if v.ndim == 2:
+            flat[var] = v
+        else:
+            for i in range(v.shape[2]):
+                flat[f"{var}[{i}]"] = v[:, :, i]
+    table = summary(flat)
+    cols = ("mean", "sd", "ess_bulk", "r_hat")
+    summary_dict = {c: {k: float(row[c]) for k, row in table.items()} for c in cols}
+    summary_dict["mcse_mean"] = {k: float(row["sd"] / np.sqrt(max(row["ess_bulk"], 1.0))) for k, row in table.items()}
+    summary_dict["total_sampling_time"] = float(sampling_time)
+    summary_dict["final_integrator_step_size"] = float(step_size)
+    for name, total in (call_counts or {}).items():
+        summary_dict[f"total_{name}_calls"] = int(total)
+    with open(os.path.join(output_dir, "summary.json"), mode="w") as f:
+        json.dump(summary_dict, f, ensure_ascii=False, indent=2)
+    for var, v in traces.items():
+        v = np.asarray(v)
+        for c in range(v.shape[0]):
+            np.save(os.path.join(output_dir, f"trace_{c}_{var}.npy"), v[c])
+    if verbose:
+        print(f"Integrator step size = {step_size:.2g}")
+        print(f"Total sampling time = {sampling_time:.0f} seconds")
+        for k, row in table.items():
+            print(f"{k:>10s}  mean {row['mean']:9.4f}  sd {row['sd']:8.4f}  ess_bulk {row['ess_bulk']:8.0f}  "
+                  f"r_hat {row['r_hat']:.3f}")
+    return summary_dict

@@ -105,6 +105,7 @@ class ConditionedDiffusionConstrainedSystem(System):
             noise, sigma = 2, 0.0
             funcs.append(generate_σ)
         model = _model_tag(*funcs)
+        self._model = model
         y_seq = np.asarray(y_seq, dtype=np.float64)
         num_obs, dim_y = y_seq.shape
         dim_v_0 = dim_x if dim_v_0 is None else dim_v_0
@@ -348,6 +349,7 @@ def _dense_jacobian_blocks(system, partition):
     K = bc.get_factor("K")[0]
     Psib = bc.get_factor("Psib")[0]
     A = bc.get_factor("A")[0]
+    xend = bc.get_factor("xend")[0]
     q = np.frombuffer(system._resident[0], dtype=np.float64)
     sigma = 0.0 if noise == 0 else (bc._sigma_fixed if noise == 1 else float(np.exp(q[U - 1])))
     dc_du, dc_dv, dc_dn = [], [], []
@@ -364,7 +366,10 @@ def _dense_jacobian_blocks(system, partition):
             kr = r if r < ny else n - 1
             h = np.zeros(X)
             if r < ny:
-                h[0] = 1.0  # obs_func gradient of the FHN model (x[0]); nonlinear models use xend
+                if system._model == "sir":     # obs_func = exp(x[1]): gradient at the state of observation r
+                    h[1] = float(np.exp(xend[b].reshape(-1, X)[r, 1]))
+                else:                          # FHN: obs_func = x[0]
+                    h[0] = 1.0
             else:
                 h[r - ny] = 1.0
             vec = h
@@ -373,7 +378,8 @@ def _dense_jacobian_blocks(system, partition):
                     vec = Pb[k + 1].T @ vec
                 Jv[r, off + k * S * V: off + (k + 1) * S * V] = np.einsum("i,tij->tj", vec, Kb[k]).reshape(-1)
             if ini:
-                Jv[r, :V0] = (Pb[0].T @ vec)[:V0]  # d x_0 / d v_0 = I for the registered models
+                d0 = Pb[0].T @ vec            # d c_r / d x_0; d x_0 / d v_0 = I (FHN) or e_2 (SIR)
+                Jv[r, :V0] = d0[:V0] if system._model != "sir" else d0[2:3]
         Jn = None
         if noise:
             Jn = np.zeros((nrows, n))

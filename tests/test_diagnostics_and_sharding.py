@@ -80,3 +80,24 @@ def test_allgather_chains_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_summary_json_and_trace_files(tmp_path):
+    """Output format the reference's loaders expect (scripts/utils.py:368-381, 484-569)."""
+    import glob
+    import json
+    import os
+
+    from manifold_mcmc_for_diffusions_b200.diagnostics import save_and_print_summary
+
+    rng = np.random.default_rng(0)
+    traces = {"σ": rng.standard_normal((4, 200)) * 0.1 + 0.8, "x_0": rng.standard_normal((4, 200, 2))}
+    out = save_and_print_summary(str(tmp_path), traces, ["σ", "x_0"], 12.0, 0.13, call_counts={"constr": 1234},
+                                 verbose=False)
+    loaded = json.load(open(os.path.join(tmp_path, "summary.json")))
+    assert loaded == out
+    assert set(loaded["mean"]) == {"σ", "x_0[0]", "x_0[1]"}
+    assert abs(loaded["mean"]["σ"] - 0.8) < 0.02 and loaded["r_hat"]["σ"] < 1.05
+    assert loaded["total_constr_calls"] == 1234 and loaded["final_integrator_step_size"] == 0.13
+    assert len(glob.glob(os.path.join(tmp_path, "trace_*_σ.npy"))) == 4
+    assert np.load(os.path.join(tmp_path, "trace_2_x_0.npy")).shape == (200, 2)

@@ -78,15 +78,17 @@ def test_system_methods_match_oracle(prob, part):
     assert counts["constr"] == 1 and counts["grad_log_det_sqrt_gram"] == 1
 
 
+@pytest.mark.parametrize("solver", ["quasi_newton", "newton"])
 @pytest.mark.parametrize("part", [0, 1])
-def test_mici_integrator_steps_match_oracle(prob, part):
+def test_mici_integrator_steps_match_oracle(prob, part, solver):
     from manifold_mcmc_for_diffusions_b200 import mici_compat, mici_extensions as me
 
     system = _system(prob)
     sysm = prob["system"]
     integrator = mici_compat.integrators.ConstrainedLeapfrogIntegrator(
         system, step_size=0.05, n_inner_step=1, reverse_check_tol=2e-8,
-        projection_solver=me.jitted_solve_projection_onto_manifold_quasi_newton,
+        projection_solver=(me.jitted_solve_projection_onto_manifold_newton if solver == "newton"
+                           else me.jitted_solve_projection_onto_manifold_quasi_newton),
         projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
     rng = np.random.default_rng(3)
     q0, xo = prob["q"][1], prob["xobs"][1]
@@ -98,7 +100,7 @@ def test_mici_integrator_steps_match_oracle(prob, part):
     q = torch.tensor(q0)
     for s in range(3):
         state = integrator.step(state)
-        q, p, pt, inf = O.leapfrog_step(sysm, q, p, xo, part, 0.05, pt=pt)
+        q, p, pt, inf = O.leapfrog_step(sysm, q, p, xo, part, 0.05, pt=pt, solver=solver)
         assert _rel(state.pos, q.numpy()) < 1e-9
         assert _rel(state.mom, p.numpy()) < 1e-8
         assert abs(system.h(state) - sysm.h(q, p, pt)) < 1e-9 * abs(system.h(state))
@@ -149,3 +151,33 @@ def test_nuts_transitions_and_partition_switch():
         assert state.partition == (it + 1) % 2
         assert np.max(np.abs(system.constr(state))) < 1e-7    # on the manifold of the NEW partition
     assert n_step >= 4
+
+
+def test_sir_system_through_the_plugin_surface():
+    """SIR model selected by the tagged callables of example_models.sir (non-linear observation, inferred
+    noise scale through a callable generate_σ), one Mici-style leapfrog step with the Newton solver."""
+    from manifold_mcmc_for_diffusions_b200 import example_models, mici_compat, mici_extensions as me
+    from tests.test_gpu_sir import make_sir_problem
+
+    prob = make_sir_problem(6, 4, 3, n_chains=1)
+    m = example_models.sir
+    system = me.ConditionedDiffusionConstrainedSystem(
+        prob["obs_interval"], prob["S"], prob["R"], prob["y"], 5, m.dim_x, m.dim_v, m.forward_func, m.generate_x_0,
+        m.generate_z, m.obs_func, generate_σ=m.generate_σ_y, dim_v_0=m.dim_v_0)
+    sysm = prob["system"]
+    q0, xo = prob["q"][0], prob["xobs"][0]
+    state = me.ConditionedDiffusionHamiltonianState(pos=q0.copy(), x_obs_seq=xo, partition=1)
+    pt = sysm.point(q0, xo, 1)
+    assert np.max(np.abs(system.constr(state))) < 1e-9
+    assert abs(system.log_det_sqrt_gram(state) - pt["ld"]) < 1e-10 * max(1, abs(pt["ld"]))
+    assert _rel(system.grad_log_det_sqrt_gram(state), pt["grad_ld"].numpy()) < 1e-9
+    rng = np.random.default_rng(2)
+    p_raw = rng.standard_normal(q0.shape)
+    state.mom = system.project_onto_cotangent_space(p_raw.copy(), state)
+    integrator = mici_compat.integrators.ConstrainedLeapfrogIntegrator(
+        system, step_size=0.02, projection_solver=me.jitted_solve_projection_onto_manifold_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    new = integrator.step(state)
+    p = sysm.project_onto_cotangent_space(torch.tensor(p_raw), pt)
+    q, p, ptn, _ = O.leapfrog_step(sysm, q0, p, xo, 1, 0.02, pt=pt, solver="newton")
+    assert _rel(new.pos, q.numpy()) < 1e-9 and _rel(new.mom, p.numpy()) < 1e-8
