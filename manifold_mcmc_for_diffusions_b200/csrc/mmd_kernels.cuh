@@ -25,6 +25,9 @@
 #ifndef MMD_PREFETCH_STEPS
 #define MMD_PREFETCH_STEPS 2      // cp.async ring depth of the recursion sweeps (steps in flight to shared memory)
 #endif
+#ifndef MMD_POINTWISE_L2_PREFETCH
+#define MMD_POINTWISE_L2_PREFETCH 8   // look-ahead (steps) of the HBM -> L2 prefetch in the pointwise passes (0 = off)
+#endif
 #ifndef MMD_L2_PREFETCH_STEPS
 #define MMD_L2_PREFETCH_STEPS 8   // additional look-ahead of the HBM -> L2 prefetch (0 = off)
 #endif

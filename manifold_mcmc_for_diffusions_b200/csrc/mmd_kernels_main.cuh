@@ -592,6 +592,8 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
   const bool write1 = kick || (src_sel != dst_sel);
   Blk B;
   if (t.slot < d.nb[part]) B = get_block<M>(d, part, t.slot);
+  const int nsteps_blk = (t.slot < d.nb[part]) ? B.n * d.S : 0;
+  (void)nsteps_blk;
   double pu[UMAX], sres[UMAX], pv0[M::V0];
   double dx0_dv0[X * M::V0], dx0_dz[X * Z];
   double sig = 0.0;
@@ -641,6 +643,14 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
       for (int tt = 0; tt < d.S; ++tt) {
         const int so = (k * d.S + tt) * nta;
         double Kt[XV], pv[V];
+#if MMD_POINTWISE_L2_PREFETCH > 0
+        if (k * d.S + tt + MMD_POINTWISE_L2_PREFETCH < nsteps_blk) {   // pull a later step's records into L2
+          const int sp = so + MMD_POINTWISE_L2_PREFETCH * nta;
+          prefetch_l2(Kc + sp * XV);
+          prefetch_l2(ps.body + sp * V);
+          if (kick) { prefetch_l2(q.body + sp * V); prefetch_l2(g.body + sp * V); }
+        }
+#endif
         ldrec<XV>(Kc + so * XV, Kt);
         ldrec<V>(ps.body + so * V, pv);
         if (kick) {
@@ -699,6 +709,14 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
       for (int tt = 0; tt < d.S; ++tt) {
         const int so = (k * d.S + tt) * nta;
         double Kt[XV], pv[V];
+#if MMD_POINTWISE_L2_PREFETCH > 0
+        if (k * d.S + tt + MMD_POINTWISE_L2_PREFETCH < nsteps_blk) {
+          const int sp = so + MMD_POINTWISE_L2_PREFETCH * nta;
+          prefetch_l2(Kc + sp * XV);
+          prefetch_l2((write1 ? pd.body : ps.body) + sp * V);
+          if (fl.mode) prefetch_l2(q.body + sp * V);
+        }
+#endif
         ldrec<XV>(Kc + so * XV, Kt);
         ldrec<V>((write1 ? pd.body : ps.body) + so * V, pv);
 #pragma unroll
@@ -1128,6 +1146,14 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
           for (int tt = 0; tt < d.S; ++tt) {
             const int so = (k * d.S + tt) * nta;
             double Kt[XV], qv[V], ov[V], pv[V];
+#if MMD_POINTWISE_L2_PREFETCH > 0
+            if (k * d.S + tt + MMD_POINTWISE_L2_PREFETCH < B.n * d.S) {
+              const int sp = so + MMD_POINTWISE_L2_PREFETCH * nta;
+              prefetch_l2(Kc + sp * XV);
+              prefetch_l2(qw.body + sp * V);
+              prefetch_l2((mode == 0 ? pin.body : qref.body) + sp * V);
+            }
+#endif
             ldrec<XV>(Kc + so * XV, Kt);
             ldrec<V>(qw.body + so * V, qv);
             ldrec<V>((mode == 0 ? pin.body : qref.body) + so * V, ov);
