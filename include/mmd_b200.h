@@ -148,6 +148,27 @@ int mmd_get_step_sizes(mmd_handle h, double* dt);
 int mmd_adapt_start(mmd_handle h, double init_step_size, double target, double reg_coefficient, double iter_decay,
                     double iter_offset);
 int mmd_adapt_stop(mmd_handle h, int pool);
+/* same update from accept statistics supplied by the caller (dynamic transitions built by the host) */
+int mmd_adapt_update(mmd_handle h, const double* accept_stat);
+
+/* ---- vector primitives for host-driven tree building -------------------------------------------
+ * (mici.transitions.MultinomialDynamicIntegrationTransition, scripts/utils.py:292-301, batched: the host
+ * keeps the per-chain tree bookkeeping, the device holds every state vector and does every O(dim_q)
+ * operation.)  Vectors are addressed by id: MMD_VEC_Q / MMD_VEC_P = the chains' live position / momentum,
+ * 0 .. n-1 = auxiliary arrays reserved with mmd_aux_reserve.  mask: host int[n_chains] or NULL (all). */
+enum { MMD_VEC_Q = -1, MMD_VEC_P = -2 };
+int mmd_aux_reserve(mmd_handle h, int n_arrays);
+/* dst = beta * dst + alpha * src for the masked chains */
+int mmd_vec_axpby(mmd_handle h, int dst, int src, double alpha, double beta, const int* mask);
+/* per chain, with s = c - d + a:  out1 = a . s,  out2 = e . s  (no-U-turn criterion on momentum sums;
+ * e may be MMD_VEC_P) */
+int mmd_vec_uturn(mmd_handle h, int a, int d, int c, int e, double* out1, double* out2);
+/* park (mask != 0) / release chains: parked chains are skipped by every kernel like failed ones, without an
+ * error bit; clear_errors also clears the integrator error bits of all chains */
+int mmd_set_inactive(mmd_handle h, const int* mask, int clear_errors);
+/* re-evaluate everything cached at the live position (after mmd_vec_axpby wrote it) without touching the
+ * per-chain status words */
+int mmd_relinearize(mmd_handle h);
 /* accepted flag, accept_stat = min(1, exp(h0 - h1)), integrator status of the last transition */
 int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, int* status);
 /* per-chain status / diagnostics of the last step (any pointer may be NULL) */

@@ -97,6 +97,12 @@ SIGNATURES = {
     "mmd_get_step_sizes": (C.c_int, [_H, _dp]),
     "mmd_adapt_start": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
     "mmd_adapt_stop": (C.c_int, [_H, C.c_int]),
+    "mmd_adapt_update": (C.c_int, [_H, _dp]),
+    "mmd_aux_reserve": (C.c_int, [_H, C.c_int]),
+    "mmd_vec_axpby": (C.c_int, [_H, C.c_int, C.c_int, C.c_double, C.c_double, _ip]),
+    "mmd_vec_uturn": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+    "mmd_set_inactive": (C.c_int, [_H, _ip, C.c_int]),
+    "mmd_relinearize": (C.c_int, [_H]),
     "mmd_successful_steps": (C.c_longlong, [_H, C.c_int]),
     "mmd_total_qn_iterations": (C.c_longlong, [_H, C.c_int]),
     "mmd_profile_enable": (C.c_int, [_H, C.c_int, C.c_int]),

@@ -209,6 +209,35 @@ class BatchedChains:
     def adapt_stop(self, pool=False):
         check(self._L.mmd_adapt_stop(self._h, int(pool)))
 
+    def adapt_update(self, accept_stat):
+        check(self._L.mmd_adapt_update(self._h, _dp(_c(accept_stat))))
+
+    # ---- vector primitives for host-driven tree building (see nuts.py) -------------------
+    VEC_Q, VEC_P = -1, -2
+
+    def aux_reserve(self, n_arrays):
+        check(self._L.mmd_aux_reserve(self._h, int(n_arrays)))
+
+    @staticmethod
+    def _mask(mask):
+        return None if mask is None else np.ascontiguousarray(mask, dtype=np.int32)
+
+    def vec_axpby(self, dst, src, alpha=1.0, beta=0.0, mask=None):
+        m = self._mask(mask)
+        check(self._L.mmd_vec_axpby(self._h, int(dst), int(src), float(alpha), float(beta), None if m is None else _ip(m)))
+
+    def vec_uturn(self, a, d, c, e):
+        o1, o2 = np.empty(self.n_chains), np.empty(self.n_chains)
+        check(self._L.mmd_vec_uturn(self._h, int(a), int(d), int(c), int(e), _dp(o1), _dp(o2)))
+        return o1, o2
+
+    def set_inactive(self, mask=None, clear_errors=False):
+        m = self._mask(mask)
+        check(self._L.mmd_set_inactive(self._h, None if m is None else _ip(m), int(clear_errors)))
+
+    def relinearize(self):
+        check(self._L.mmd_relinearize(self._h))
+
     def successful_steps(self, reset=False):
         return int(self._L.mmd_successful_steps(self._h, int(reset)))
 

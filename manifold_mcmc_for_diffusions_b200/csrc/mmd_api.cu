@@ -215,6 +215,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   rc |= dalloc(h, &W.dt_chain, nc);
   W.use_dt_chain = 0;
   rc |= dalloc(h, &h->ad_state, 4 * nc);
+  rc |= dalloc(h, &h->maskbuf, nc);
   h->adapting = false;
   rc |= dalloc(h, &h->y, (size_t)T * ops->Y);
   const size_t stage_n = (size_t)d.n_chains * (size_t)(d.dim_q > (int)(T * X) ? d.dim_q : T * X);
@@ -558,6 +559,87 @@ int mmd_adapt_stop(mmd_handle h, int pool) {
   h->launches++;
   CK(cudaGetLastError());
   h->adapting = false;
+  return 0;
+}
+
+// ---- vector primitives for host-driven tree building (batched dynamic HMC) ----------------------
+static const int* upload_mask(mmd_handle h, const int* mask) {
+  if (!mask) return nullptr;
+  if (cudaMemcpyAsync(h->maskbuf, mask, h->d.n_chains * sizeof(int), cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+    return nullptr;
+  return h->maskbuf;
+}
+static int resolve_vec(mmd_handle h, int id, double** ptr, int* live) {
+  if (id == MMD_VEC_Q) { *ptr = h->S.q; *live = 1; return 0; }
+  if (id == MMD_VEC_P) { *ptr = h->S.p; *live = 1; return 0; }
+  if (id < 0 || id >= (int)h->aux.size()) FAIL("bad vector id");
+  *ptr = h->aux[id];
+  *live = 0;
+  return 0;
+}
+
+int mmd_aux_reserve(mmd_handle h, int n_arrays) {
+  while ((int)h->aux.size() < n_arrays) {
+    double* p = nullptr;
+    if (dalloc(h, &p, (size_t)h->d.qsize)) return -2;
+    h->aux.push_back(p);
+  }
+  return 0;
+}
+
+int mmd_vec_axpby(mmd_handle h, int dst, int src, double alpha, double beta, const int* mask) {
+  double *pd, *ps;
+  int ld, ls;
+  if (resolve_vec(h, dst, &pd, &ld) || resolve_vec(h, src, &ps, &ls)) return -1;
+  const int* m = upload_mask(h, mask);
+  if (mask && !m) FAIL("mask upload failed");
+  k_vec_axpby<<<1184, 256, 0, h->stream>>>(h->d, pd, ld, ps, ls, h->S.s_q, h->S.cur, alpha, beta, m);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (ld) h->lin_valid = h->lin_valid && dst != MMD_VEC_Q;   // overwriting the live position invalidates the cache
+  return 0;
+}
+
+int mmd_vec_uturn(mmd_handle h, int a, int dd, int c, int e, double* out1, double* out2) {
+  double *pa, *pd, *pc, *pe;
+  int la, ldd, lc, le;
+  if (resolve_vec(h, a, &pa, &la) || resolve_vec(h, dd, &pd, &ldd) || resolve_vec(h, c, &pc, &lc) ||
+      resolve_vec(h, e, &pe, &le))
+    return -1;
+  if (la || ldd || lc) FAIL("only the last operand of mmd_vec_uturn may be a live vector");
+  int rc = DISPATCH(h, vec_uturn(h, pa, pd, pc, pe, le, h->hbuf, h->accp));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out1, h->hbuf, h->d.n_chains * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out2, h->accp, h->d.n_chains * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int mmd_set_inactive(mmd_handle h, const int* mask, int clear_errors) {
+  const int* m = upload_mask(h, mask);
+  if (mask && !m) FAIL("mask upload failed");
+  k_set_inactive<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->W, m, clear_errors);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int mmd_relinearize(mmd_handle h) {
+  int rc = DISPATCH(h, point(h, 0, 1));
+  if (rc) return rc;
+  h->lin_valid = true;
+  return 0;
+}
+
+int mmd_adapt_update(mmd_handle h, const double* accept_stat) {
+  if (!h->adapting) FAIL("mmd_adapt_start was not called");
+  CK(cudaMemcpyAsync(h->accp, accept_stat, h->d.n_chains * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const long long nc = (long long)h->d.n_tiles * h->d.cpb;
+  k_dual_averaging<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->ad_state, nc, h->accp, h->ad_target,
+                                                                      h->ad_reg_coef, h->ad_decay, h->ad_offset,
+                                                                      h->W.dt_chain);
+  h->launches++;
+  CK(cudaGetLastError());
   return 0;
 }
 

@@ -83,6 +83,8 @@ struct mmd_handle_s {
   bool adapting;
   double ad_target, ad_reg_coef, ad_decay, ad_offset;
   double* ad_state;  // [4][chains]: iteration count, smoothed log step size, adapt-stat error, reg target
+  std::vector<double*> aux;   // auxiliary q-like arrays of the host-driven tree builder
+  int* maskbuf;               // [chains] device copy of the caller's chain mask
 };
 
 
@@ -120,6 +122,7 @@ struct mmd_ops {
   int (*pack)(mmd_handle, const double*, double*, long long, int);
   int (*unpack)(mmd_handle, double*, const double*, long long, int);
   int (*retile)(mmd_handle, int, int);
+  int (*vec_uturn)(mmd_handle, const double*, const double*, const double*, const double*, int, double*, double*);
   int (*gen_xobs)(mmd_handle);
   int (*init_interp)(mmd_handle);
   int (*philox)(mmd_handle, uint64_t, uint64_t);

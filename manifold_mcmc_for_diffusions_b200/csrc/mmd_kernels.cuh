@@ -152,7 +152,8 @@ MMD_HD StepCoef make_step_coef(int gaussian, double dt) {
   return sc;
 }
 
-enum : int { ST_NOTCONV = 1, ST_DIVERGED = 2, ST_NONREV = 4, ST_NONFINITE = 8 };
+enum : int { ST_NOTCONV = 1, ST_DIVERGED = 2, ST_NONREV = 4, ST_NONFINITE = 8,
+             ST_INACTIVE = 16 /* parked by the host-side tree builder: not an error, the kernels just skip the chain */ };
 enum : int { PSEL_CUR = 0, PSEL_OTHER = 1, PSEL_WORK = 2 };
 
 // ------------------------------------------------------------------------------------------

@@ -1311,8 +1311,8 @@ k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, doub
            int reset_status) {
   const Tid t = thread_id(d);
   const FlowCoef noflow = {0, 1.0, 0.0, 0.0};
-  // per-chain step sizes keep the sign (integration direction) of the scalar argument
-  const StepCoef sc = make_step_coef(d.gaussian, W.use_dt_chain ? copysign(W.dt_chain[t.cix], dt) : dt);
+  // per-chain step sizes may be signed (per-chain integration direction); a negative scalar flips them all
+  const StepCoef sc = make_step_coef(d.gaussian, W.use_dt_chain ? (dt < 0.0 ? -W.dt_chain[t.cix] : W.dt_chain[t.cix]) : dt);
   for (int s = 0; s < n_steps; ++s) {
     if (reset_status && t.slot == 0) W.status[t.cix] = 0;
     __syncthreads();
@@ -1368,6 +1368,100 @@ __global__ void k_hamiltonian(Dims d, Slots S, Work W, int part, int sel, double
   }
   block_reduce<1, 0>(acc, smem, t);
   if (t.slot == 0 && t.act) hout[t.cix] = acc[0] + S.ldv[sl * S.s_ld + t.cix];
+}
+
+// ------------------------------------------------------------------------------------------
+// vector primitives on q-like arrays for host-driven tree building (batched dynamic HMC / NUTS):
+// masked copy / axpy and the U-turn inner products.  Array selectors: VEC_Q / VEC_P = the live
+// position / momentum (slot resolved per chain), otherwise a pointer to an auxiliary q-like array.
+// ------------------------------------------------------------------------------------------
+MMD_D int chain_of_qlike_index(const Dims& d, long long e) {
+  int tile, cl;
+  if (e < d.off_body) {
+    tile = (int)(e / ((long long)d.rows_head * d.cpb));
+    cl = (int)(e % d.cpb);
+  } else if (e < d.off_noise) {
+    const long long r = e - d.off_body;
+    tile = (int)(r / ((long long)d.rows_body * d.nta));
+    cl = (int)(((r % (d.V * d.nta)) / d.V) % d.cpb);
+  } else {
+    const long long r = e - d.off_noise;
+    tile = (int)(r / ((long long)d.rows_noise * d.nta));
+    cl = (int)(r % d.cpb);
+  }
+  return tile * d.cpb + cl;
+}
+// dst = beta * dst + alpha * src for the chains with mask != 0 (mask == nullptr: all chains).
+// live_dst / live_src: 0 = plain array, 1 = slot array S.q / S.p indexed by cur[chain]
+static __global__ void k_vec_axpby(Dims d, double* __restrict__ dst, int live_dst, const double* __restrict__ src,
+                                   int live_src, long long slot_stride, const int* __restrict__ cur, double alpha,
+                                   double beta, const int* __restrict__ mask) {
+  const long long n = d.qsize;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int chain = chain_of_qlike_index(d, e);
+    if (chain >= d.n_chains || (mask && !mask[chain])) continue;
+    const long long od = live_dst ? cur[chain] * slot_stride + e : e;
+    const long long os = live_src ? cur[chain] * slot_stride + e : e;
+    const double sv = (alpha == 0.0) ? 0.0 : alpha * src[os];
+    dst[od] = (beta == 0.0) ? sv : fma(beta, dst[od], sv);
+  }
+}
+// U-turn inner products per chain: with s = c - dd + a,  out1 = a . s,  out2 = e . s   (only valid rows)
+template <class M>
+__global__ void k_vec_uturn(Dims d, int part, const double* __restrict__ a, const double* __restrict__ dd,
+                            const double* __restrict__ c, const double* __restrict__ e, int live_e,
+                            long long slot_stride, const int* __restrict__ cur, double* __restrict__ out1,
+                            double* __restrict__ out2) {
+  const Tid t = thread_id(d);
+  extern __shared__ double smem[];
+  const long long oe = live_e ? (long long)cur[t.cix] * slot_stride : 0;
+  const QPtr pa = qptr<M>(const_cast<double*>(a), d, t), pd = qptr<M>(const_cast<double*>(dd), d, t);
+  const QPtr pc = qptr<M>(const_cast<double*>(c), d, t), pe = qptr<M>(const_cast<double*>(e) + oe, d, t);
+  double acc[2] = {0.0, 0.0};
+  if (t.slot < d.nb[part]) {
+    const Blk B = get_block<M>(d, part, t.slot);
+    const int nstep = B.n * d.S;
+    for (int s = 0; s < nstep; ++s) {
+      double va[M::V], vd[M::V], vc[M::V], ve[M::V];
+      ldrec<M::V>(pa.body + s * M::V * t.nta, va);
+      ldrec<M::V>(pd.body + s * M::V * t.nta, vd);
+      ldrec<M::V>(pc.body + s * M::V * t.nta, vc);
+      ldrec<M::V>(pe.body + s * M::V * t.nta, ve);
+#pragma unroll
+      for (int j = 0; j < M::V; ++j) {
+        const double sv = vc[j] - vd[j] + va[j];
+        acc[0] = fma(va[j], sv, acc[0]);
+        acc[1] = fma(ve[j], sv, acc[1]);
+      }
+    }
+    if (d.noisy)
+      for (int k = 0; k < B.n; ++k) {
+        const double sv = pc.noise[k * t.nta] - pd.noise[k * t.nta] + pa.noise[k * t.nta];
+        acc[0] = fma(pa.noise[k * t.nta], sv, acc[0]);
+        acc[1] = fma(pe.noise[k * t.nta], sv, acc[1]);
+      }
+    if (B.ini)
+      for (int r = 0; r < d.rows_head; ++r) {
+        const double sv = pc.head[r * t.cpb] - pd.head[r * t.cpb] + pa.head[r * t.cpb];
+        acc[0] = fma(pa.head[r * t.cpb], sv, acc[0]);
+        acc[1] = fma(pe.head[r * t.cpb], sv, acc[1]);
+      }
+  }
+  block_reduce<2, 0>(acc, smem, t);
+  if (t.slot == 0 && t.act) {
+    out1[t.cix] = acc[0];
+    out2[t.cix] = acc[1];
+  }
+}
+// park / release chains: sets or clears ST_INACTIVE according to mask; clear_errors also drops the error bits
+static __global__ void k_set_inactive(Dims d, Work W, const int* __restrict__ mask, int clear_errors) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.n_chains) return;
+  int st = W.status[c];
+  if (clear_errors) st = 0;
+  st = mask && mask[c] ? (st | ST_INACTIVE) : (st & ~ST_INACTIVE);
+  W.status[c] = st;
 }
 
 // ------------------------------------------------------------------------------------------

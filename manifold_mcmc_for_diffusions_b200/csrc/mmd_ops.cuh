@@ -129,6 +129,15 @@ struct Ops {
     CK(cudaGetLastError());
     return 0;
   }
+  static int vec_uturn(mmd_handle h, const double* a, const double* dd, const double* c, const double* e, int live_e,
+                       double* out1, double* out2) {
+    const int n = nt(h);
+    k_vec_uturn<Mdl><<<h->d.n_tiles, n, (size_t)2 * n * sizeof(double), h->stream>>>(
+        h->d, h->partition, a, dd, c, e, live_e, h->S.s_q, h->S.cur, out1, out2);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
   static void constr_rows(mmd_handle h, const std::vector<double>& buf, double* c_out) {
     // thread-private [tile][NRMAX][nta] -> [chain][n_c]: rows of block b start at its row0
     const Dims& d = h->d;
@@ -152,7 +161,7 @@ mmd_ops make_ops() {
   t.X = Mdl::X; t.V = Mdl::V; t.Z = Mdl::Z; t.V0 = Mdl::V0; t.Y = Mdl::Y; t.nrmax = NRMAX; t.rmax = RMAX;
   t.point = O::point; t.constr = O::constr; t.project = O::project; t.qn = O::qn; t.leapfrog = O::leapfrog;
   t.hamiltonian = O::hamiltonian; t.pack = O::pack; t.unpack = O::unpack; t.retile = O::retile;
-  t.gen_xobs = O::gen_xobs; t.init_interp = O::init_interp; t.philox = O::philox; t.constr_rows = O::constr_rows;
+  t.vec_uturn = O::vec_uturn; t.gen_xobs = O::gen_xobs; t.init_interp = O::init_interp; t.philox = O::philox; t.constr_rows = O::constr_rows;
   return t;
 }
 

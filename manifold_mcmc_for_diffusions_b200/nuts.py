@@ -1,0 +1,143 @@
+"""Batched dynamic-HMC (NUTS) transition for resident chains: the reference's
+``mici.transitions.MultinomialDynamicIntegrationTransition`` (call site ``scripts/utils.py:292-301``; Mici 0.1.10
+semantics as in SURVEY.md appendix A) for thousands of chains at once.
+
+The host keeps the per-chain tree bookkeeping (a few scalars per chain, NumPy); every state vector lives on the
+device and every O(dim_q) operation -- constrained leapfrog steps, Hamiltonians, momentum sums, no-U-turn inner
+products, proposal copies -- is a kernel of ``libmmd_b200.so`` (``mmd_vec_*`` entry points).  Trees are built by
+iterative doubling with multinomial sampling inside the new sub-tree, biased progressive sampling between the old
+tree and the new sub-tree, the no-U-turn criterion on momentum sums (sub-tree checks through momentum / momentum-sum
+check-points at the power-of-two leaves, tree check on the two edges), termination on a Hamiltonian error above
+``max_delta_h`` (divergence) or an integrator error (convergence / non-reversible step; the current proposal is
+kept, like Mici).  All chains start their transition together and advance leaf by leaf; chains whose tree is
+finished are parked (``mmd_set_inactive``) until the deepest tree of the batch is complete.
+"""
+
+import numpy as np
+
+EQ0, EQ1, EP0, EP1, PROP, SUMP, SUBPROP, SUBSUM, CK0 = range(9)
+
+
+def _popcount(x):
+    return bin(x).count("1")
+
+
+def _trailing_ones(x):
+    n = 0
+    while x & 1:
+        n += 1
+        x >>= 1
+    return n
+
+
+class BatchedNUTS:
+    def __init__(self, chains, max_tree_depth=10, max_delta_h=1000.0):
+        self.bc = chains
+        self.max_tree_depth = int(max_tree_depth)
+        self.max_delta_h = float(max_delta_h)
+        self.ckp = [CK0 + i for i in range(self.max_tree_depth)]
+        self.cks = [CK0 + self.max_tree_depth + i for i in range(self.max_tree_depth)]
+        chains.aux_reserve(CK0 + 2 * self.max_tree_depth)
+
+    def transition(self, step_size, rng, seed, it, switch_partition=True):
+        """One momentum refresh + dynamic integration transition (+ partition switch) for every chain.
+        step_size: scalar or per-chain array; rng: NumPy Generator for the tree decisions (directions,
+        multinomial / progressive sampling); (seed, it) key the on-device Philox momentum draw.
+        Returns the per-chain statistics Mici reports."""
+        bc, n = self.bc, self.bc.n_chains
+        Q, P = bc.VEC_Q, bc.VEC_P
+        eps = np.broadcast_to(np.asarray(step_size, dtype=np.float64), (n,)).copy()
+        bc.transition_begin(seed, it)
+        h0 = bc.hamiltonian()
+        for a in (EQ0, EQ1, PROP):
+            bc.vec_axpby(a, Q)
+        for a in (EP0, EP1, SUMP):
+            bc.vec_axpby(a, P)
+        logw = -h0
+        active = np.isfinite(h0)
+        last_dir = np.zeros(n, dtype=np.int64)
+        n_step = np.zeros(n, dtype=np.int64)
+        sum_acc = np.zeros(n)
+        depth_reached = np.zeros(n, dtype=np.int64)
+        diverging = np.zeros(n, dtype=bool)
+        conv_err = np.zeros(n, dtype=bool)
+        nonrev = np.zeros(n, dtype=bool)
+        for depth in range(self.max_tree_depth):
+            if not active.any():
+                break
+            dirs = np.where(rng.random(n) < 0.5, 1, -1)
+            # put the live state of every chain at the edge its new sub-tree grows from
+            sw = active & (last_dir != 0) & (dirs != last_dir)
+            if sw.any():
+                for sgn, eq, ep in ((1, EQ1, EP1), (-1, EQ0, EP0)):
+                    m = sw & (dirs == sgn)
+                    if m.any():
+                        bc.vec_axpby(Q, eq, mask=m)
+                        bc.vec_axpby(P, ep, mask=m)
+                bc.set_inactive(~active)
+                bc.relinearize()
+            last_dir = np.where(active, dirs, last_dir)
+            bc.set_step_sizes(dirs * eps)
+            bc.vec_axpby(SUBSUM, SUBSUM, alpha=0.0, beta=0.0)
+            sub_logw = np.full(n, -np.inf)
+            in_sub = active.copy()
+            for leaf in range(2 ** depth):
+                if not in_sub.any():
+                    break
+                bc.set_inactive(~in_sub)
+                bc.transition_steps(1.0, 1)
+                st = bc.step_info()["status"]
+                err = in_sub & ((st & 7) != 0)
+                conv_err |= err & ((st & 3) != 0)
+                nonrev |= err & ((st & 4) != 0)
+                ok = in_sub & ~err
+                h = bc.hamiltonian()
+                h = np.where(np.isnan(h), np.inf, h)
+                n_step[ok] += 1
+                with np.errstate(over="ignore", invalid="ignore"):
+                    sum_acc[ok] += np.minimum(1.0, np.exp(h0[ok] - h[ok]))
+                div = ok & (h - h0 > self.max_delta_h)
+                diverging |= div
+                ok &= ~div
+                bc.vec_axpby(SUBSUM, P, 1.0, 1.0, mask=ok)
+                lw = -h
+                new_logw = np.logaddexp(sub_logw, lw)
+                with np.errstate(divide="ignore"):
+                    take = ok & (np.log(rng.random(n)) < lw - new_logw)
+                sub_logw = np.where(ok, new_logw, sub_logw)
+                if take.any():
+                    bc.vec_axpby(SUBPROP, Q, mask=take)
+                turning = np.zeros(n, dtype=bool)
+                idx_max = _popcount(leaf >> 1)
+                if leaf % 2 == 0:
+                    bc.vec_axpby(self.ckp[idx_max], P, mask=ok)
+                    bc.vec_axpby(self.cks[idx_max], SUBSUM, mask=ok)
+                else:
+                    for i in range(idx_max, idx_max - _trailing_ones(leaf), -1):
+                        d1, d2 = bc.vec_uturn(self.ckp[i], self.cks[i], SUBSUM, P)
+                        turning |= ok & ((d1 < 0) | (d2 < 0))
+                in_sub = ok & ~turning
+                active &= ~(err | div | turning)
+            done = in_sub & active
+            with np.errstate(divide="ignore"):
+                accept = done & (np.log(rng.random(n)) < sub_logw - logw)
+            if accept.any():
+                bc.vec_axpby(PROP, SUBPROP, mask=accept)
+            logw = np.where(done, np.logaddexp(logw, sub_logw), logw)
+            bc.vec_axpby(SUMP, SUBSUM, 1.0, 1.0, mask=done)
+            for sgn, eq, ep in ((1, EQ1, EP1), (-1, EQ0, EP0)):
+                m = done & (dirs == sgn)
+                if m.any():
+                    bc.vec_axpby(eq, Q, mask=m)
+                    bc.vec_axpby(ep, P, mask=m)
+            d1, d2 = bc.vec_uturn(EP0, EP0, SUMP, EP1)      # s = SUMP: (EP0 . SUMP, EP1 . SUMP)
+            depth_reached[done] = depth + 1
+            active &= done & ~((d1 < 0) | (d2 < 0))
+        bc.set_inactive(None, clear_errors=True)
+        bc.vec_axpby(Q, PROP)
+        bc.set_step_sizes(eps)
+        if switch_partition:
+            bc.switch_partition()
+        return {"n_step": n_step, "accept_stat": sum_acc / np.maximum(n_step, 1), "tree_depth": depth_reached,
+                "diverging": diverging, "convergence_error": conv_err, "non_reversible_step": nonrev,
+                "hamiltonian_init": h0}

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""The reference notebook's experiment end to end with the batched on-device machinery: dynamic HMC (NUTS,
+multinomial, max depth 10) + per-chain dual-averaging warm-up (target 0.8, regularisation 0.1) + partition switching,
+Gaussian splitting, Newton projection -- compared with the numbers the notebook recorded (cell 43/45: accept_stat
+0.83, n_step 28.3, convergence_error 0.15, posterior table)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from manifold_mcmc_for_diffusions_b200 import BatchedChains  # noqa: E402
+from manifold_mcmc_for_diffusions_b200.diagnostics import rhat  # noqa: E402
+from manifold_mcmc_for_diffusions_b200.example_models import fhn_notebook as m  # noqa: E402
+from manifold_mcmc_for_diffusions_b200.nuts import BatchedNUTS  # noqa: E402
+from tools.notebook_known_answer import NOTEBOOK  # noqa: E402
+
+
+def main():
+    n = int(os.environ.get("NCH", 64))
+    n_warm = int(os.environ.get("NWARM", 150))
+    n_main = int(os.environ.get("NMAIN", 150))
+    depth = int(os.environ.get("DEPTH", 10))
+    T, S, R, obs_interval = 100, 25, 5, 0.5
+    q_ref = np.random.RandomState(20200710).standard_normal(m.dim_z + m.dim_x + T * S * m.dim_v)
+    _, y_seq, _, _ = m.generate_from_model(q_ref, obs_interval / S, S)
+    bc = BatchedChains("fhn_notebook", obs_interval, S, R, y_seq, 4, n, use_gaussian_splitting=True)
+    bc.opts.solver = 1
+    bc.opts.constraint_tol, bc.opts.position_tol, bc.opts.reverse_check_tol = 1e-9, 1e-8, 2e-8
+    rng = np.random.default_rng(20200710)
+    u, v0 = 0.5 * rng.standard_normal((n, 4)), rng.standard_normal((n, 2))
+    xo = np.concatenate((np.broadcast_to(y_seq, (n, T, 1)), 0.5 * rng.standard_normal((n, T, 1))), -1)
+    bc.init_linear_interpolation(u, v0, xo, 0)
+    # short static-HMC phase to leave the interpolated initial states (as in tools/notebook_known_answer.py)
+    it = 0
+    for step in (0.025, 0.05):
+        moved = np.zeros(n)
+        for _ in range(int(os.environ.get("NPRE", 150))):
+            bc.hmc_transition(step, 8, 20200710, it)
+            it += 1
+            moved += bc.transition_stats()["accepted"]
+        stuck = np.flatnonzero(moved == 0)
+        if len(stuck) and len(stuck) < n:
+            q, _, x = bc.get_state()
+            src = rng.choice(np.flatnonzero(moved > 0), size=len(stuck))
+            q[stuck], x[stuck] = q[src], x[src]
+            bc.set_state(q, x, bc.partition)
+    nuts = BatchedNUTS(bc, max_tree_depth=depth)
+    t0 = time.time()
+    bc.adapt_start(0.05, target=0.8, reg_coefficient=0.1)
+    warm = {"accept_stat": [], "n_step": []}
+    for k in range(n_warm):
+        st = nuts.transition(bc.get_step_sizes(), rng, 20200710, it)
+        it += 1
+        bc.adapt_update(st["accept_stat"])
+        warm["accept_stat"].append(st["accept_stat"].mean())
+        warm["n_step"].append(st["n_step"].mean())
+    bc.adapt_stop(pool=True)
+    eps = float(bc.get_step_sizes()[0])
+    names = ["σ", "ϵ", "γ", "β", "x_0[0]", "x_0[1]"]
+    draws = np.empty((n, n_main, 6))
+    acc, nst, cerr, nrv, dep = [], [], [], [], []
+    for k in range(n_main):
+        st = nuts.transition(eps, rng, 20200710, it)
+        it += 1
+        acc.append(st["accept_stat"].mean()); nst.append(st["n_step"].mean())
+        cerr.append(st["convergence_error"].mean()); nrv.append(st["non_reversible_step"].mean())
+        dep.append(st["tree_depth"].mean())
+        q, _, _ = bc.get_state()
+        z = m.generate_z(q[:, :4])
+        draws[:, k, :4] = z
+        draws[:, k, 4:] = m.generate_x_0(z, q[:, 4:6])
+    out = {"chains": n, "warm_up_transitions": n_warm, "main_transitions": n_main, "max_tree_depth": depth,
+           "adapted_step_size": eps, "accept_stat": float(np.mean(acc)), "n_step": float(np.mean(nst)),
+           "convergence_error": float(np.mean(cerr)), "non_reversible_step": float(np.mean(nrv)),
+           "tree_depth": float(np.mean(dep)), "wall_s": round(time.time() - t0, 1),
+           "warm_up_accept_stat_last20": float(np.mean(warm["accept_stat"][-20:])),
+           "notebook": {"accept_stat": 0.833, "n_step": 28.3, "convergence_error": 0.15, "non_reversible_step": 0.0},
+           "vars": {}}
+    worst = 0.0
+    for j, nm in enumerate(names):
+        x = draws[:, :, j]
+        mean, sd = float(x.mean()), float(x.std())
+        mcse = float(x.mean(1).std(ddof=1) / np.sqrt(n))
+        rm, rs, rmc = NOTEBOOK[nm]
+        zs = (mean - rm) / np.hypot(rmc, mcse)
+        worst = max(worst, abs(zs))
+        out["vars"][nm] = {"mean": round(mean, 4), "sd": round(sd, 4), "mcse": round(mcse, 5), "rhat": round(float(rhat(x)), 3),
+                           "notebook_mean": rm, "notebook_sd": rs, "z": round(float(zs), 2)}
+    out["max_abs_z"] = round(worst, 2)
+    print(json.dumps(out, ensure_ascii=False))
+
+
+if __name__ == "__main__":
+    main()
