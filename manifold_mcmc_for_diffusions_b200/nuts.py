@@ -15,7 +15,7 @@ finished are parked (``mmd_set_inactive``) until the deepest tree of the batch i
 
 import numpy as np
 
-EQ0, EQ1, EP0, EP1, PROP, SUMP, SUBPROP, SUBSUM, CK0 = range(9)
+EQ0, EQ1, EP0, EP1, PROP, SUMP, SUBPROP, SUBSUM, TMP, CK0 = range(10)
 
 
 def _popcount(x):
@@ -31,13 +31,20 @@ def _trailing_ones(x):
 
 
 class BatchedNUTS:
-    def __init__(self, chains, max_tree_depth=10, max_delta_h=1000.0):
+    def __init__(self, chains, max_tree_depth=10, max_delta_h=1000.0, do_extra_subtree_checks=True):
         self.bc = chains
-        self.max_tree_depth = int(max_tree_depth)
+        self.max_tree_depth = D = int(max_tree_depth)
         self.max_delta_h = float(max_delta_h)
-        self.ckp = [CK0 + i for i in range(self.max_tree_depth)]
-        self.cks = [CK0 + self.max_tree_depth + i for i in range(self.max_tree_depth)]
-        chains.aux_reserve(CK0 + 2 * self.max_tree_depth)
+        self.do_extra_subtree_checks = bool(do_extra_subtree_checks)
+        # check-points per span level: momentum / running momentum sum at the first leaf of the span (ckp, cks), and
+        # for the extra checks at the last leaf of its first half (midp, mids) and momentum at the first leaf of
+        # its second half (inop)
+        self.ckp = [CK0 + i for i in range(D)]
+        self.cks = [CK0 + D + i for i in range(D)]
+        self.midp = [CK0 + 2 * D + i for i in range(D)]
+        self.mids = [CK0 + 3 * D + i for i in range(D)]
+        self.inop = [CK0 + 4 * D + i for i in range(D)]
+        chains.aux_reserve(CK0 + (5 if self.do_extra_subtree_checks else 2) * D)
 
     def transition(self, step_size, rng, seed, it, switch_partition=True):
         """One momentum refresh + dynamic integration transition (+ partition switch) for every chain.
@@ -108,14 +115,33 @@ class BatchedNUTS:
                 if take.any():
                     bc.vec_axpby(SUBPROP, Q, mask=take)
                 turning = np.zeros(n, dtype=bool)
-                idx_max = _popcount(leaf >> 1)
+                idx_max, t_ones = _popcount(leaf >> 1), _trailing_ones(leaf)
+                extra = self.do_extra_subtree_checks
                 if leaf % 2 == 0:
                     bc.vec_axpby(self.ckp[idx_max], P, mask=ok)
                     bc.vec_axpby(self.cks[idx_max], SUBSUM, mask=ok)
+                    if extra and leaf > 0:
+                        # first leaf of the second half of the span whose first half ended at leaf - 1
+                        bc.vec_axpby(self.inop[_trailing_ones(leaf - 1)], P, mask=ok)
                 else:
-                    for i in range(idx_max, idx_max - _trailing_ones(leaf), -1):
+                    # spans of 2, 4, ... leaves ending here (Mici _build_tree merges, innermost first)
+                    for k, i in enumerate(range(idx_max, idx_max - t_ones, -1), start=1):
                         d1, d2 = bc.vec_uturn(self.ckp[i], self.cks[i], SUBSUM, P)
                         turning |= ok & ((d1 < 0) | (d2 < 0))
+                        if extra and k >= 2:
+                            lv = k - 1
+                            # (first leaf, first leaf of 2nd half) with sum(1st half) + that momentum
+                            bc.vec_axpby(TMP, self.mids[lv])
+                            bc.vec_axpby(TMP, self.inop[lv], 1.0, 1.0)
+                            d1, d2 = bc.vec_uturn(self.ckp[i], self.cks[i], TMP, self.inop[lv])
+                            turning |= ok & ((d1 < 0) | (d2 < 0))
+                            # (last leaf of 1st half, last leaf) with sum(2nd half) + that momentum
+                            d1, d2 = bc.vec_uturn(self.midp[lv], self.mids[lv], SUBSUM, P)
+                            turning |= ok & ((d1 < 0) | (d2 < 0))
+                    if extra and 2 ** (t_ones + 1) <= 2 ** depth:
+                        # this leaf ends the first half of the span of 2^(t_ones+1) leaves
+                        bc.vec_axpby(self.midp[t_ones], P, mask=ok)
+                        bc.vec_axpby(self.mids[t_ones], SUBSUM, mask=ok)
                 in_sub = ok & ~turning
                 active &= ~(err | div | turning)
             done = in_sub & active
@@ -138,6 +164,8 @@ class BatchedNUTS:
         bc.set_step_sizes(eps)
         if switch_partition:
             bc.switch_partition()
+        else:
+            bc.relinearize()
         return {"n_step": n_step, "accept_stat": sum_acc / np.maximum(n_step, 1), "tree_depth": depth_reached,
                 "diverging": diverging, "convergence_error": conv_err, "non_reversible_step": nonrev,
                 "hamiltonian_init": h0}

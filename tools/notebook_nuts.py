@@ -63,12 +63,15 @@ def main():
     names = ["σ", "ϵ", "γ", "β", "x_0[0]", "x_0[1]"]
     draws = np.empty((n, n_main, 6))
     acc, nst, cerr, nrv, dep = [], [], [], [], []
+    per = {"n_step": [], "accept_stat": [], "convergence_error": [], "tree_depth": []}
     for k in range(n_main):
         st = nuts.transition(eps, rng, 20200710, it)
         it += 1
         acc.append(st["accept_stat"].mean()); nst.append(st["n_step"].mean())
         cerr.append(st["convergence_error"].mean()); nrv.append(st["non_reversible_step"].mean())
         dep.append(st["tree_depth"].mean())
+        for key in per:
+            per[key].append(np.asarray(st[key], dtype=np.float64))
         q, _, _ = bc.get_state()
         z = m.generate_z(q[:, :4])
         draws[:, k, :4] = z
@@ -91,6 +94,12 @@ def main():
         out["vars"][nm] = {"mean": round(mean, 4), "sd": round(sd, 4), "mcse": round(mcse, 5), "rhat": round(float(rhat(x)), 3),
                            "notebook_mean": rm, "notebook_sd": rs, "z": round(float(zs), 2)}
     out["max_abs_z"] = round(worst, 2)
+    ns, ce = np.concatenate(per["n_step"]), np.concatenate(per["convergence_error"]) > 0
+    out["n_step_quantiles_error_transitions"] = np.quantile(ns[ce], [0.1, 0.5, 0.9]).tolist() if ce.any() else None
+    out["n_step_quantiles_clean_transitions"] = np.quantile(ns[~ce], [0.1, 0.5, 0.9]).tolist() if (~ce).any() else None
+    out["fraction_no_step"] = float(np.mean(ns == 0))
+    if os.environ.get("STATS_OUT"):
+        np.savez(os.environ["STATS_OUT"], **{k: np.stack(v) for k, v in per.items()})
     print(json.dumps(out, ensure_ascii=False))
 
 
