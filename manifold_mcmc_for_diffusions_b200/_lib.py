@@ -105,6 +105,7 @@ SIGNATURES = {
     "mmd_relinearize": (C.c_int, [_H]),
     "mmd_successful_steps": (C.c_longlong, [_H, C.c_int]),
     "mmd_total_qn_iterations": (C.c_longlong, [_H, C.c_int]),
+    "mmd_debug_phase_cycles": (C.c_int, [_H, C.POINTER(C.c_ulonglong), C.c_int]),
     "mmd_profile_enable": (C.c_int, [_H, C.c_int, C.c_int]),
     "mmd_profile_summary": (C.c_int, [_H, C.c_int, _ip, _dp]),
     "mmd_launch_count": (C.c_longlong, [_H]),

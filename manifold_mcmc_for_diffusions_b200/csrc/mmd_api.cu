@@ -188,6 +188,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   rc |= dalloc(h, &Sx.K, 2 * Sx.s_K);
   rc |= dalloc(h, &Sx.Psib, 2 * Sx.s_Psib);
   rc |= dalloc(h, &Sx.xend, 2 * Sx.s_xend);
+  rc |= dalloc(h, &Sx.kap, 2 * Sx.s_xend);
   rc |= dalloc(h, &Sx.A, 2 * Sx.s_A);
   rc |= dalloc(h, &Sx.L, 2 * Sx.s_L);
   rc |= dalloc(h, &Sx.DinvA, 2 * Sx.s_A);
@@ -214,6 +215,10 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   rc |= dalloc(h, &W.itsum, nc);
   rc |= dalloc(h, &W.dt_chain, nc);
   W.use_dt_chain = 0;
+  W.phase = nullptr;
+#ifdef MMD_PHASE_CLOCK
+  rc |= dalloc(h, &W.phase, 32);
+#endif
   rc |= dalloc(h, &h->ad_state, 4 * nc);
   rc |= dalloc(h, &h->maskbuf, nc);
   h->adapting = false;
@@ -697,6 +702,14 @@ static long long sum_counter(mmd_handle h, long long* dev, int reset) {
 
 long long mmd_successful_steps(mmd_handle h, int reset) { return sum_counter(h, h->n_ok, reset); }
 long long mmd_total_qn_iterations(mmd_handle h, int reset) { return sum_counter(h, h->W.itsum, reset); }
+
+int mmd_debug_phase_cycles(mmd_handle h, unsigned long long* out32, int reset) {
+  if (!h->W.phase) FAIL("phase clocks are compiled in only with -DMMD_PHASE_CLOCK (tools/phase_times.py)");
+  CK(cudaMemcpyAsync(out32, h->W.phase, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (reset) CK(cudaMemsetAsync(h->W.phase, 0, 32 * sizeof(unsigned long long), h->stream));
+  return 0;
+}
 
 int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, int* status) {
   const int n = h->d.n_chains;

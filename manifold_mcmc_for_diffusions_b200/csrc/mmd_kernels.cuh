@@ -86,6 +86,7 @@ struct Slots {
   double* K;       // thread-private [rmax*S*X*V]
   double* Psib;    // thread-private [rmax*X*X]
   double* xend;    // thread-private [rmax*X]      state at the observation times (nonlinear obs_func)
+  double* kap;     // thread-private [rmax*X]      kap_k[i] = max_{t in interval k, j} |K_t[i][j]| (update-norm bound)
   double* A;       // thread-private [NRMAX*U]     dc/du rows
   double* L;       // thread-private [NRTRI]       packed lower Cholesky factor of D_b (diagonal stored inverted)
   double* DinvA;   // thread-private [NRMAX*U]
@@ -114,7 +115,30 @@ struct Work {
   long long* itsum;  // [chains] total projection iterations executed (both directions)
   double* dt_chain;  // [chains] per-chain step sizes (used instead of the scalar step size when use_dt_chain)
   int use_dt_chain;
+  unsigned long long* phase;  // [32] per-phase cycle counters of thread 0 of every CTA (MMD_PHASE_CLOCK builds only)
 };
+
+// Phase clocks (tools/phase_times.py): compiled in only with -DMMD_PHASE_CLOCK; thread 0 of each CTA adds the
+// cycles between successive marks to W.phase[i]
+#ifdef MMD_PHASE_CLOCK
+#define PH_T0 long long _pc = clock64();
+#define PH(i)                                                                     \
+  do {                                                                            \
+    if (threadIdx.x == 0 && W.phase) {                                            \
+      const long long _n = clock64();                                             \
+      atomicAdd(&W.phase[i], (unsigned long long)(_n - _pc));                     \
+      _pc = _n;                                                                   \
+    }                                                                             \
+  } while (0)
+#define PH_ADD(i, n)                                                              \
+  do {                                                                            \
+    if (threadIdx.x == 0 && W.phase) atomicAdd(&W.phase[i], (unsigned long long)(n)); \
+  } while (0)
+#else
+#define PH_T0
+#define PH(i)
+#define PH_ADD(i, n)
+#endif
 
 struct FlowCoef {
   int mode;

@@ -46,6 +46,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
   double* Kc = tpr<XV>(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
   double* Psibc = tp(S.Psib + sl * S.s_Psib, d.rmax * X * X, t);
   double* xendc = tp(S.xend + sl * S.s_xend, d.rmax * X, t);
+  double* kapc = tp(S.kap + sl * S.s_xend, d.rmax * X, t);
   double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
   double* DinvAc = tp(S.DinvA + sl * S.s_A, NRMAX * U, t);
   double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
@@ -71,6 +72,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #pragma unroll
   for (int i = 0; i < UTRI + 1; ++i) red[i] = 0.0;
   double xlast[X];  // state at the end of the block
+  PH_T0
 
   if (has_blk && !skip) {
     double dx0_dv0[X * M::V0], dx0_dz[X * Z];
@@ -94,11 +96,13 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
         for (int i = 0; i < X; ++i) x[i] = xn[i];
       }
       if (!M::OBS_LINEAR) stcol<X>(xendc + k * X * nta, nta, x);
-      double Psi[X * X], Qk[X * X], Zk[X * Z];
+      double Psi[X * X], Qk[X * X], Zk[X * Z], kap[X];
 #pragma unroll
       for (int i = 0; i < X * X; ++i) { Psi[i] = (i % (X + 1) == 0) ? 1.0 : 0.0; Qk[i] = 0.0; }
 #pragma unroll
       for (int i = 0; i < X * Z; ++i) Zk[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < X; ++i) kap[i] = 0.0;
       double* Kk = Kc + k * d.S * XV * nta;
       for (int tt = d.S - 1; tt >= 0; --tt) {
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], tmp[X * X];
@@ -109,7 +113,11 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
         M::jac_z(P.C, xt, v, G);
         mm<X, V, X>(Psi, Bm, Kt);
         strec<XV>(Kk + tt * XV * nta, Kt);
-        // Qk += Kt Kt^T ; Zk += Psi G ; Psi = Psi F
+        // Qk += Kt Kt^T ; Zk += Psi G ; Psi = Psi F ; kap = max |Kt| per row
+#pragma unroll
+        for (int i = 0; i < X; ++i)
+#pragma unroll
+          for (int j = 0; j < V; ++j) kap[i] = fmax(kap[i], fabs(Kt[i * V + j]));
 #pragma unroll
         for (int i = 0; i < X; ++i)
 #pragma unroll
@@ -127,9 +135,11 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       stcol<X * X>(Psibc + k * X * X * nta, nta, Psi);
       stcol<X * X>(Qc + k * X * X * nta, nta, Qk);
       stcol<X * Z>(Ztc + k * X * Z * nta, nta, Zk);
+      stcol<X>(kapc + k * X * nta, nta, kap);
     }
 #pragma unroll
     for (int i = 0; i < X; ++i) xlast[i] = x[i];
+    PH(16);
     // ---------------- per-observation algebra: A_b = dc/du rows, D_b = J_v J_v^T (+ noise terms)
     double Su[X * Z], Pm[X * X], w[NRMAX * X], Dm[NTRI], Am[NRMAX * UMAX];
 #pragma unroll
@@ -216,8 +226,10 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       }
     }
     red[UTRI] = ldpart;
+    PH(17);
   }
   block_reduce<UTRI + 1, 0>(red, sm_red, t);
+  PH(18);
   double LCm[UTRI];
   for (int i = 0; i < U; ++i)
     for (int j = 0; j <= i; ++j) LCm[tri(i, j)] = red[tri(i, j)] + (i == j ? 1.0 : 0.0);
@@ -403,6 +415,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
           for (int j = 0; j < U; ++j) Gam[m * UMAX + j] = fma(az[m], Om[r * UMAX + j], Gam[m * UMAX + j]);
       }
     }
+    PH(19);
     // ---------------- second-order sweeps, last interval first
     double gam[X], gz[Z];
 #pragma unroll
@@ -428,6 +441,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #pragma unroll
         for (int i = 0; i < X; ++i) gam[i] += hv[i];
       }
+      PH(22);
       for (int tt = 0; tt < d.S; ++tt) {
         strec<X * X>(Yk + tt * X * X * nta, Y);
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], KM[V * X], Yn[X * X];
@@ -444,6 +458,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #pragma unroll
         for (int i = 0; i < X * X; ++i) Y[i] = Yn[i];
       }
+      PH(20);
       double Psi[X * X];
 #pragma unroll
       for (int i = 0; i < X * X; ++i) Psi[i] = (i % (X + 1) == 0) ? 1.0 : 0.0;
@@ -478,6 +493,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #pragma unroll
         for (int i = 0; i < X * X; ++i) Psi[i] = tmp[i];
       }
+      PH(21);
     }
     double gv0[M::V0];
     if (B.ini) {
@@ -504,6 +520,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
   }
   (void)xlast;
   block_reduce<UMAX, 0>(gu, sm_red, t);
+  PH(23);
   if (t.slot == 0 && !skip)
     for (int j = 0; j < U; ++j) gq.head[j * cpb] = gu[j];
 }
@@ -1003,6 +1020,110 @@ MMD_D void newton_solve_block(const Dims& d, const Blk& B, bool work, const Chai
 // mode 0 (forward):  linearisation = cur; on convergence q(other) = q_new, p(other) = pw - mom_coef * mu
 // mode 1 (reverse):  linearisation = other; compare q_back with q(cur) -> revd, no writes (Mici reverse check)
 // ------------------------------------------------------------------------------------------
+// One pointwise pass of the projection solve for this thread's block: q = q_w - J_lin^T lam_tot (mode 0: written to
+// the other slot together with the momentum update; mode 1: reverse check, only the distance to the reference
+// position).  WITH_INC also returns |J_lin^T (last increment)|_inf, the position-change norm of the reference's
+// convergence test (:1047-1055).
+template <class M, int NRMAX, int UMAX, bool WITH_INC>
+MMD_D double qn_pass(const Dims& d, const Slots& S, const Work& W, const Blk& B, const Tid& t, int mode, int cur, int sl,
+                     double mom_coef, double sig_lin, const double* dx0_dv0, const double* __restrict__ alph,
+                     const double* __restrict__ alphi, const double* a0tot, const double* a0inc, const double* u0,
+                     const double* stot, const double* sres, const double* sm_l, const double* sm_c, int NT,
+                     double* final_norm) {
+  constexpr int X = M::X, V = M::V, XV = M::X * M::V;
+  const int U = d.U, nta = t.nta, cpb = t.cpb;
+  const double* Kc = tpr<XV>(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
+  const QPtr qw = qptr<M>(W.qw, d, t);
+  const QPtr qout = qptr<M>(S.q + (1 - cur) * S.s_q, d, t);
+  const QPtr pout = qptr<M>(S.p + (1 - cur) * S.s_q, d, t);
+  const QPtr pin = qptr<M>(W.pw, d, t);
+  const QPtr qref = qptr<M>(S.q + cur * S.s_q, d, t);
+  double nm = 0.0, rv = 0.0;
+  for (int k = 0; k < B.n; ++k) {
+    double al[X], ai[X];
+    ldcol<X>(alph + k * X * nta, nta, al);
+    if (WITH_INC) ldcol<X>(alphi + k * X * nta, nta, ai);
+#pragma unroll 4
+    for (int tt = 0; tt < d.S; ++tt) {
+      const int so = (k * d.S + tt) * nta;
+      double Kt[XV], qv[V], ov[V], pv[V];
+#if MMD_POINTWISE_L2_PREFETCH > 0
+      if (k * d.S + tt + MMD_POINTWISE_L2_PREFETCH < B.n * d.S) {
+        const int sp = so + MMD_POINTWISE_L2_PREFETCH * nta;
+        prefetch_l2(Kc + sp * XV);
+        prefetch_l2(qw.body + sp * V);
+        prefetch_l2((mode == 0 ? pin.body : qref.body) + sp * V);
+      }
+#endif
+      ldrec<XV>(Kc + so * XV, Kt);
+      ldrec<V>(qw.body + so * V, qv);
+      ldrec<V>((mode == 0 ? pin.body : qref.body) + so * V, ov);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        double mu = 0.0, inc = 0.0;
+#pragma unroll
+        for (int i = 0; i < X; ++i) {
+          mu = fma(Kt[i * V + j], al[i], mu);
+          if (WITH_INC) inc = fma(Kt[i * V + j], ai[i], inc);
+        }
+        if (WITH_INC) nm = fmax(nm, fabs(inc));
+        qv[j] -= mu;
+        if (mode == 0) pv[j] = fma(-mom_coef, mu, ov[j]);
+        else rv = fmax(rv, fabs(qv[j] - ov[j]));
+      }
+      if (mode == 0) {
+        strec<V>(qout.body + so * V, qv);
+        strec<V>(pout.body + so * V, pv);
+      }
+    }
+    if (d.noisy) {
+      double mu = 0.0;
+      if (k < B.ny) {
+        mu = sig_lin * sm_l[k * NT];
+        if (WITH_INC) nm = fmax(nm, fabs(sig_lin * sm_c[k * NT]));
+      }
+      const double qn = qw.noise[k * nta] - mu;
+      if (mode == 0) {
+        qout.noise[k * nta] = qn;
+        pout.noise[k * nta] = fma(-mom_coef, mu, pin.noise[k * nta]);
+      } else {
+        rv = fmax(rv, fabs(qn - qref.noise[k * nta]));
+      }
+    }
+  }
+  if (B.ini) {
+    double t0[M::V0], ti[M::V0];
+    mtv<X, M::V0>(dx0_dv0, a0tot, t0);
+    mtv<X, M::V0>(dx0_dv0, a0inc, ti);
+#pragma unroll
+    for (int j = 0; j < M::V0; ++j) {
+      if (WITH_INC) nm = fmax(nm, fabs(ti[j]));
+      const int row = (U + j) * cpb;
+      const double qn = qw.head[row] - t0[j];
+      if (mode == 0) {
+        qout.head[row] = qn;
+        pout.head[row] = fma(-mom_coef, t0[j], pin.head[row]);
+      } else {
+        rv = fmax(rv, fabs(qn - qref.head[row]));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UMAX; ++j)
+      if (j < U) {
+        if (WITH_INC) nm = fmax(nm, fabs(sres[j]));
+        const double qn = u0[j] - stot[j];
+        if (mode == 0) {
+          qout.head[j * cpb] = qn;
+          pout.head[j * cpb] = fma(-mom_coef, stot[j], pin.head[j * cpb]);
+        } else {
+          rv = fmax(rv, fabs(qn - qref.head[j * cpb]));
+        }
+      }
+  }
+  *final_norm = rv;
+  return nm;
+}
+
 template <class M, int NRMAX, int RMAXP, int UMAX, bool NEWTON>
 MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ y, int part, int mode,
                   double mom_coef, double ctol, double ptol, double dtol, int max_iters) {
@@ -1017,6 +1138,7 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
   const double* Kc = tpr<XV>(S.K + sl * S.s_K, d.rmax * d.S * XV, t);
   const double* Psibc = tp(S.Psib + sl * S.s_Psib, d.rmax * X * X, t);
   const double* xendc = tp(S.xend + sl * S.s_xend, d.rmax * X, t);
+  const double* kapc = tp(S.kap + sl * S.s_xend, d.rmax * X, t);
   const double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
   const double* DinvAc = tp(S.DinvA + sl * S.s_A, NRMAX * U, t);
   const double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
@@ -1030,6 +1152,7 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
   Blk B;
   if (in_blk) B = get_block<M>(d, part, t.slot);
   bool done = !t.act || (W.status[t.cix] != 0);
+  bool pend = false;  // converged through the bound: iterate not written yet
   int st = 0, it = 0;
   double u0[UMAX], stot[UMAX];
 #pragma unroll
@@ -1059,8 +1182,11 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
   }
   double final_norm = 0.0;
   ChainPar<M, UMAX> Pkeep;
+  PH_T0
   while (true) {
     if (__syncthreads_and(done ? 1 : 0)) break;
+    PH(8);
+    PH_ADD(12, 1);
     const bool work = in_blk && !done;
     double sres[UMAX], err = 0.0;
     if (work) {
@@ -1108,12 +1234,18 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
     // the prefetch ring of the sweep and the reduction scratch share shared memory: every thread must have
     // left its sweep before any thread starts the cross-block reduction
     __syncthreads();
+    PH(9);
     if (NEWTON)
       newton_solve_block<M, NRMAX, RMAXP, UMAX>(d, B, work, Pkeep, sig_lin, dx0_dv0, qw, Kc, Psibc, xendc, Ac, alph,
                                                 sm_l, W, rr, sres, &err, sm_red, t, NT);
     else
       inv_gram_block<M, NRMAX, UMAX>(d, B, work, Ac, Lc, DinvAc, LCc, rr, sres, &err, sm_red, t);
-    // norm of this iteration's update and (speculative) finalisation when the constraint is met
+    // Convergence test of the reference (:1047-1055): |c| < constraint_tol AND |delta_q|_inf < position_tol for THIS
+    // iteration's update delta_q = J_lin^T (increment of the multipliers).  The exact norm needs a pass over K; a
+    // cheap upper bound (per-interval row maxima kap of K from the linearisation, exact for the head / noise
+    // entries) decides it whenever the bound is already below the tolerance -- the usual case, since |c| < 1e-9
+    // makes the update tiny.  Only an undecided chain pays for the exact pass; the iterate of a chain accepted
+    // through the bound is written once, after the loop, together with the other chains of the tile.
     const bool check = !done && (err < ctol);
     double nrm[1];
     nrm[0] = 0.0;
@@ -1129,105 +1261,46 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
       for (int j = 0; j < UMAX; ++j) stot[j] += sres[j];
       alpha_block<M, NRMAX, RMAXP>(B, lt, Psibc, xendc, nta, alph, a0tot);
     }
-    if (__syncthreads_or(check ? 1 : 0)) {
+    const int any_check = __syncthreads_or(check ? 1 : 0);
+    PH(10);
+    bool converged = false;
+    if (any_check) {
+      PH_ADD(13, 1);
+      double a0inc[X];
       if (work && check) {
-        double a0inc[X];
-        alpha_block<M, NRMAX, RMAXP>(B, rr, Psibc, xendc, nta, alphi, a0inc);
-        double nm = 0.0, rv = 0.0;
-        const QPtr qout = qptr<M>(S.q + (1 - cur) * S.s_q, d, t);
-        const QPtr pout = qptr<M>(S.p + (1 - cur) * S.s_q, d, t);
-        const QPtr pin = qptr<M>(W.pw, d, t);
-        const QPtr qref = qptr<M>(S.q + cur * S.s_q, d, t);
-        for (int k = 0; k < B.n; ++k) {
-          double al[X], ai[X];
-          ldcol<X>(alph + k * X * nta, nta, al);
-          ldcol<X>(alphi + k * X * nta, nta, ai);
-#pragma unroll 4
-          for (int tt = 0; tt < d.S; ++tt) {
-            const int so = (k * d.S + tt) * nta;
-            double Kt[XV], qv[V], ov[V], pv[V];
-#if MMD_POINTWISE_L2_PREFETCH > 0
-            if (k * d.S + tt + MMD_POINTWISE_L2_PREFETCH < B.n * d.S) {
-              const int sp = so + MMD_POINTWISE_L2_PREFETCH * nta;
-              prefetch_l2(Kc + sp * XV);
-              prefetch_l2(qw.body + sp * V);
-              prefetch_l2((mode == 0 ? pin.body : qref.body) + sp * V);
-            }
-#endif
-            ldrec<XV>(Kc + so * XV, Kt);
-            ldrec<V>(qw.body + so * V, qv);
-            ldrec<V>((mode == 0 ? pin.body : qref.body) + so * V, ov);
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-              double mu = 0.0, inc = 0.0;
-#pragma unroll
-              for (int i = 0; i < X; ++i) {
-                mu = fma(Kt[i * V + j], al[i], mu);
-                inc = fma(Kt[i * V + j], ai[i], inc);
-              }
-              nm = fmax(nm, fabs(inc));
-              qv[j] -= mu;
-              if (mode == 0) pv[j] = fma(-mom_coef, mu, ov[j]);
-              else rv = fmax(rv, fabs(qv[j] - ov[j]));
-            }
-            if (mode == 0) {
-              strec<V>(qout.body + so * V, qv);
-              strec<V>(pout.body + so * V, pv);
-            }
-          }
-          if (d.noisy) {
-            double mu = 0.0;
-            if (k < B.ny) {
-              mu = sig_lin * sm_l[k * NT];
-              nm = fmax(nm, fabs(sig_lin * sm_c[k * NT]));
-            }
-            const double qn = qw.noise[k * nta] - mu;
-            if (mode == 0) {
-              qout.noise[k * nta] = qn;
-              pout.noise[k * nta] = fma(-mom_coef, mu, pin.noise[k * nta]);
-            } else {
-              rv = fmax(rv, fabs(qn - qref.noise[k * nta]));
-            }
-          }
-        }
+        double ub = 0.0;
+        alpha_block<M, NRMAX, RMAXP>(B, rr, Psibc, xendc, nta, alphi, a0inc, kapc, &ub);
+        if (d.noisy)
+          for (int k = 0; k < B.ny; ++k) ub = fmax(ub, fabs(sig_lin * rr[k < NRMAX ? k : 0]));
         if (B.ini) {
-          double t0[M::V0], ti[M::V0];
-          mtv<X, M::V0>(dx0_dv0, a0tot, t0);
+          double ti[M::V0];
           mtv<X, M::V0>(dx0_dv0, a0inc, ti);
 #pragma unroll
-          for (int j = 0; j < M::V0; ++j) {
-            nm = fmax(nm, fabs(ti[j]));
-            const int row = (U + j) * cpb;
-            const double qn = qw.head[row] - t0[j];
-            if (mode == 0) {
-              qout.head[row] = qn;
-              pout.head[row] = fma(-mom_coef, t0[j], pin.head[row]);
-            } else {
-              rv = fmax(rv, fabs(qn - qref.head[row]));
-            }
-          }
+          for (int j = 0; j < M::V0; ++j) ub = fmax(ub, fabs(ti[j]));
 #pragma unroll
           for (int j = 0; j < UMAX; ++j)
-            if (j < U) {
-              nm = fmax(nm, fabs(sres[j]));
-              const double qn = u0[j] - stot[j];
-              if (mode == 0) {
-                qout.head[j * cpb] = qn;
-                pout.head[j * cpb] = fma(-mom_coef, stot[j], pin.head[j * cpb]);
-              } else {
-                rv = fmax(rv, fabs(qn - qref.head[j * cpb]));
-              }
-            }
+            if (j < U) ub = fmax(ub, fabs(sres[j]));
         }
-        nrm[0] = nm;
-        final_norm = rv;
+        nrm[0] = ub;
       }
       block_reduce<0, 1>(nrm, sm_red, t);
+      const bool undecided = check && !(nrm[0] < ptol);
+      if (check && !undecided) { converged = true; pend = true; }
+      if (__syncthreads_or(undecided ? 1 : 0)) {
+        PH_ADD(14, 1);
+        double ex[1];
+        ex[0] = 0.0;
+        if (work && undecided)
+          ex[0] = qn_pass<M, NRMAX, UMAX, true>(d, S, W, B, t, mode, cur, sl, mom_coef, sig_lin, dx0_dv0, alph, alphi,
+                                                a0tot, a0inc, u0, stot, sres, sm_l, sm_c, NT, &final_norm);
+        block_reduce<0, 1>(ex, sm_red, t);
+        if (undecided) converged = ex[0] < ptol;
+      }
+      PH(11);
     }
     if (!done) {
       it += 1;
       const bool diverged = (err > dtol) || (err != err);
-      const bool converged = check && (nrm[0] < ptol);
       if (converged) {
         done = true;
       } else if (diverged) {
@@ -1238,6 +1311,18 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
         st = ST_NOTCONV;
       }
     }
+  }
+  // iterates (mode 0) / reverse-check distances (mode 1) of the chains accepted through the bound
+  if (__syncthreads_or(pend ? 1 : 0)) {
+    double a0inc[X], sres0[UMAX];
+#pragma unroll
+    for (int i = 0; i < X; ++i) a0inc[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < UMAX; ++j) sres0[j] = 0.0;
+    if (in_blk && pend)
+      qn_pass<M, NRMAX, UMAX, false>(d, S, W, B, t, mode, cur, sl, mom_coef, sig_lin, dx0_dv0, alph, alphi, a0tot, a0inc,
+                                     u0, stot, sres0, sm_l, sm_c, NT, &final_norm);
+    PH(15);
   }
   // epilogue
   const bool live = t.act && (W.status[t.cix] == 0);
@@ -1316,20 +1401,29 @@ k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, doub
   for (int s = 0; s < n_steps; ++s) {
     if (reset_status && t.slot == 0) W.status[t.cix] = 0;
     __syncthreads();
+    PH_T0
     dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 0, PSEL_CUR, PSEL_WORK, sc.half_dt, sc.qcoef, sc.fwd);
     __syncthreads();
+    PH(0);
     dev_qn<M, NRMAX, RMAX, UMAX, NEWTON>(d, S, W, y, part, 0, sc.mom_coef, ctol, ptol, dtol, max_iters);
     __syncthreads();
+    PH(1);
     dev_point<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, 1, 1);
     __syncthreads();
+    PH(2);
     dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 1, PSEL_OTHER, PSEL_OTHER, 0.0, 0.0, sc.back);
     __syncthreads();
+    PH(3);
     dev_qn<M, NRMAX, RMAX, UMAX, NEWTON>(d, S, W, y, part, 1, 0.0, ctol, ptol, dtol, max_iters);
     __syncthreads();
+    PH(4);
     dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 1, PSEL_OTHER, PSEL_OTHER, sc.half_dt, sc.qcoef, noflow);
     __syncthreads();
+    PH(5);
     if (t.slot == 0 && t.act) dev_commit(d, S, W, rev_tol, n_ok, t.cix);
     __syncthreads();
+    PH(6);
+    PH_ADD(7, 1);
   }
 }
 

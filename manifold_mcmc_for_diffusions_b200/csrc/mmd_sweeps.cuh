@@ -260,9 +260,10 @@ MMD_D void lu_solve(const double* A, const int* piv, int n, double* x) {
 // recursion) are issued together instead of one L2 round trip per interval.
 template <class M, int NRMAX, int RMAX>
 MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict__ Psibc,
-                       const double* __restrict__ xendc, int nta, double* alph_out, double* alpha_start) {
+                       const double* __restrict__ xendc, int nta, double* alph_out, double* alpha_start,
+                       const double* __restrict__ kapc = nullptr, double* body_bound = nullptr) {
   constexpr int X = M::X;
-  double al[X];
+  double al[X], bnd = 0.0;
 #pragma unroll
   for (int i = 0; i < X; ++i) al[i] = 0.0;
   MMD_SOLVE_UNROLL
@@ -291,7 +292,15 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
           for (int i = 0; i < X; ++i)
             if (r == B.ny + i) al[i] += lam[r];
       }
-      stcol<X>(alph_out + k * X * nta, nta, al);
+      if (alph_out) stcol<X>(alph_out + k * X * nta, nta, al);
+      if (kapc) {
+        // |(J^T lam)_{v_t, j}| = |sum_i K_t[i][j] al[i]| <= sum_i kap_k[i] |al[i]| for every step t of interval k
+        double kp[X], sb = 0.0;
+        ldcol<X>(kapc + k * X * nta, nta, kp);
+#pragma unroll
+        for (int i = 0; i < X; ++i) sb = fma(kp[i], fabs(al[i]), sb);
+        bnd = (sb > bnd || sb != sb) ? sb : bnd;
+      }
     }
   }
   {
@@ -299,6 +308,7 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
     ldcol<X * X>(Psibc, nta, Ps);
     mtv<X, X>(Ps, al, alpha_start);
   }
+  if (body_bound) *body_bound = bnd;
 }
 
 // Woodbury solve G^{-1} r for this thread's block (lmult_by_inv_gram :915-942):
