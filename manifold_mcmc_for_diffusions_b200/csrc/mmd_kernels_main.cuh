@@ -249,83 +249,127 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
     double dx0_dv0[X * M::V0], dx0_dz[X * Z];
     M::gen_x0_jac(P.z, dx0_dv0, dx0_dz);
     const int nr = B.nrows;
-    // C^{-1}
+    // rows: compile-time bound and full unrolling for the small blocks (FHN), run-time bound for the large (SIR)
+    constexpr bool STATIC_ROWS = NRMAX <= 8;
+    constexpr int UR = STATIC_ROWS ? NRMAX : 1;
+    const int NRL = STATIC_ROWS ? NRMAX : nr;
+    // Block algebra of the adjoint.  Every array below is indexed by compile-time constants (rows / columns padded
+    // to NRMAX / UMAX with zeros, the triangular factors with an identity) except for the interval index of `a`, so
+    // the compiler keeps them in registers or fixed local slots and issues the independent loads and FMAs together
+    // instead of one dependent local-memory access per operation.
     double Cinv[UMAX * UMAX];
-    for (int j = 0; j < U; ++j) {
-      double e[UMAX];
-      for (int i = 0; i < U; ++i) e[i] = (i == j) ? 1.0 : 0.0;
-      chol_solve_invdiag(LCm, U, e);
-      for (int i = 0; i < U; ++i) Cinv[i * UMAX + j] = e[i];
+    {
+      double LCp[UTRI];
+#pragma unroll
+      for (int i = 0; i < UMAX; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) LCp[tri(i, j)] = (i < U) ? LCm[tri(i, j)] : (i == j ? 1.0 : 0.0);
+#pragma unroll
+      for (int j = 0; j < UMAX; ++j) {
+        double e[UMAX];
+#pragma unroll
+        for (int i = 0; i < UMAX; ++i) e[i] = (i == j) ? 1.0 : 0.0;
+        chol_solve_invdiag_fixed<UMAX>(LCp, UMAX, e);
+#pragma unroll
+        for (int i = 0; i < UMAX; ++i) Cinv[i * UMAX + j] = e[i];
+      }
     }
-    double Lm[NTRI], DiA[NRMAX * UMAX], Om[NRMAX * UMAX], E[NRMAX * NRMAX];
-    for (int i = 0; i < nr * (nr + 1) / 2; ++i) Lm[i] = Lc[i * nta];
-    for (int r = 0; r < nr; ++r)
-      for (int j = 0; j < U; ++j) DiA[r * UMAX + j] = DinvAc[(r * U + j) * nta];
-    for (int r = 0; r < nr; ++r)
-      for (int j = 0; j < U; ++j) {
+    double DiA[NRMAX * UMAX], Om[NRMAX * UMAX], E[NRMAX * NRMAX];
+#pragma unroll UR
+    for (int r = 0; r < NRL; ++r)
+#pragma unroll
+      for (int j = 0; j < UMAX; ++j) DiA[r * UMAX + j] = (r < nr && j < U) ? DinvAc[(r * U + j) * nta] : 0.0;
+#pragma unroll UR
+    for (int r = 0; r < NRL; ++r)
+#pragma unroll
+      for (int j = 0; j < UMAX; ++j) {
         double s = 0.0;
-        for (int l = 0; l < U; ++l) s = fma(DiA[r * UMAX + l], Cinv[l * UMAX + j], s);
+#pragma unroll
+        for (int l = 0; l < UMAX; ++l) s = fma(DiA[r * UMAX + l], Cinv[l * UMAX + j], s);
         Om[r * UMAX + j] = s;
       }
-    for (int c2 = 0; c2 < nr; ++c2) {  // E[:, c2] = D^{-1} e_c2 - Om DiA[c2]^T
-      double e[NRMAX];
-      for (int i = 0; i < nr; ++i) e[i] = (i == c2) ? 1.0 : 0.0;
-      chol_solve_invdiag(Lm, nr, e);
-      for (int r = 0; r < nr; ++r) {
-        double s = e[r];
-        for (int j = 0; j < U; ++j) s = fma(-Om[r * UMAX + j], DiA[c2 * UMAX + j], s);
-        E[r * NRMAX + c2] = s;
+    {
+      double Lm[NTRI];
+#pragma unroll UR
+      for (int r = 0; r < NRL; ++r)
+#pragma unroll
+        for (int c2 = 0; c2 <= r; ++c2) Lm[tri(r, c2)] = (r < nr) ? Lc[tri(r, c2) * nta] : (r == c2 ? 1.0 : 0.0);
+#pragma unroll UR
+      for (int c2 = 0; c2 < NRL; ++c2) {  // E[:, c2] = D^{-1} e_c2 - Om DiA[c2]^T
+        double e[NRMAX];
+#pragma unroll
+        for (int i = 0; i < NRMAX; ++i) e[i] = (i == c2) ? 1.0 : 0.0;
+        if constexpr (STATIC_ROWS) chol_solve_invdiag_fixed<NRMAX>(Lm, NRMAX, e);
+        else chol_solve_invdiag(Lm, nr, e);
+#pragma unroll UR
+        for (int r = 0; r < NRL; ++r) {
+          double s = e[r];
+#pragma unroll
+          for (int j = 0; j < UMAX; ++j) s = fma(-Om[r * UMAX + j], DiA[c2 * UMAX + j], s);
+          E[r * NRMAX + c2] = s;
+        }
       }
     }
     // noise-scale terms (sigma = exp(u_Z) inferred): d/du_Z and d/dn of 1/2 <E, sigma^2 P_y> + <Om[:, Z], sigma n>
     if (d.noisy) {
-      for (int k = 0; k < B.n; ++k) {
-        double gn = 0.0;
-        if (d.noisy == 2 && k < B.ny) {
-          const double nk = q.noise[k * nta];
-          gu[Z] += E[k * NRMAX + k] * sigy * sigy + Om[k * UMAX + Z] * sigy * nk;
-          gn = Om[k * UMAX + Z] * sigy;
-        }
-        gq.noise[k * nta] = gn;
-      }
-    }
-    // a[r][k] = Phi(t_kr, t_k)^T H_r^T  (zero for k > kr)
-    double a[NRMAX * RMAX * X], be[NRMAX * RMAX * X];
-    for (int i = 0; i < NRMAX * RMAX * X; ++i) a[i] = 0.0;  // indexed [(r * RMAX + k) * X + i]
-    for (int r = 0; r < nr; ++r) {
-      const int kr = (r < B.ny) ? r : B.n - 1;
-      double vec[X];
-      if (r < B.ny) {
-        double xe[X];
-        if (!M::OBS_LINEAR) ldcol<X>(xendc + kr * X * nta, nta, xe);
-        M::obs_grad(xe, vec);
-      } else {
 #pragma unroll
-        for (int i = 0; i < X; ++i) vec[i] = (i == r - B.ny) ? 1.0 : 0.0;
-      }
-      for (int k = kr; k >= 0; --k) {
-        if (k < kr) {
-          double Ps[X * X], tv[X];
+      for (int k = 0; k < (RMAX < NRMAX ? RMAX : NRMAX); ++k)
+        if (k < B.n) {
+          double gn = 0.0;
+          if (d.noisy == 2 && k < B.ny) {
+            const double nk = q.noise[k * nta];
+            gu[Z < UMAX ? Z : 0] += E[k * NRMAX + k] * sigy * sigy + Om[k * UMAX + (Z < UMAX ? Z : 0)] * sigy * nk;
+            gn = Om[k * UMAX + (Z < UMAX ? Z : 0)] * sigy;
+          }
+          gq.noise[k * nta] = gn;
+        }
+    }
+    // a[k][r] = Phi(t_kr, t_k)^T H_r^T (zero for k > kr; kr = r for observation rows, the last interval for the
+    // rows of the conditioned full state): one backward recursion shared by all rows
+    double a[RMAX * NRMAX * X];
+    {
+      double vec[NRMAX * X];
+#pragma unroll
+      for (int i = 0; i < NRMAX * X; ++i) vec[i] = 0.0;
+      for (int k = B.n - 1; k >= 0; --k) {
+        if (k < B.n - 1) {
+          double Ps[X * X];
           ldcol<X * X>(Psibc + (k + 1) * X * X * nta, nta, Ps);
-          mtv<X, X>(Ps, vec, tv);
+#pragma unroll UR
+          for (int r = 0; r < NRL; ++r) {
+            double tv[X];
+            mtv<X, X>(Ps, &vec[r * X], tv);
 #pragma unroll
-          for (int i = 0; i < X; ++i) vec[i] = tv[i];
+            for (int i = 0; i < X; ++i) vec[r * X + i] = tv[i];
+          }
+        }
+        if (k < B.ny) {
+          double xe[X], h[X];
+          if (!M::OBS_LINEAR) ldcol<X>(xendc + k * X * nta, nta, xe);
+          M::obs_grad(xe, h);
+#pragma unroll UR
+          for (int r = 0; r < NRL; ++r)
+            if (r == k) {
+#pragma unroll
+              for (int i = 0; i < X; ++i) vec[r * X + i] = h[i];
+            }
+        }
+        if (k == B.n - 1) {
+#pragma unroll UR
+          for (int r = 0; r < NRL; ++r)
+            if (r >= B.ny && r < nr) {
+#pragma unroll
+              for (int i = 0; i < X; ++i) vec[r * X + i] = (i == r - B.ny) ? 1.0 : 0.0;
+            }
         }
 #pragma unroll
-        for (int i = 0; i < X; ++i) a[(r * RMAX + k) * X + i] = vec[i];
+        for (int i = 0; i < NRMAX * X; ++i) a[k * NRMAX * X + i] = vec[i];
       }
     }
-    for (int r = 0; r < nr; ++r)
-      for (int k = 0; k < B.n; ++k)
-#pragma unroll
-        for (int i = 0; i < X; ++i) {
-          double s = 0.0;
-          for (int s2 = 0; s2 < nr; ++s2) s = fma(E[r * NRMAX + s2], a[(s2 * RMAX + k) * X + i], s);
-          be[(r * RMAX + k) * X + i] = s;
-        }
     // u-directions in z-space: omz[r] = dzdu Om[r]
     double omz[NRMAX * Z];
-    for (int r = 0; r < nr; ++r)
+#pragma unroll UR
+    for (int r = 0; r < NRL; ++r)
 #pragma unroll
       for (int m = 0; m < Z; ++m) {
         double s = 0.0;
@@ -335,19 +379,27 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       }
     // per-interval constants M_k, LamZ_k, Yb_k ; tangent recursion ; Az rows (for d2z/du2 term)
     double dprev[NRMAX * X];
-    for (int r = 0; r < nr; ++r) {
-      if (B.ini) {
-        double Ps[X * X], b0[X], t0[M::V0], t1[X], t2[X];
-        ldcol<X * X>(Psibc, nta, Ps);
-        mtv<X, X>(Ps, &be[(r * RMAX + 0) * X], b0);
+#pragma unroll
+    for (int i = 0; i < NRMAX * X; ++i) dprev[i] = 0.0;
+    if (B.ini) {
+      double Ps[X * X];
+      ldcol<X * X>(Psibc, nta, Ps);
+#pragma unroll UR
+      for (int r = 0; r < NRL; ++r) {
+        double be0[X], b0[X], t0[M::V0], t1[X], t2[X];
+#pragma unroll
+        for (int i = 0; i < X; ++i) {
+          double s = 0.0;
+#pragma unroll UR
+          for (int s2 = 0; s2 < NRL; ++s2) s = fma(E[r * NRMAX + s2], a[s2 * X + i], s);
+          be0[i] = s;
+        }
+        mtv<X, X>(Ps, be0, b0);
         mtv<X, M::V0>(dx0_dv0, b0, t0);
         mv<X, M::V0>(dx0_dv0, t0, t1);
         mv<X, Z>(dx0_dz, &omz[r * Z], t2);
 #pragma unroll
         for (int i = 0; i < X; ++i) dprev[r * X + i] = t1[i] + t2[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < X; ++i) dprev[r * X + i] = 0.0;
       }
     }
     double Suz[X * Z], Gam[Z * UMAX];
@@ -355,30 +407,42 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
     (void)gobs;
 #pragma unroll
     for (int i = 0; i < X * Z; ++i) Suz[i] = B.ini ? dx0_dz[i] : 0.0;
+#pragma unroll
     for (int i = 0; i < Z * UMAX; ++i) Gam[i] = 0.0;
     double* Mkc = tp(W.Mk, d.rmax * X * X, t);
     double* LamZc = tp(W.LamZ, d.rmax * Z * X, t);
     double* Ybc = tp(W.Yb, d.rmax * X * X, t);
     for (int k = 0; k < B.n; ++k) {
+      double Ak[NRMAX * X], bek[NRMAX * X];
+#pragma unroll
+      for (int i = 0; i < NRMAX * X; ++i) Ak[i] = a[k * NRMAX * X + i];
+#pragma unroll UR
+      for (int r = 0; r < NRL; ++r)
+#pragma unroll
+        for (int i = 0; i < X; ++i) {
+          double s = 0.0;
+#pragma unroll UR
+          for (int s2 = 0; s2 < NRL; ++s2) s = fma(E[r * NRMAX + s2], Ak[s2 * X + i], s);
+          bek[r * X + i] = s;
+        }
       double Mk[X * X], Lam[Z * X], Yb[X * X];
 #pragma unroll
       for (int i = 0; i < X * X; ++i) { Mk[i] = 0.0; Yb[i] = 0.0; }
 #pragma unroll
       for (int i = 0; i < Z * X; ++i) Lam[i] = 0.0;
-      for (int r = 0; r < nr; ++r) {
-        const double* ar = &a[(r * RMAX + k) * X];
-        const double* br = &be[(r * RMAX + k) * X];
+#pragma unroll UR
+      for (int r = 0; r < NRL; ++r) {
 #pragma unroll
         for (int i = 0; i < X; ++i)
 #pragma unroll
           for (int j = 0; j < X; ++j) {
-            Mk[i * X + j] = fma(br[i], ar[j], Mk[i * X + j]);
-            Yb[i * X + j] = fma(dprev[r * X + i], ar[j], Yb[i * X + j]);
+            Mk[i * X + j] = fma(bek[r * X + i], Ak[r * X + j], Mk[i * X + j]);
+            Yb[i * X + j] = fma(dprev[r * X + i], Ak[r * X + j], Yb[i * X + j]);
           }
 #pragma unroll
         for (int m = 0; m < Z; ++m)
 #pragma unroll
-          for (int j = 0; j < X; ++j) Lam[m * X + j] = fma(omz[r * Z + m], ar[j], Lam[m * X + j]);
+          for (int j = 0; j < X; ++j) Lam[m * X + j] = fma(omz[r * Z + m], Ak[r * X + j], Lam[m * X + j]);
       }
       stcol<X * X>(Mkc + k * X * X * nta, nta, Mk);
       stcol<Z * X>(LamZc + k * Z * X * nta, nta, Lam);
@@ -387,10 +451,11 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       ldcol<X * X>(Psibc + k * X * X * nta, nta, Ps);
       ldcol<X * X>(Qc + k * X * X * nta, nta, Qk);
       ldcol<X * Z>(Ztc + k * X * Z * nta, nta, Zk);
-      for (int r = 0; r < nr; ++r) {
+#pragma unroll UR
+      for (int r = 0; r < NRL; ++r) {
         double t1[X], t2[X], t3[X];
         mv<X, X>(Ps, &dprev[r * X], t1);
-        mv<X, X>(Qk, &be[(r * RMAX + k) * X], t2);
+        mv<X, X>(Qk, &bek[r * X], t2);
         mv<X, Z>(Zk, &omz[r * Z], t3);
 #pragma unroll
         for (int i = 0; i < X; ++i) dprev[r * X + i] = t1[i] + t2[i] + t3[i];
@@ -398,21 +463,27 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       if (!M::OBS_LINEAR && k < B.ny) {
         // tangent of the state at observation time k in the direction that weights row k: the observation
         // curvature enters the adjoint there (d H_k = Hess h(x_k) d x_k)
+#pragma unroll UR
+        for (int r = 0; r < NRL; ++r)
+          if (r == k) {
 #pragma unroll
-        for (int i = 0; i < X; ++i) gobs[k * X + i] = dprev[k * X + i];
+            for (int i = 0; i < X; ++i) gobs[k * X + i] = dprev[r * X + i];
+          }
       }
       double ts[X * Z];
       mm<X, Z, X>(Ps, Suz, ts);
 #pragma unroll
       for (int i = 0; i < X * Z; ++i) Suz[i] = ts[i] + Zk[i];
-      for (int r = 0; r < nr; ++r) {
+#pragma unroll UR
+      for (int r = 0; r < NRL; ++r) {
         const int kr = (r < B.ny) ? r : B.n - 1;
-        if (kr != k) continue;
+        if (kr != k || r >= nr) continue;
         double az[Z];
-        mtv<X, Z>(Suz, &a[(r * RMAX + k) * X], az);  // a[r][kr] = H_r^T
+        mtv<X, Z>(Suz, &Ak[r * X], az);  // a[kr][r] = H_r^T
 #pragma unroll
         for (int m = 0; m < Z; ++m)
-          for (int j = 0; j < U; ++j) Gam[m * UMAX + j] = fma(az[m], Om[r * UMAX + j], Gam[m * UMAX + j]);
+#pragma unroll
+          for (int j = 0; j < UMAX; ++j) Gam[m * UMAX + j] = fma(az[m], Om[r * UMAX + j], Gam[m * UMAX + j]);
       }
     }
     PH(19);
@@ -1129,7 +1200,7 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
                   double mom_coef, double ctol, double ptol, double dtol, int max_iters) {
   const Tid t = thread_id(d);
   MMD_SMEM_SETUP
-  constexpr int X = M::X, V = M::V, Z = M::Z, XV = M::X * M::V;
+  constexpr int X = M::X, Z = M::Z, XV = M::X * M::V;
   constexpr int NTRI = NRMAX * (NRMAX + 1) / 2;
   constexpr int UTRI = UMAX * (UMAX + 1) / 2;
   const int U = d.U, nta = t.nta, cpb = t.cpb;

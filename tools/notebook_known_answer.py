@@ -89,6 +89,7 @@ def main():
     acc, fail = [], []
     acc_chain = np.zeros(n)
     bits = np.zeros(4)
+    t_main = time.time()
     for k in range(n_main):
         bc.hmc_transition(dt, L, 20200710, it)
         it += 1
@@ -103,6 +104,7 @@ def main():
         draws[:, k, :4] = z
         draws[:, k, 4:] = m.generate_x_0(z, q[:, 4:6])
     wall = time.time() - t0
+    main_wall = time.time() - t_main
     out = {"chains": n, "burn_in": log, "main_transitions": n_main, "leapfrog_per_transition": L, "dt": dt,
            "solver": "newton" if solver else "quasi_newton", "accept_stat": float(np.mean(acc)),
            "integrator_error_rate": float(np.mean(fail)),
@@ -122,6 +124,14 @@ def main():
                            "notebook_mean": ref_mean, "notebook_sd": ref_sd, "notebook_mcse": ref_mcse,
                            "z": round(float(zscore), 2)}
     out["max_abs_z"] = round(worst, 2)
+    # effective samples per second of the main phase (wall clock incl. the per-transition trace read-back):
+    # rank-normalised bulk ESS pooled over chains, minimum over the traced variables
+    ess_min = min(v["ess_bulk"] for v in out["vars"].values())
+    out["ess"] = {"min_bulk_ess": ess_min, "main_phase_wall_s": round(main_wall, 2),
+                  "ess_per_s": round(ess_min / main_wall, 1),
+                  "ess_per_chain_leapfrog_step": ess_min / (n * n_main * L),
+                  "chain_leapfrog_steps_per_s": round(n * n_main * L / main_wall, 0),
+                  "notebook": "2 chains x 750 NUTS transitions in 591 s on the authors' CPU (cell 43 output)"}
     out["stuck_chain_fraction"] = float(np.mean(acc_chain == 0))
     out["init_u_scale"] = u_scale
     out["restarted_chains_during_burn_in"] = int(n_restarted)
