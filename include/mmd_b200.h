@@ -67,6 +67,10 @@ int mmd_n_chains(mmd_handle h);
 /* Upload positions / momenta / conditioned states; p may be NULL (left unchanged).  Invalidates
  * the cached linearisation like a Mici ChainState variable assignment does. */
 int mmd_set_state(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition);
+/* The same without waiting for the copies: the host buffers must be page-locked and must stay untouched until the
+ * next mmd_synchronize (or any blocking call) on this handle.  Lets a host thread keep several handles busy, e.g.
+ * upload the next batch of chains on one handle while another handle computes (bench.py's end-to-end pipeline). */
+int mmd_set_state_async(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition);
 int mmd_get_state(mmd_handle h, double* q, double* p, double* x_obs_seq);
 int mmd_set_momentum(mmd_handle h, const double* p);
 /* Same with DEVICE pointers in the reference layout ([n_chains][dim_q], [n_chains][T][dim_x]): the

@@ -95,13 +95,23 @@ class BatchedChains:
     def num_constraints(self, partition=None):
         return self._L.mmd_num_constraints(self._h, self.partition if partition is None else partition)
 
-    def set_state(self, q, x_obs_seq, partition=0, p=None):
-        q = _c(q)
-        x = _c(x_obs_seq)
+    def set_state(self, q, x_obs_seq, partition=0, p=None, blocking=True):
+        """Upload positions, conditioned states and (optionally) momenta.  blocking=False returns before the copies
+        have finished: the arrays must then be page-locked, C-contiguous float64 and stay untouched until
+        `synchronize()` (or any call that reads results back); it lets one host thread overlap the upload for one
+        BatchedChains object with the computation of another."""
+        if blocking:
+            q, x = _c(q), _c(x_obs_seq)
+            pp = None if p is None else _c(p)
+        else:
+            q, x, pp = q, x_obs_seq, p
+            for a in (q, x) + (() if pp is None else (pp,)):
+                if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
+                    raise ValueError("set_state(blocking=False) needs C-contiguous float64 arrays (no hidden copies)")
         assert q.shape == (self.n_chains, self.dim_q), q.shape
         assert x.shape[0] == self.n_chains and x.size == self.n_chains * x.shape[1] * x.shape[2]
-        pp = None if p is None else _c(p)
-        check(self._L.mmd_set_state(self._h, _dp(q), None if pp is None else _dp(pp), _dp(x), int(partition)))
+        fn = self._L.mmd_set_state if blocking else self._L.mmd_set_state_async
+        check(fn(self._h, _dp(q), None if pp is None else _dp(pp), _dp(x), int(partition)))
         self._dim_x = x.shape[2]
 
     def init_linear_interpolation(self, u, v_0, x_obs_seq, partition=0):

@@ -276,7 +276,8 @@ static int set_state_dev_impl(mmd_handle h, const double* q_dev, const double* p
   return 0;
 }
 
-int mmd_set_state(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition) {
+static int set_state_host(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition,
+                          bool blocking) {
   const size_t nq = (size_t)h->d.n_chains * h->d.dim_q;
   if (q) { if (h2d_stage(h, q, h->stage, nq)) return -2; }
   if (set_state_dev_impl(h, q ? h->stage : nullptr, nullptr, nullptr, partition)) return -2;
@@ -289,8 +290,16 @@ int mmd_set_state(mmd_handle h, const double* q, const double* p, const double* 
     if (h2d_stage(h, x_obs_seq, h->stage, (size_t)h->d.n_chains * h->d.T * h->X)) return -2;
     if (pack_chain(h, h->d.T * h->X, h->stage, h->W.xobs)) return -2;
   }
-  CK(cudaStreamSynchronize(h->stream));
+  if (blocking) CK(cudaStreamSynchronize(h->stream));
   return 0;
+}
+
+int mmd_set_state(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition) {
+  return set_state_host(h, q, p, x_obs_seq, partition, true);
+}
+
+int mmd_set_state_async(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition) {
+  return set_state_host(h, q, p, x_obs_seq, partition, false);
 }
 
 int mmd_set_state_dev(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_dev, int partition) {

@@ -28,6 +28,9 @@
 #ifndef MMD_POINTWISE_L2_PREFETCH
 #define MMD_POINTWISE_L2_PREFETCH 8   // look-ahead (steps) of the HBM -> L2 prefetch in the pointwise passes (0 = off)
 #endif
+#ifndef MMD_POINT_L2_PREFETCH
+#define MMD_POINT_L2_PREFETCH 0   // look-ahead (steps) of the HBM -> L2 prefetch in the linearisation sweeps (0 = off)
+#endif
 #ifndef MMD_L2_PREFETCH_STEPS
 #define MMD_L2_PREFETCH_STEPS 8   // additional look-ahead of the HBM -> L2 prefetch (0 = off)
 #endif
@@ -385,7 +388,9 @@ MMD_HD int block_of_obs(const Dims& d, int part, int o) {
 // cross-block (same chain) reductions through shared memory.  All threads of the CTA must call.
 // vals[0..NSUM) are replaced by the sum over block slots (deterministic ascending order),
 // vals[NSUM..NSUM+NMAX) by the NaN-propagating maximum of non-negative values.
-template <int NSUM, int NMAX>
+// TAIL_SYNC = false leaves out the trailing barrier: only where the caller's next CTA-wide barrier comes before
+// anything writes the scratch again.
+template <int NSUM, int NMAX, bool TAIL_SYNC = true>
 MMD_D void block_reduce(double* vals, double* smem, const Tid& t) {
   constexpr int NV = NSUM + NMAX;
   const int NT = t.nslot * t.cpb;
@@ -406,7 +411,7 @@ MMD_D void block_reduce(double* vals, double* smem, const Tid& t) {
     }
     vals[i] = s;
   }
-  __syncthreads();
+  if (TAIL_SYNC) __syncthreads();
 }
 #endif
 

@@ -88,6 +88,9 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       const double* vp = q.body + k * d.S * V * nta;
       double* xk = xsc + k * d.S * X * nta;
       for (int tt = 0; tt < d.S; ++tt) {
+#if MMD_POINT_L2_PREFETCH > 0
+        if (k * d.S + tt + MMD_POINT_L2_PREFETCH < B.n * d.S) prefetch_l2(vp + (tt + MMD_POINT_L2_PREFETCH) * V * nta);
+#endif
         strec<X>(xk + tt * X * nta, x);
         double v[V], xn[X];
         ldrec<V>(vp + tt * V * nta, v);
@@ -515,6 +518,13 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       PH(22);
       for (int tt = 0; tt < d.S; ++tt) {
         strec<X * X>(Yk + tt * X * X * nta, Y);
+#if MMD_POINT_L2_PREFETCH > 0
+        if (tt + MMD_POINT_L2_PREFETCH < d.S) {
+          prefetch_l2(xk + (tt + MMD_POINT_L2_PREFETCH) * X * nta);
+          prefetch_l2(vp + (tt + MMD_POINT_L2_PREFETCH) * V * nta);
+          prefetch_l2(Kk + (tt + MMD_POINT_L2_PREFETCH) * XV * nta);
+        }
+#endif
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], KM[V * X], Yn[X * X];
         ldrec<X>(xk + tt * X * nta, xt);
         ldrec<V>(vp + tt * V * nta, v);
@@ -535,6 +545,14 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       for (int i = 0; i < X * X; ++i) Psi[i] = (i % (X + 1) == 0) ? 1.0 : 0.0;
       for (int tt = d.S - 1; tt >= 0; --tt) {
         double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], Yt[X * X];
+#if MMD_POINT_L2_PREFETCH > 0
+        if (k > 0 && d.S - 1 - tt < MMD_POINT_L2_PREFETCH) {
+          const int sp = (d.S - 1 - tt) - d.S;   // step of interval k - 1, relative to this interval's base
+          prefetch_l2(xk + sp * X * nta);
+          prefetch_l2(vp + sp * V * nta);
+          prefetch_l2(Kk + sp * XV * nta);
+        }
+#endif
         ldrec<X>(xk + tt * X * nta, xt);
         ldrec<V>(vp + tt * V * nta, v);
         ldrec<X * X>(Yk + tt * X * X * nta, Yt);
@@ -1255,9 +1273,6 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
   ChainPar<M, UMAX> Pkeep;
   PH_T0
   while (true) {
-    if (__syncthreads_and(done ? 1 : 0)) break;
-    PH(8);
-    PH_ADD(12, 1);
     const bool work = in_blk && !done;
     double sres[UMAX], err = 0.0;
     if (work) {
@@ -1303,14 +1318,17 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
       err = e;
     }
     // the prefetch ring of the sweep and the reduction scratch share shared memory: every thread must have
-    // left its sweep before any thread starts the cross-block reduction
-    __syncthreads();
+    // left its sweep before any thread starts the cross-block reduction.  The same barrier ends the loop once
+    // every chain of the tile is done (their threads skipped the sweep).
+    if (__syncthreads_and(done ? 1 : 0)) break;
     PH(9);
+    PH_ADD(12, 1);
     if (NEWTON)
       newton_solve_block<M, NRMAX, RMAXP, UMAX>(d, B, work, Pkeep, sig_lin, dx0_dv0, qw, Kc, Psibc, xendc, Ac, alph,
                                                 sm_l, W, rr, sres, &err, sm_red, t, NT);
     else
-      inv_gram_block<M, NRMAX, UMAX>(d, B, work, Ac, Lc, DinvAc, LCc, rr, sres, &err, sm_red, t);
+      // (no trailing barrier: the next write to the scratch comes after the __syncthreads_or below)
+      inv_gram_block<M, NRMAX, UMAX, false>(d, B, work, Ac, Lc, DinvAc, LCc, rr, sres, &err, sm_red, t);
     // Convergence test of the reference (:1047-1055): |c| < constraint_tol AND |delta_q|_inf < position_tol for THIS
     // iteration's update delta_q = J_lin^T (increment of the multipliers).  The exact norm needs a pass over K; a
     // cheap upper bound (per-interval row maxima kap of K from the linearisation, exact for the head / noise

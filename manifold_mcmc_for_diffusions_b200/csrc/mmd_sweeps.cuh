@@ -318,7 +318,7 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
 // maximum (the solver's |c|_inf).  Everything is unrolled over NRMAX x UMAX with guards so that the
 // factor loads (L, A, D^{-1}A: thread-private, L2-resident) are issued up front, not one per
 // dependent multiply-add.
-template <class M, int NRMAX, int UMAX>
+template <class M, int NRMAX, int UMAX, bool TAIL_SYNC = true>
 MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const double* __restrict__ Ac,
                           const double* __restrict__ Lc, const double* __restrict__ DinvAc,
                           const double* __restrict__ LCc, double* r, double* s_out, double* extra_max,
@@ -359,7 +359,7 @@ MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const doubl
       }
     }
   }
-  block_reduce<UMAX, 1>(g, smem_red, t);
+  block_reduce<UMAX, 1, TAIL_SYNC>(g, smem_red, t);
   if (extra_max) *extra_max = g[UMAX];
   double LCm[UMAX * (UMAX + 1) / 2];
 #pragma unroll
