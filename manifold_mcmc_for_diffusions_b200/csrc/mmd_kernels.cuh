@@ -31,6 +31,10 @@
 #ifndef MMD_POINT_L2_PREFETCH
 #define MMD_POINT_L2_PREFETCH 0   // look-ahead (steps) of the HBM -> L2 prefetch in the linearisation sweeps (0 = off)
 #endif
+// compiler-only barrier: values read from shared memory are re-read after it instead of being kept in registers
+#ifndef MMD_SMEM_RELOAD
+#define MMD_SMEM_RELOAD asm volatile("" ::: "memory")
+#endif
 #ifndef MMD_L2_PREFETCH_STEPS
 #define MMD_L2_PREFETCH_STEPS 8   // additional look-ahead of the HBM -> L2 prefetch (0 = off)
 #endif

@@ -67,6 +67,17 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
   const bool has_blk = t.slot < d.nb[part];
   Blk B;
   if (has_blk) B = get_block<M>(d, part, t.slot);
+  // The model coefficients (22 doubles for FHN) and the per-interval constants of the adjoint would have to live in
+  // registers across the sweep loops -- they do not fit next to the sweep's own state in 96 registers and end up
+  // in local memory.  They are kept in shared memory instead (one coefficient block per chain of the tile behind
+  // the per-thread regions; the per-thread constants in the rows the projection solves use for residuals and
+  // multipliers) and read where they are used; MMD_SMEM_RELOAD keeps the compiler from hoisting those loads out
+  // of the loops (which would put them back into registers / local memory).
+  static_assert(X * X + Z * X + Z <= 2 * NRMAX, "per-interval constants must fit the residual + multiplier rows");
+  typename M::Coef* const sm_coef = reinterpret_cast<typename M::Coef*>(smem + SmemPlan<M, NRMAX, UMAX>::PER_THREAD * NT);
+  if (t.slot == 0) sm_coef[t.cl] = P.C;
+  __syncthreads();
+  const typename M::Coef& CC = sm_coef[t.cl];
 
   double red[UTRI + 1];
 #pragma unroll
@@ -88,56 +99,78 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       const double* vp = q.body + k * d.S * V * nta;
       double* xk = xsc + k * d.S * X * nta;
       for (int tt = 0; tt < d.S; ++tt) {
+        MMD_SMEM_RELOAD;
 #if MMD_POINT_L2_PREFETCH > 0
         if (k * d.S + tt + MMD_POINT_L2_PREFETCH < B.n * d.S) prefetch_l2(vp + (tt + MMD_POINT_L2_PREFETCH) * V * nta);
 #endif
         strec<X>(xk + tt * X * nta, x);
         double v[V], xn[X];
         ldrec<V>(vp + tt * V * nta, v);
-        M::step(P.C, x, v, xn);
+        M::step(CC, x, v, xn);
 #pragma unroll
         for (int i = 0; i < X; ++i) x[i] = xn[i];
       }
       if (!M::OBS_LINEAR) stcol<X>(xendc + k * X * nta, nta, x);
-      double Psi[X * X], Qk[X * X], Zk[X * Z], kap[X];
+      double Psi[X * X], Qk[X * X], kap[X];
 #pragma unroll
       for (int i = 0; i < X * X; ++i) { Psi[i] = (i % (X + 1) == 0) ? 1.0 : 0.0; Qk[i] = 0.0; }
+      // Z_k = sum_t Psi_{t+1} G_t accumulates in this thread's shared-memory rows (8 doubles less to keep live)
 #pragma unroll
-      for (int i = 0; i < X * Z; ++i) Zk[i] = 0.0;
+      for (int i = 0; i < X * Z; ++i) sm_c[i * NT] = 0.0;
 #pragma unroll
       for (int i = 0; i < X; ++i) kap[i] = 0.0;
       double* Kk = Kc + k * d.S * XV * nta;
       for (int tt = d.S - 1; tt >= 0; --tt) {
-        double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], tmp[X * X];
+        MMD_SMEM_RELOAD;
+        // one Jacobian at a time (little live at once): K_t, then Z_k, then Psi
+        double xt[X], v[V];
         ldrec<X>(xk + tt * X * nta, xt);
         ldrec<V>(vp + tt * V * nta, v);
-        M::jac_x(P.C, xt, v, F);
-        M::jac_v(P.C, xt, v, Bm);
-        M::jac_z(P.C, xt, v, G);
-        mm<X, V, X>(Psi, Bm, Kt);
-        strec<XV>(Kk + tt * XV * nta, Kt);
-        // Qk += Kt Kt^T ; Zk += Psi G ; Psi = Psi F ; kap = max |Kt| per row
+        {
+          double Bm[X * V], Kt[X * V];
+          M::jac_v(CC, xt, v, Bm);
+          mm<X, V, X>(Psi, Bm, Kt);
+          strec<XV>(Kk + tt * XV * nta, Kt);
+          // Qk += Kt Kt^T ; kap = max |Kt| per row
 #pragma unroll
-        for (int i = 0; i < X; ++i)
+          for (int i = 0; i < X; ++i)
 #pragma unroll
-          for (int j = 0; j < V; ++j) kap[i] = fmax(kap[i], fabs(Kt[i * V + j]));
+            for (int j = 0; j < V; ++j) kap[i] = fmax(kap[i], fabs(Kt[i * V + j]));
 #pragma unroll
-        for (int i = 0; i < X; ++i)
+          for (int i = 0; i < X; ++i)
 #pragma unroll
-          for (int j = 0; j < X; ++j) {
-            double s = Qk[i * X + j];
+            for (int j = 0; j < X; ++j) {
+              double s2 = Qk[i * X + j];
 #pragma unroll
-            for (int l = 0; l < V; ++l) s = fma(Kt[i * V + l], Kt[j * V + l], s);
-            Qk[i * X + j] = s;
-          }
-        mm_acc<X, Z, X>(Psi, G, Zk);
-        mm<X, X, X>(Psi, F, tmp);
+              for (int l = 0; l < V; ++l) s2 = fma(Kt[i * V + l], Kt[j * V + l], s2);
+              Qk[i * X + j] = s2;
+            }
+        }
+        {
+          double G[X * Z], Zk[X * Z];
+          M::jac_z(CC, xt, v, G);
 #pragma unroll
-        for (int i = 0; i < X * X; ++i) Psi[i] = tmp[i];
+          for (int i = 0; i < X * Z; ++i) Zk[i] = sm_c[i * NT];
+          mm_acc<X, Z, X>(Psi, G, Zk);
+#pragma unroll
+          for (int i = 0; i < X * Z; ++i) sm_c[i * NT] = Zk[i];
+        }
+        {
+          double F[X * X], tmp[X * X];
+          M::jac_x(CC, xt, v, F);
+          mm<X, X, X>(Psi, F, tmp);
+#pragma unroll
+          for (int i = 0; i < X * X; ++i) Psi[i] = tmp[i];
+        }
       }
       stcol<X * X>(Psibc + k * X * X * nta, nta, Psi);
       stcol<X * X>(Qc + k * X * X * nta, nta, Qk);
-      stcol<X * Z>(Ztc + k * X * Z * nta, nta, Zk);
+      {
+        double Zk[X * Z];
+#pragma unroll
+        for (int i = 0; i < X * Z; ++i) Zk[i] = sm_c[i * NT];
+        stcol<X * Z>(Ztc + k * X * Z * nta, nta, Zk);
+      }
       stcol<X>(kapc + k * X * nta, nta, kap);
     }
 #pragma unroll
@@ -494,8 +527,15 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
     double gam[X], gz[Z];
 #pragma unroll
     for (int i = 0; i < X; ++i) gam[i] = 0.0;
+    // the parameter gradient accumulates in shared memory during the sweeps (rows behind M_k and Lambda_k)
+    constexpr int GZ0 = X * X + Z * X;
+    // contraction weights of one step: (X+V+Z)*X doubles per thread in the scratch region, thread stride odd in
+    // doubles (at most 2-way bank conflicts); only when they fit (FHN: 16 + 1 <= 18)
+    constexpr int NTH = (X + V + Z) * X;
+    constexpr bool TH_SMEM = NTH + 1 <= SmemPlan<M, NRMAX, UMAX>::NSCR;
+    double* const sm_th = smem + t.tid * (NTH + 1);
 #pragma unroll
-    for (int i = 0; i < Z; ++i) gz[i] = 0.0;
+    for (int i = 0; i < Z; ++i) sm_c[(GZ0 + i) * NT] = 0.0;
     double* Ywc = tpr<X * X>(W.Yw, d.rmax * d.S * X * X, t);
     for (int k = B.n - 1; k >= 0; --k) {
       const double* vp = q.body + k * d.S * V * nta;
@@ -503,9 +543,16 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       const double* Kk = Kc + k * d.S * XV * nta;
       double* Yk = Ywc + k * d.S * X * X * nta;
       double* gk = gq.body + k * d.S * V * nta;
-      double Mk[X * X], Lam[Z * X], Y[X * X];
-      ldcol<X * X>(Mkc + k * X * X * nta, nta, Mk);
-      ldcol<Z * X>(LamZc + k * Z * X * nta, nta, Lam);
+      double Y[X * X];
+      {
+        double Mk[X * X], Lam[Z * X];
+        ldcol<X * X>(Mkc + k * X * X * nta, nta, Mk);
+        ldcol<Z * X>(LamZc + k * Z * X * nta, nta, Lam);
+#pragma unroll
+        for (int i = 0; i < X * X; ++i) sm_c[i * NT] = Mk[i];
+#pragma unroll
+        for (int i = 0; i < Z * X; ++i) sm_c[(X * X + i) * NT] = Lam[i];
+      }
       ldcol<X * X>(Ybc + k * X * X * nta, nta, Y);
       if (!M::OBS_LINEAR && k < B.ny) {
         // curvature of the observation function: adjoint source at the observation time t_k
@@ -517,6 +564,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       }
       PH(22);
       for (int tt = 0; tt < d.S; ++tt) {
+        MMD_SMEM_RELOAD;
         strec<X * X>(Yk + tt * X * X * nta, Y);
 #if MMD_POINT_L2_PREFETCH > 0
         if (tt + MMD_POINT_L2_PREFETCH < d.S) {
@@ -525,17 +573,31 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
           prefetch_l2(Kk + (tt + MMD_POINT_L2_PREFETCH) * XV * nta);
         }
 #endif
-        double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], KM[V * X], Yn[X * X];
+        // Y <- F Y + B (K^T M) + G Lam, one Jacobian at a time
+        double xt[X], v[V], Yn[X * X];
         ldrec<X>(xk + tt * X * nta, xt);
         ldrec<V>(vp + tt * V * nta, v);
-        ldrec<XV>(Kk + tt * XV * nta, Kt);
-        M::jac_x(P.C, xt, v, F);
-        M::jac_v(P.C, xt, v, Bm);
-        M::jac_z(P.C, xt, v, G);
-        mm<X, X, X>(F, Y, Yn);
-        mtm<V, X, X>(Kt, Mk, KM);
-        mm_acc<X, X, V>(Bm, KM, Yn);
-        mm_acc<X, X, Z>(G, Lam, Yn);
+        {
+          double F[X * X];
+          M::jac_x(CC, xt, v, F);
+          mm<X, X, X>(F, Y, Yn);
+        }
+        {
+          double Bm[X * V], Kt[X * V], KM[V * X], Mk[X * X];
+          ldrec<XV>(Kk + tt * XV * nta, Kt);
+#pragma unroll
+          for (int i = 0; i < X * X; ++i) Mk[i] = sm_c[i * NT];
+          M::jac_v(CC, xt, v, Bm);
+          mtm<V, X, X>(Kt, Mk, KM);
+          mm_acc<X, X, V>(Bm, KM, Yn);
+        }
+        {
+          double G[X * Z], Lam[Z * X];
+#pragma unroll
+          for (int i = 0; i < Z * X; ++i) Lam[i] = sm_c[(X * X + i) * NT];
+          M::jac_z(CC, xt, v, G);
+          mm_acc<X, X, Z>(G, Lam, Yn);
+        }
 #pragma unroll
         for (int i = 0; i < X * X; ++i) Y[i] = Yn[i];
       }
@@ -544,7 +606,11 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #pragma unroll
       for (int i = 0; i < X * X; ++i) Psi[i] = (i % (X + 1) == 0) ? 1.0 : 0.0;
       for (int tt = d.S - 1; tt >= 0; --tt) {
-        double xt[X], v[V], F[X * X], Bm[X * V], G[X * Z], Kt[X * V], Yt[X * X];
+        MMD_SMEM_RELOAD;
+        // staged so that little is live at once: (1) the contraction weights Th = [Y Psi ; K^T M Psi ; Lam Psi] go to
+        // this thread's shared-memory scratch, (2) the Hessian contraction reads them from there, (3) the
+        // first-order terms follow one Jacobian at a time
+        double xt[X], v[V], Bm[X * V], g[X + V + Z];
 #if MMD_POINT_L2_PREFETCH > 0
         if (k > 0 && d.S - 1 - tt < MMD_POINT_L2_PREFETCH) {
           const int sp = (d.S - 1 - tt) - d.S;   // step of interval k - 1, relative to this interval's base
@@ -555,35 +621,57 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #endif
         ldrec<X>(xk + tt * X * nta, xt);
         ldrec<V>(vp + tt * V * nta, v);
-        ldrec<X * X>(Yk + tt * X * X * nta, Yt);
-        M::jac_x(P.C, xt, v, F);
-        M::jac_v(P.C, xt, v, Bm);
-        M::jac_z(P.C, xt, v, G);
-        mm<X, V, X>(Psi, Bm, Kt);
-        double Th[(X + V + Z) * X], MP[X * X], g[X + V + Z];
-        mm<X, X, X>(Yt, Psi, &Th[0]);
-        mm<X, X, X>(Mk, Psi, MP);
-        mtm<V, X, X>(Kt, MP, &Th[X * X]);
-        mm<Z, X, X>(Lam, Psi, &Th[(X + V) * X]);
-        M::hess_contract(P.C, xt, v, Th, g);
-        double gv[V], gn[X], tz[Z];
-        mtv<X, V>(Bm, gam, gv);
+        M::jac_v(CC, xt, v, Bm);
+        {
+          double Th[NTH], MP[X * X], Kt[X * V], Yt[X * X], Mk[X * X], Lam[Z * X];
+          ldrec<X * X>(Yk + tt * X * X * nta, Yt);
 #pragma unroll
-        for (int j = 0; j < V; ++j) gv[j] += g[X + j];
-        strec<V>(gk + tt * V * nta, gv);
-        mtv<X, Z>(G, gam, tz);
+          for (int i = 0; i < X * X; ++i) Mk[i] = sm_c[i * NT];
 #pragma unroll
-        for (int m = 0; m < Z; ++m) gz[m] += tz[m] + g[X + V + m];
-        mtv<X, X>(F, gam, gn);
+          for (int i = 0; i < Z * X; ++i) Lam[i] = sm_c[(X * X + i) * NT];
+          mm<X, V, X>(Psi, Bm, Kt);
+          mm<X, X, X>(Yt, Psi, &Th[0]);
+          mm<X, X, X>(Mk, Psi, MP);
+          mtm<V, X, X>(Kt, MP, &Th[X * X]);
+          mm<Z, X, X>(Lam, Psi, &Th[(X + V) * X]);
+          if constexpr (TH_SMEM) {
 #pragma unroll
-        for (int i = 0; i < X; ++i) gam[i] = gn[i] + g[i];
-        double tmp[X * X];
-        mm<X, X, X>(Psi, F, tmp);
+            for (int i = 0; i < NTH; ++i) sm_th[i] = Th[i];
+            MMD_SMEM_RELOAD;
+            M::hess_contract(CC, xt, v, sm_th, g);
+          } else {
+            M::hess_contract(CC, xt, v, Th, g);
+          }
+        }
+        {
+          double gv[V];
+          mtv<X, V>(Bm, gam, gv);
 #pragma unroll
-        for (int i = 0; i < X * X; ++i) Psi[i] = tmp[i];
+          for (int j = 0; j < V; ++j) gv[j] += g[X + j];
+          strec<V>(gk + tt * V * nta, gv);
+        }
+        {
+          double G[X * Z], tz[Z];
+          M::jac_z(CC, xt, v, G);
+          mtv<X, Z>(G, gam, tz);
+#pragma unroll
+          for (int m = 0; m < Z; ++m) sm_c[(GZ0 + m) * NT] += tz[m] + g[X + V + m];
+        }
+        {
+          double F[X * X], gn[X], tmp[X * X];
+          M::jac_x(CC, xt, v, F);
+          mtv<X, X>(F, gam, gn);
+#pragma unroll
+          for (int i = 0; i < X; ++i) gam[i] = gn[i] + g[i];
+          mm<X, X, X>(Psi, F, tmp);
+#pragma unroll
+          for (int i = 0; i < X * X; ++i) Psi[i] = tmp[i];
+        }
       }
       PH(21);
     }
+#pragma unroll
+    for (int i = 0; i < Z; ++i) gz[i] = sm_c[(GZ0 + i) * NT];
     double gv0[M::V0];
     if (B.ini) {
       double tz[Z];
@@ -608,6 +696,9 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
     }
   }
   (void)xlast;
+  // the sweeps use the scratch region thread by thread (contraction weights): every thread must have left them
+  // before the reduction writes it column by column
+  __syncthreads();
   block_reduce<UMAX, 0>(gu, sm_red, t);
   PH(23);
   if (t.slot == 0 && !skip)
@@ -1479,7 +1570,11 @@ static __global__ void k_commit(Dims d, Slots S, Work W, double rev_tol, long lo
 // (the per-chain iteration count is long-tailed: mean ~8, 1 % > 30, max_iters = 50).
 // Step order: Mici ConstrainedLeapfrogIntegrator._step = A(dt/2) B(dt) A(dt/2), SURVEY.md 3.3.
 template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB, bool NEWTON>
+#ifdef MMD_LEAPFROG_MAXNREG
+__global__ void __maxnreg__(MMD_LEAPFROG_MAXNREG)
+#else
 __global__ void __launch_bounds__(NTMAX, MINB)
+#endif
 k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, double dt, double ctol, double ptol,
            double dtol, int max_iters, double rev_tol, long long* __restrict__ n_ok, int n_steps,
            int reset_status) {

@@ -10,7 +10,11 @@ namespace {
 // kernel launchers for one model / block-size instantiation
 template <class Mdl, int NRMAX, int RMAX>
 struct Ops {
-  static size_t smem(int nt) { return (size_t)SmemPlan<Mdl, NRMAX, UMAX>::PER_THREAD * nt * sizeof(double); }
+  // per-thread regions + one model-coefficient block per chain of the tile (used by the linearisation sweeps)
+  static size_t smem(mmd_handle h, int nt) {
+    return (size_t)SmemPlan<Mdl, NRMAX, UMAX>::PER_THREAD * nt * sizeof(double) +
+           (size_t)h->d.cpb * sizeof(typename Mdl::Coef);
+  }
   static int nt(mmd_handle h) { return h->d.nb[h->partition] * h->d.cpb; }
   template <class Kern>
   static int prep(Kern kern, size_t bytes) {
@@ -21,8 +25,8 @@ struct Ops {
     ProfScope ps(h, KID_POINT);
     auto kern = k_point<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
     const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, which, with_grad);
+    if (prep(kern, smem(h, n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(h, n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, which, with_grad);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -30,8 +34,8 @@ struct Ops {
   static int constr(mmd_handle h) {
     auto kern = k_constr<Mdl, NRMAX, UMAX, NTMAX, MMD_MINB>;
     const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, h->tpbuf);
+    if (prep(kern, smem(h, n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(h, n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, h->tpbuf);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -40,8 +44,8 @@ struct Ops {
     ProfScope ps(h, KID_PROJECT);
     auto kern = k_project<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB>;
     const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->partition, lin, src, dst, hh, qcoef, fl);
+    if (prep(kern, smem(h, n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(h, n), h->stream>>>(h->d, h->S, h->W, h->partition, lin, src, dst, hh, qcoef, fl);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -51,8 +55,8 @@ struct Ops {
     ProfScope ps(h, KID_QN);
     auto kern = k_qn<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB, NEWTON>;
     const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, mode, mom_coef,
+    if (prep(kern, smem(h, n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(h, n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, mode, mom_coef,
                                                    o->constraint_tol, o->position_tol, o->divergence_tol,
                                                    o->max_iters);
     h->launches++;
@@ -67,8 +71,8 @@ struct Ops {
     ProfScope ps(h, KID_LEAPFROG);
     auto kern = k_leapfrog<Mdl, NRMAX, RMAX, UMAX, NTMAX, MMD_MINB, NEWTON>;
     const int n = nt(h);
-    if (prep(kern, smem(n))) return -2;
-    kern<<<h->d.n_tiles, n, smem(n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, dt,
+    if (prep(kern, smem(h, n))) return -2;
+    kern<<<h->d.n_tiles, n, smem(h, n), h->stream>>>(h->d, h->S, h->W, h->y, h->partition, dt,
                                                    o->constraint_tol, o->position_tol, o->divergence_tol,
                                                    o->max_iters, o->reverse_check_tol, h->n_ok, n_steps,
                                                    reset_status);
