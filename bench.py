@@ -81,14 +81,16 @@ class ClockSampler(threading.Thread):
 
 
 # work model (SURVEY.md 8d / DESIGN.md): bytes one quasi-Newton sweep must read per chain
-def leapfrog_bytes_per_chain_step(qn_iters):
+def leapfrog_bytes_per_chain_step(qn_iters, newton=False):
     """Algorithmic HBM bytes of one constrained leapfrog step of one chain: doubles
     per SDE time step summed over the phases (X=V=2: a K_t record is 4 doubles, v_t / p_t / x_t records 2)."""
     # momentum projections (pass 1: J p, pass 2: p - J^T lambda), h1 kick and h2_flow fused in:
     project = (4 + 2 + 2 + 2 + 2) + (4 + 2 + 2 + 2 + 2)   # A(dt/2) at the old point + flow -> qw, pw
     project += (4 + 2) + (4 + 2 + 2 + 2 + 2)              # tangent projection at the new point + back flow
     project += (4 + 2 + 2 + 2 + 2) + (4 + 2 + 2)          # A(dt/2) at the new point
-    qn = 6 * qn_iters                                      # one sweep per iteration: K_t + work position
+    # quasi-Newton: one sweep per iteration (K_t + work position); Newton: forward sweep that also stores the
+    # trajectory (4 + 2 + 2) and a backward sweep re-linearising at the iterate (trajectory, work position, K_t)
+    qn = (16 if newton else 6) * qn_iters
     qn_final = (4 + 2 + 2 + 2 + 2) + (4 + 2 + 2)           # forward: write q, p; reverse: compare with q_prev
     point = 4 + 8 + 12 + 10                                # trajectory, compressed Jacobian, tangent, adjoint sweeps
     return 8 * T * S * (project + qn + qn_final + point)
@@ -115,6 +117,7 @@ def run_ours(args):
     y, u, v0, xo = init_inputs(n, rank)
     bc = BatchedChains("fhn", OBS_INTERVAL, S, R, y, 4, n, device=local_rank)
     bc.set_chain_offset(rank * n)   # disjoint Philox streams per rank
+    bc.opts.solver = 1 if args.solver == "newton" else 0
     bc.init_linear_interpolation(u, v0, xo, 0)
     L = args.traj_len
     # untimed burn-in towards the typical set (the linear-interpolation states are far in the tails)
@@ -175,6 +178,8 @@ def run_ours(args):
     else:
         parts = [BatchedChains("fhn", OBS_INTERVAL, S, R, y, 4, bounds[i + 1] - bounds[i], device=local_rank)
                  for i in range(n_parts)]
+        for b in parts:
+            b.opts.solver = bc.opts.solver
     pins = []
     for i in range(n_parts):
         sl = slice(bounds[i], bounds[i + 1])
@@ -236,7 +241,7 @@ def run_ours(args):
         # Algorithmic bytes: doubles moved per SDE time step and chain, summed over the
         # phases of one leapfrog step, with the MEASURED number of quasi-Newton sweeps.
         iters_per_step = qn_iters / max(ok, 1)          # forward + reverse iterations per successful step
-        alg_bytes_step = leapfrog_bytes_per_chain_step(iters_per_step)
+        alg_bytes_step = leapfrog_bytes_per_chain_step(iters_per_step, newton=args.solver == "newton")
         alg_bytes = alg_bytes_step * ok                   # over the timed region, this rank
         lf_ms = ms_lf
         achieved = alg_bytes / (lf_ms * 1e-3) / 1e9 if lf_ms > 0 else 0.0
@@ -254,7 +259,7 @@ def run_ours(args):
             "dtype": "f64",
             "data": "synthetic",
             "config": {
-                "workload": WORKLOAD,
+                "workload": WORKLOAD if args.solver == "quasi-newton" else WORKLOAD.replace("quasi-Newton", "Newton"),
                 "chains_per_gpu": n,
                 "chains_per_cta_tile": bc.chains_per_tile(),
                 "step_size": args.dt,
@@ -396,6 +401,9 @@ def main():
     ap.add_argument("--traj-len", type=int, default=8)
     ap.add_argument("--burnin", type=int, default=60)
     ap.add_argument("--burnin-dt", type=float, default=0.05)
+    ap.add_argument("--solver", choices=("quasi-newton", "newton"), default="quasi-newton",
+                    help="projection solver (north-star item 3 names the quasi-Newton loop; the reference scripts "
+                         "default to Newton, scripts/utils.py:137-142)")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-pipeline", type=int, default=2,
                     help="number of BatchedChains objects the end-to-end loop alternates between (1 = no overlap)")
