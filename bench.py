@@ -118,6 +118,8 @@ def run_ours(args):
     bc = BatchedChains("fhn", OBS_INTERVAL, S, R, y, 4, n, device=local_rank)
     bc.set_chain_offset(rank * n)   # disjoint Philox streams per rank
     bc.opts.solver = 1 if args.solver == "newton" else 0
+    if args.regroup:
+        bc.set_chain_regrouping(True)   # per-chain results unchanged; chains with similar iteration counts share tiles
     bc.init_linear_interpolation(u, v0, xo, 0)
     L = args.traj_len
     # untimed burn-in towards the typical set (the linear-interpolation states are far in the tails)
@@ -262,6 +264,7 @@ def run_ours(args):
                 "workload": WORKLOAD if args.solver == "quasi-newton" else WORKLOAD.replace("quasi-Newton", "Newton"),
                 "chains_per_gpu": n,
                 "chains_per_cta_tile": bc.chains_per_tile(),
+                "chain_regrouping": bool(args.regroup),
                 "step_size": args.dt,
                 "traj_len": L,
                 "burnin_transitions": args.burnin,
@@ -404,6 +407,10 @@ def main():
     ap.add_argument("--solver", choices=("quasi-newton", "newton"), default="quasi-newton",
                     help="projection solver (north-star item 3 names the quasi-Newton loop; the reference scripts "
                          "default to Newton, scripts/utils.py:137-142)")
+    ap.add_argument("--regroup", type=int, default=0,
+                    help="re-assign chains to CTA tiles by iteration count at every partition switch (results per "
+                         "chain are bit-identical, tests/test_gpu_regrouping.py; measured: no gain, the iteration "
+                         "count of a chain is not persistent across transitions)")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-pipeline", type=int, default=2,
                     help="number of BatchedChains objects the end-to-end loop alternates between (1 = no overlap)")

@@ -85,6 +85,17 @@ int mmd_chains_per_tile(mmd_handle h);
 /* global index of this handle's first chain: offsets the Philox counters so that ranks that shard
  * one population of chains draw disjoint, rank-count-independent streams */
 int mmd_set_chain_offset(mmd_handle h, int chain0);
+/* Chain regrouping (throughput option, off by default).  The iteration loops of the projection solves run per CTA
+ * tile for as long as the tile's slowest chain; a chain's iteration count is persistent (it follows the stiffness
+ * of its parameters).  With regrouping on, every partition switch (mmd_switch_partition, mmd_transition_end,
+ * mmd_hmc_transition) re-assigns the chains to slots sorted by the iteration count of their last step -- the
+ * re-tiling pass of the switch moves every position anyway.  Every chain's results are bit-identical to a run
+ * without regrouping (Philox streams are keyed by chain id, nothing depends on the tile neighbours); per-chain
+ * OUTPUTS are then in slot order and mmd_get_slot_chains returns the chain id of every slot.  Setting states
+ * (mmd_set_state*, mmd_init_linear_interpolation) returns to chain order.  Not combinable with per-chain step
+ * sizes, adaptation or the mmd_vec_* work vectors. */
+int mmd_set_chain_regrouping(mmd_handle h, int on);
+int mmd_get_slot_chains(mmd_handle h, int* chain_of_slot /* [n_chains] */);
 
 /* ---- system ops on the resident state ----------------------------------------------------------- */
 /* jacob_constr_blocks + chol_gram_blocks + log_det_sqrt_gram (+ grad_log_det_sqrt_gram when

@@ -60,6 +60,8 @@ SIGNATURES = {
     "mmd_n_chains": (C.c_int, [_H]),
     "mmd_set_state": (C.c_int, [_H, _dp, _dp, _dp, C.c_int]),
     "mmd_set_state_async": (C.c_int, [_H, _dp, _dp, _dp, C.c_int]),
+    "mmd_set_chain_regrouping": (C.c_int, [_H, C.c_int]),
+    "mmd_get_slot_chains": (C.c_int, [_H, C.POINTER(C.c_int)]),
     "mmd_get_state": (C.c_int, [_H, _dp, _dp, _dp]),
     "mmd_set_momentum": (C.c_int, [_H, _dp]),
     "mmd_set_state_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

@@ -114,6 +114,18 @@ class BatchedChains:
         check(fn(self._h, _dp(q), None if pp is None else _dp(pp), _dp(x), int(partition)))
         self._dim_x = x.shape[2]
 
+    def set_chain_regrouping(self, on=True):
+        """Throughput option: at every partition switch re-assign the chains to CTA tiles sorted by the projection
+        iteration count of their last step (slow chains then delay only each other).  Per-chain results are
+        bit-identical; per-chain outputs (get_state, transition_stats, ...) come in SLOT order afterwards and
+        `slot_chains()` gives the chain id of every slot: canonical[slot_chains()] = slot_ordered."""
+        check(self._L.mmd_set_chain_regrouping(self._h, int(bool(on))))
+
+    def slot_chains(self):
+        out = np.empty(self.n_chains, dtype=np.int32)
+        check(self._L.mmd_get_slot_chains(self._h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
     def init_linear_interpolation(self, u, v_0, x_obs_seq, partition=0):
         """Batched `find_initial_state_by_linear_interpolation` (mici_extensions.py:1479-1547)."""
         u, v_0, x = _c(u), _c(v_0), _c(x_obs_seq)

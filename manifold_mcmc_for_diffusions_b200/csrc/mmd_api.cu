@@ -54,10 +54,48 @@ int unpack_chain(mmd_handle h, int rows, double* canon_dev, const double* src) {
   CK(cudaGetLastError());
   return 0;
 }
-int reset_flags(mmd_handle h) {
+int reset_slot_order(mmd_handle h) {
+  if (!h->regroup) return 0;
+  for (int c = 0; c < h->d.n_chains; ++c) h->slot_chain_host[c] = c;
+  CK(cudaMemcpyAsync(h->slot_chain, h->slot_chain_host.data(), h->d.n_chains * sizeof(int), cudaMemcpyHostToDevice,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int reset_flags(mmd_handle h) {   // new states from the caller (in the caller's chain order)
   const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
   CK(cudaMemsetAsync(h->S.cur, 0, nc * sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->W.status, 0, nc * sizeof(int), h->stream));
+  return reset_slot_order(h);
+}
+template <class T>
+int permute_slots(mmd_handle h, T* arr, T* tmp) {
+  const int n = h->d.n_chains;
+  k_permute<T><<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->newpos, arr, tmp);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(arr, tmp, n * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+// Plan of the next slot assignment: chains sorted (stably) by the projection iterations of their last leapfrog step,
+// failed chains last -- the per-tile iteration loops run as long as their slowest chain, and a chain's iteration
+// count is persistent (it follows the stiffness of its parameters), tools/iter_corr.py.
+int regroup_plan(mmd_handle h) {
+  const int n = h->d.n_chains;
+  const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
+  std::vector<int> it(2 * nc), st(nc), order(n), newpos(n), sc(n);
+  CK(cudaMemcpyAsync(it.data(), h->W.iters, 2 * nc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(st.data(), h->W.status, nc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i) order[i] = i;
+  auto key = [&](int i) { return (st[i] & ~mmd::ST_INACTIVE) ? (1 << 20) : it[i] + it[nc + i]; };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+  for (int j = 0; j < n; ++j) newpos[order[j]] = j;
+  for (int i = 0; i < n; ++i) sc[newpos[i]] = h->slot_chain_host[i];
+  h->slot_chain_host = sc;
+  CK(cudaMemcpyAsync(h->newpos, newpos.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->slot_chain, sc.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));   // the host vectors go out of scope
   return 0;
 }
 
@@ -167,6 +205,9 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   h->lin_valid = false;
   h->partition = 0;
   h->chain0 = 0;
+  h->regroup = h->regroup_now = false;
+  h->slot_chain = h->newpos = h->perm_i = nullptr;
+  h->perm_d = nullptr;
 
   const size_t X = ops->X, V = ops->V, Z = ops->Z;
   const size_t NTRI = (size_t)NRMAX * (NRMAX + 1) / 2, UTRI = UMAX * (UMAX + 1) / 2;
@@ -407,11 +448,52 @@ int mmd_update_x_obs_seq(mmd_handle h) {
 int mmd_switch_partition(mmd_handle h) {
   // SwitchPartitionTransition.sample (:1279-1282): next partition, regenerate x_obs_seq from the position
   const int pa = h->partition, pb = (h->partition + 1) % h->d.num_partition;
-  if (pa != pb) {
+  if (h->regroup) {
+    // the re-tiling pass moves every position anyway: let it also re-assign the slots
+    const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
+    if (regroup_plan(h)) return -2;
+    h->regroup_now = true;
+    const int rc = DISPATCH(h, retile(h, pa, pb));
+    h->regroup_now = false;
+    if (rc) return -2;
+    h->partition = pb;
+    // per-slot results of the transition that just ended follow their chains
+    if (permute_slots(h, h->accepted, h->perm_i) || permute_slots(h, h->W.status, h->perm_i) ||
+        permute_slots(h, h->W.iters, h->perm_i) || permute_slots(h, h->W.iters + nc, h->perm_i) ||
+        permute_slots(h, h->accp, h->perm_d) || permute_slots(h, h->W.revd, h->perm_d))
+      return -2;
+  } else if (pa != pb) {
     if (DISPATCH(h, retile(h, pa, pb))) return -2;
     h->partition = pb;
   }
   return mmd_update_x_obs_seq(h);
+}
+
+int mmd_set_chain_regrouping(mmd_handle h, int on) {
+  if (on && (h->adapting || h->W.use_dt_chain || !h->aux.empty()))
+    FAIL("chain regrouping cannot be combined with per-chain step sizes / adaptation / NUTS work vectors");
+  if (on && !h->slot_chain) {
+    const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
+    if (dalloc(h, &h->slot_chain, nc) || dalloc(h, &h->newpos, nc) || dalloc(h, &h->perm_i, nc) ||
+        dalloc(h, &h->perm_d, nc))
+      return -2;
+    h->slot_chain_host.assign(h->d.n_chains, 0);
+  }
+  if (on && !h->regroup) {
+    h->regroup = true;
+    return reset_slot_order(h);
+  }
+  if (!on && h->regroup) {
+    for (int c = 0; c < h->d.n_chains; ++c)
+      if (h->slot_chain_host[c] != c) FAIL("chains are regrouped: read the states back and set them again to return to chain order");
+    h->regroup = false;
+  }
+  return 0;
+}
+
+int mmd_get_slot_chains(mmd_handle h, int* out) {
+  for (int c = 0; c < h->d.n_chains; ++c) out[c] = h->regroup ? h->slot_chain_host[c] : c;
+  return 0;
 }
 
 int mmd_sample_momentum(mmd_handle h, uint64_t seed, uint64_t offset) {
@@ -519,7 +601,8 @@ int mmd_transition_steps(mmd_handle h, double dt, int n_steps, const mmd_integra
 int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_partition) {
   int rc = DISPATCH(h, hamiltonian(h, 0, h->hbuf)); if (rc) return rc;
   k_decide<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->S, h->W, h->h0buf, h->hbuf, h->cur0, seed,
-                                                              2 * iter + 1, h->chain0, h->accepted, h->accp);
+                                                              2 * iter + 1, h->chain0, h->accepted, h->accp,
+                                                              h->regroup ? h->slot_chain : nullptr);
   h->launches++;
   k_restore<<<1184, 256, 0, h->stream>>>(h->d, h->S, h->accepted, h->qsave);
   h->launches++;
@@ -539,6 +622,7 @@ int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_pa
 
 int mmd_set_step_sizes(mmd_handle h, const double* dt) {
   if (!dt) { h->W.use_dt_chain = 0; return 0; }
+  if (h->regroup) FAIL("per-chain step sizes cannot be combined with chain regrouping");
   CK(cudaMemcpyAsync(h->W.dt_chain, dt, h->d.n_chains * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->W.use_dt_chain = 1;
@@ -554,6 +638,7 @@ int mmd_get_step_sizes(mmd_handle h, double* dt) {
 int mmd_adapt_start(mmd_handle h, double init_step_size, double target, double reg_coefficient, double iter_decay,
                     double iter_offset) {
   if (!(init_step_size > 0.0)) FAIL("initial step size must be positive");
+  if (h->regroup) FAIL("step-size adaptation cannot be combined with chain regrouping");
   const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
   std::vector<double> st(4 * nc, 0.0), dt(nc, init_step_size);
   for (size_t c = 0; c < nc; ++c) st[3 * nc + c] = log(10.0 * init_step_size);   // log_step_size_reg_target
@@ -593,6 +678,7 @@ static int resolve_vec(mmd_handle h, int id, double** ptr, int* live) {
 }
 
 int mmd_aux_reserve(mmd_handle h, int n_arrays) {
+  if (h->regroup && n_arrays > 0) FAIL("work vectors cannot be combined with chain regrouping");
   while ((int)h->aux.size() < n_arrays) {
     double* p = nullptr;
     if (dalloc(h, &p, (size_t)h->d.qsize)) return -2;

@@ -10,6 +10,7 @@
 #include <string.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -66,6 +67,14 @@ struct mmd_handle_s {
   int partition;
   int ncmax, nbmax;
   int chain0;     // global index of this handle's first chain (Philox stream offset)
+  // chain regrouping (mmd_set_chain_regrouping): slots are re-assigned at every partition switch so that chains
+  // with similar projection iteration counts share a CTA tile
+  bool regroup, regroup_now;
+  int* slot_chain;   // device [chains]: local chain id living in each slot
+  int* newpos;       // device [chains]: slot each slot's chain moves to at the pending re-tiling
+  int* perm_i;       // device scratch [chains]
+  double* perm_d;    // device scratch [chains]
+  std::vector<int> slot_chain_host;
   bool fused;
   const mmd_ops* ops;  // kernel launchers of the handle's model
   cudaStream_t stream;

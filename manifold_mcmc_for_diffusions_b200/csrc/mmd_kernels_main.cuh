@@ -1788,14 +1788,22 @@ __global__ void k_unpack(Dims d, int part, double* __restrict__ canon, const dou
 }
 // re-tile the current position from partition `pa` to partition `pb` (SwitchPartitionTransition)
 template <class M>
+// newpos (optional): the chain in slot `chain` moves to slot newpos[chain] (chain regrouping, mmd_set_chain_regrouping)
 __global__ void k_retile(Dims d, int pa, int pb, const double* __restrict__ src, double* __restrict__ dst,
-                         long long slot_stride, const int* __restrict__ cur) {
+                         long long slot_stride, const int* __restrict__ cur, const int* __restrict__ newpos) {
   const long long n = (long long)d.n_chains * d.dim_q;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     const int chain = (int)(e / d.dim_q), i = (int)(e % d.dim_q);
-    dst[tile_index<M>(d, pb, chain, i)] = src[cur[chain] * slot_stride + tile_index<M>(d, pa, chain, i)];
+    const int to = newpos ? newpos[chain] : chain;
+    dst[tile_index<M>(d, pb, to, i)] = src[cur[chain] * slot_stride + tile_index<M>(d, pa, chain, i)];
   }
+}
+// per-slot arrays follow their chains: dst[newpos[i]] = src[i]
+template <class T>
+__global__ void k_permute(int n, const int* __restrict__ newpos, const T* __restrict__ src, T* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[newpos[i]] = src[i];
 }
 // per-chain arrays [chain][rows] (canonical) <-> [tile][rows][cpb]
 static __global__ void k_pack_chain(Dims d, int rows, const double* __restrict__ canon, double* __restrict__ dst) {
@@ -1942,14 +1950,17 @@ __global__ void k_init_interp(Dims d, Slots S, Work W, int part) {
 // tile shape, the partition or the number of GPUs.  One thread per (chain, canonical pair).
 template <class M>
 __global__ void k_philox_momentum(Dims d, int part, double* __restrict__ base, long long slot_stride,
-                                  const int* __restrict__ cur, uint64_t seed, uint64_t offset, int chain0) {
+                                  const int* __restrict__ cur, uint64_t seed, uint64_t offset, int chain0,
+                                  const int* __restrict__ slot_chain) {
   const int npair = (d.dim_q + 1) / 2;
   const long long n = (long long)d.n_chains * npair;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     const int chain = (int)(e / npair), pr = (int)(e % npair);
     double a, b;
-    philox_normal_pair(seed, offset, ((uint64_t)(chain0 + chain) << 32) | (uint64_t)pr, &a, &b);
+    // the stream belongs to the chain, not to the slot it currently occupies
+    const int cid = chain0 + (slot_chain ? slot_chain[chain] : chain);
+    philox_normal_pair(seed, offset, ((uint64_t)cid << 32) | (uint64_t)pr, &a, &b);
     double* dst = base + cur[chain] * slot_stride;
     dst[tile_index<M>(d, part, chain, 2 * pr)] = a;
     if (2 * pr + 1 < d.dim_q) dst[tile_index<M>(d, part, chain, 2 * pr + 1)] = b;
@@ -1963,10 +1974,12 @@ __global__ void k_philox_momentum(Dims d, int part, double* __restrict__ base, l
 // A rejected chain returns to the slot it started the transition in (cur0).
 static __global__ void k_decide(Dims d, Slots S, Work W, const double* __restrict__ h0, const double* __restrict__ h1,
                          const int* __restrict__ cur0, uint64_t seed, uint64_t offset, int chain0,
-                         int* __restrict__ accepted, double* __restrict__ acc_prob) {
+                         int* __restrict__ accepted, double* __restrict__ acc_prob,
+                         const int* __restrict__ slot_chain) {
   const int chain = blockIdx.x * blockDim.x + threadIdx.x;
   if (chain >= d.n_chains) return;
-  uint32_t c[4] = {(uint32_t)(chain0 + chain), 0u, (uint32_t)offset, (uint32_t)(offset >> 32)};
+  uint32_t c[4] = {(uint32_t)(chain0 + (slot_chain ? slot_chain[chain] : chain)), 0u, (uint32_t)offset,
+                   (uint32_t)(offset >> 32)};
   philox4x32_10(c, (uint32_t)seed ^ 0x5bd1e995u, (uint32_t)(seed >> 32));
   const double uu = ((double)((((uint64_t)c[1] << 32) | c[0]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
   const int st = W.status[chain];

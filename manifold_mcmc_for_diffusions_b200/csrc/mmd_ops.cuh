@@ -107,7 +107,8 @@ struct Ops {
   }
   static int retile(mmd_handle h, int pa, int pb) {
     // q(cur) in the tiling of partition pa -> qtmp in the tiling of pb -> slot 0; cur := 0
-    k_retile<Mdl><<<1184, 256, 0, h->stream>>>(h->d, pa, pb, h->S.q, h->qtmp, h->S.s_q, h->S.cur);
+    k_retile<Mdl><<<1184, 256, 0, h->stream>>>(h->d, pa, pb, h->S.q, h->qtmp, h->S.s_q, h->S.cur,
+                                               h->regroup_now ? h->newpos : nullptr);
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->S.q, h->qtmp, (size_t)h->d.qsize * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -128,7 +129,8 @@ struct Ops {
   }
   static int philox(mmd_handle h, uint64_t seed, uint64_t offset) {
     k_philox_momentum<Mdl><<<1184, 256, 0, h->stream>>>(h->d, h->partition, h->S.p, h->S.s_q, h->S.cur, seed, offset,
-                                                        h->chain0);
+                                                        h->chain0,
+                                                        h->regroup ? h->slot_chain : nullptr);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
