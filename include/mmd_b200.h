@@ -162,6 +162,10 @@ int mmd_get_step_sizes(mmd_handle h, double* dt);
  * per chain, or (pool != 0) the mean over chains as Mici does for several chains. */
 int mmd_adapt_start(mmd_handle h, double init_step_size, double target, double reg_coefficient, double iter_decay,
                     double iter_offset);
+/* the same with one initial step size per chain (Mici initialises each chain's adapter from its own coarse search,
+ * DualAveragingStepSizeAdapter._find_and_set_init_step_size; batched in adaptation.find_init_step_sizes) */
+int mmd_adapt_start_per_chain(mmd_handle h, const double* init_step_sizes, double target, double reg_coefficient,
+                              double iter_decay, double iter_offset);
 int mmd_adapt_stop(mmd_handle h, int pool);
 /* same update from accept statistics supplied by the caller (dynamic transitions built by the host) */
 int mmd_adapt_update(mmd_handle h, const double* accept_stat);

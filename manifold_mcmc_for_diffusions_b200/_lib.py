@@ -99,6 +99,7 @@ SIGNATURES = {
     "mmd_set_step_sizes": (C.c_int, [_H, _dp]),
     "mmd_get_step_sizes": (C.c_int, [_H, _dp]),
     "mmd_adapt_start": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "mmd_adapt_start_per_chain": (C.c_int, [_H, _dp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "mmd_adapt_stop": (C.c_int, [_H, C.c_int]),
     "mmd_adapt_update": (C.c_int, [_H, _dp]),
     "mmd_aux_reserve": (C.c_int, [_H, C.c_int]),

@@ -225,8 +225,13 @@ class BatchedChains:
 
     def adapt_start(self, init_step_size, target=0.8, reg_coefficient=0.05, iter_decay=0.75, iter_offset=10):
         """On-device per-chain DualAveragingStepSizeAdapter (Mici defaults; scripts use target 0.8, reg 0.1)."""
-        check(self._L.mmd_adapt_start(self._h, float(init_step_size), float(target), float(reg_coefficient),
-                                      float(iter_decay), float(iter_offset)))
+        if np.ndim(init_step_size) == 0:
+            check(self._L.mmd_adapt_start(self._h, float(init_step_size), float(target), float(reg_coefficient),
+                                          float(iter_decay), float(iter_offset)))
+        else:   # one initial step size per chain (adaptation.find_init_step_sizes)
+            init = _c(np.broadcast_to(init_step_size, (self.n_chains,)))
+            check(self._L.mmd_adapt_start_per_chain(self._h, _dp(init), float(target), float(reg_coefficient),
+                                                    float(iter_decay), float(iter_offset)))
 
     def adapt_stop(self, pool=False):
         check(self._L.mmd_adapt_stop(self._h, int(pool)))

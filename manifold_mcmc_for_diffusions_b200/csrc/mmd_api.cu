@@ -635,13 +635,17 @@ int mmd_get_step_sizes(mmd_handle h, double* dt) {
   return 0;
 }
 
-int mmd_adapt_start(mmd_handle h, double init_step_size, double target, double reg_coefficient, double iter_decay,
-                    double iter_offset) {
-  if (!(init_step_size > 0.0)) FAIL("initial step size must be positive");
+static int adapt_start_impl(mmd_handle h, const double* init_per_chain, double init_scalar, double target,
+                            double reg_coefficient, double iter_decay, double iter_offset) {
   if (h->regroup) FAIL("step-size adaptation cannot be combined with chain regrouping");
   const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
-  std::vector<double> st(4 * nc, 0.0), dt(nc, init_step_size);
-  for (size_t c = 0; c < nc; ++c) st[3 * nc + c] = log(10.0 * init_step_size);   // log_step_size_reg_target
+  std::vector<double> st(4 * nc, 0.0), dt(nc, init_scalar);
+  if (init_per_chain)
+    for (int c = 0; c < h->d.n_chains; ++c) dt[c] = init_per_chain[c];
+  for (size_t c = 0; c < nc; ++c) {
+    if (!(dt[c] > 0.0)) FAIL("initial step sizes must be positive");
+    st[3 * nc + c] = log(10.0 * dt[c]);   // log_step_size_reg_target
+  }
   CK(cudaMemcpyAsync(h->ad_state, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->W.dt_chain, dt.data(), nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -649,6 +653,17 @@ int mmd_adapt_start(mmd_handle h, double init_step_size, double target, double r
   h->adapting = true;
   h->W.use_dt_chain = 1;
   return 0;
+}
+
+int mmd_adapt_start(mmd_handle h, double init_step_size, double target, double reg_coefficient, double iter_decay,
+                    double iter_offset) {
+  return adapt_start_impl(h, nullptr, init_step_size, target, reg_coefficient, iter_decay, iter_offset);
+}
+
+int mmd_adapt_start_per_chain(mmd_handle h, const double* init_step_sizes, double target, double reg_coefficient,
+                              double iter_decay, double iter_offset) {
+  if (!init_step_sizes) FAIL("init_step_sizes is NULL");
+  return adapt_start_impl(h, init_step_sizes, 1.0, target, reg_coefficient, iter_decay, iter_offset);
 }
 
 int mmd_adapt_stop(mmd_handle h, int pool) {

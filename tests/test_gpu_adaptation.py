@@ -69,3 +69,40 @@ def test_dual_averaging_reaches_target_accept_rate():
     assert np.array_equal(bc.get_step_sizes(), pooled)      # no adaptation after finalize
     assert np.max(np.abs(bc.constr())) < 1e-8
     bc.close()
+
+
+def test_init_step_size_search_and_per_chain_adapter_start(prob):
+    """Batched DualAveragingStepSizeAdapter._find_and_set_init_step_size: every chain ends on the log-2 boundary of
+    |delta H| (one more halving / doubling crosses it), positions are untouched, and the adapter starts from the
+    per-chain result."""
+    from manifold_mcmc_for_diffusions_b200.adaptation import find_init_step_sizes
+
+    bc = make_batched(prob)
+    bc.set_state(prob["q"], prob["xobs"], 0)
+    eps, found = find_init_step_sizes(bc, 7, 0)
+    assert found.all()
+    assert np.all(np.log2(eps) == np.round(np.log2(eps))) and np.all(eps < 1.0)     # halvings of 1.0
+    q, _, _ = bc.get_state()
+    assert np.array_equal(q, prob["q"])
+    assert np.all(bc.step_info()["status"] == 0)
+    # re-do the last two trials by hand with the same momenta: eps ends a "too big" search, i.e. |dH(eps)| <= log 2
+    # while the step before it (2 eps) failed or changed H by more than log 2
+    thr = np.log(2.0)
+    dh = {}
+    for k, e in (("eps", eps), ("twice", 2.0 * eps)):
+        bc.transition_begin(7, 0)
+        h0 = bc.hamiltonian()
+        bc.set_step_sizes(e)
+        bc.transition_steps(1.0, 1)
+        st = bc.step_info()["status"]
+        with np.errstate(invalid="ignore"):
+            d = np.abs(h0 - bc.hamiltonian())
+        dh[k] = np.where(st != 0, np.inf, d)
+        bc.set_state(prob["q"], prob["xobs"], 0)
+    assert np.all(dh["eps"] <= thr)
+    assert np.all(~(dh["twice"] <= thr))
+    bc.set_step_sizes(None)
+    bc.adapt_start(eps, target=0.8, reg_coefficient=0.1)
+    assert np.array_equal(bc.get_step_sizes(), eps)
+    bc.adapt_stop()
+    bc.close()

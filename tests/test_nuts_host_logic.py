@@ -185,3 +185,24 @@ def test_extra_subtree_checks_shorten_trees():
     a, _ = _run_batched(0.2, 300, 10, 3, True)
     b, _ = _run_batched(0.2, 300, 10, 3, False)
     assert a["n_step"].mean() < b["n_step"].mean()
+
+
+def test_batched_init_step_size_search_matches_the_sequential_adapter():
+    """adaptation.find_init_step_sizes against DualAveragingStepSizeAdapter._find_and_set_init_step_size of the
+    Mici restatement, chain by chain, on the same states and momenta."""
+    from manifold_mcmc_for_diffusions_b200.adaptation import find_init_step_sizes
+    from manifold_mcmc_for_diffusions_b200.mici_compat.adapters import DualAveragingStepSizeAdapter
+
+    rng = np.random.default_rng(5)
+    n = 64
+    q = rng.standard_normal((n, len(SCALES))) * SCALES * 0.9
+    bc = FakeChains(q, 21)
+    eps, found = find_init_step_sizes(bc, 0, 0)
+    assert found.all() and np.array_equal(bc.q, q) and np.all(bc.status == 0)
+    p = bc.p.copy()                               # the momenta the search used
+    ad = DualAveragingStepSizeAdapter()
+    for c in range(n):
+        integ = _Integrator(None)
+        ref = ad._find_and_set_init_step_size(_State(q[c].copy(), p[c].copy()), _System(), integ)
+        assert ref == eps[c], (c, ref, eps[c])
+    assert len(set(eps)) > 1                      # not a trivial case: chains end at different step sizes
