@@ -45,7 +45,10 @@ class MultinomialDynamicIntegrationTransition(Transition):
     }
 
     def __init__(self, system, integrator, max_tree_depth=10, max_delta_h=1000,
-                 termination_criterion=riemannian_no_u_turn_criterion, do_extra_subtree_checks=True):
+                 termination_criterion=riemannian_no_u_turn_criterion, do_extra_subtree_checks=True,
+                 error_accept_stat="zero"):
+        # error_accept_stat: see nuts.BatchedNUTS (accept_stat of a transition that ended in an integrator error)
+        self.error_accept_stat = error_accept_stat
         self.system = system
         self.integrator = integrator
         self.max_tree_depth = max_tree_depth
@@ -122,9 +125,12 @@ class MultinomialDynamicIntegrationTransition(Transition):
         new_state = proposal.copy()
         new_state.dir = state.dir
         n_step = stats["n_step"]
+        accept_stat = stats["sum_acc_prob"] / n_step if n_step > 0 else 0.0
+        if self.error_accept_stat == "zero" and (stats["convergence_error"] or stats["non_reversible_step"]):
+            accept_stat = 0.0
         out_stats = {
             "hamiltonian": self.system.h(new_state), "n_step": n_step,
-            "accept_stat": stats["sum_acc_prob"] / n_step if n_step > 0 else 0.0, "tree_depth": depth,
+            "accept_stat": accept_stat, "tree_depth": depth,
             "diverging": stats["diverging"], "non_reversible_step": stats["non_reversible_step"],
             "convergence_error": stats["convergence_error"],
         }

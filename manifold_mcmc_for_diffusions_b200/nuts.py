@@ -31,7 +31,18 @@ def _trailing_ones(x):
 
 
 class BatchedNUTS:
-    def __init__(self, chains, max_tree_depth=10, max_delta_h=1000.0, do_extra_subtree_checks=True):
+    def __init__(self, chains, max_tree_depth=10, max_delta_h=1000.0, do_extra_subtree_checks=True,
+                 error_accept_stat="zero"):
+        """error_accept_stat: the `accept_stat` reported for a transition whose tree ended in an integrator error
+        (projection not converged / non-reversible step).  "zero" reports 0, "partial" the mean acceptance
+        probability over the steps taken before the error.  Mici is not available here and its source could not be
+        consulted; the statistics recorded in the reference's notebook (accept_stat 0.83, n_step 28.3,
+        convergence_error 0.15 after dual averaging to 0.8) are reproduced with "zero" and cannot be reproduced at any
+        step size with "partial" (DESIGN.md section 2), so "zero" is the default: it is what the step-size adapter
+        sees, and it keeps the adapted step size out of the regime where most trees end in an error."""
+        if error_accept_stat not in ("zero", "partial"):
+            raise ValueError("error_accept_stat must be 'zero' or 'partial'")
+        self.error_accept_stat = error_accept_stat
         self.bc = chains
         self.max_tree_depth = D = int(max_tree_depth)
         self.max_delta_h = float(max_delta_h)
@@ -166,6 +177,9 @@ class BatchedNUTS:
             bc.switch_partition()
         else:
             bc.relinearize()
-        return {"n_step": n_step, "accept_stat": sum_acc / np.maximum(n_step, 1), "tree_depth": depth_reached,
+        accept_stat = sum_acc / np.maximum(n_step, 1)
+        if self.error_accept_stat == "zero":
+            accept_stat = np.where(conv_err | nonrev, 0.0, accept_stat)
+        return {"n_step": n_step, "accept_stat": accept_stat, "tree_depth": depth_reached,
                 "diverging": diverging, "convergence_error": conv_err, "non_reversible_step": nonrev,
                 "hamiltonian_init": h0}

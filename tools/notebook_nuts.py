@@ -50,16 +50,30 @@ def main():
             bc.set_state(q, x, bc.partition)
     nuts = BatchedNUTS(bc, max_tree_depth=depth)
     t0 = time.time()
-    bc.adapt_start(0.05, target=0.8, reg_coefficient=0.1)
+    # Mici: every chain's adapter starts from its own coarse step-size search (no step size is given in cell 33/43)
+    from manifold_mcmc_for_diffusions_b200.adaptation import find_init_step_sizes
+    eps0, found = find_init_step_sizes(bc, 20200710, it)
+    it += 1
+    eps0 = np.where(found, eps0, 0.05)
+    fixed = float(os.environ.get("FIXED_EPS", 0.0))     # > 0: no adaptation, warm-up at this step size
     warm = {"accept_stat": [], "n_step": []}
-    for k in range(n_warm):
-        st = nuts.transition(bc.get_step_sizes(), rng, 20200710, it)
-        it += 1
-        bc.adapt_update(st["accept_stat"])
-        warm["accept_stat"].append(st["accept_stat"].mean())
-        warm["n_step"].append(st["n_step"].mean())
-    bc.adapt_stop(pool=True)
-    eps = float(bc.get_step_sizes()[0])
+    if fixed > 0.0:
+        for k in range(n_warm):
+            st = nuts.transition(fixed, rng, 20200710, it)
+            it += 1
+            warm["accept_stat"].append(st["accept_stat"].mean())
+            warm["n_step"].append(st["n_step"].mean())
+        eps = fixed
+    else:
+        bc.adapt_start(eps0, target=0.8, reg_coefficient=0.1)
+        for k in range(n_warm):
+            st = nuts.transition(bc.get_step_sizes(), rng, 20200710, it)
+            it += 1
+            bc.adapt_update(st["accept_stat"])
+            warm["accept_stat"].append(st["accept_stat"].mean())
+            warm["n_step"].append(st["n_step"].mean())
+        bc.adapt_stop(pool=True)
+        eps = float(bc.get_step_sizes()[0])
     names = ["σ", "ϵ", "γ", "β", "x_0[0]", "x_0[1]"]
     draws = np.empty((n, n_main, 6))
     acc, nst, cerr, nrv, dep = [], [], [], [], []
@@ -77,7 +91,7 @@ def main():
         draws[:, k, :4] = z
         draws[:, k, 4:] = m.generate_x_0(z, q[:, 4:6])
     out = {"chains": n, "warm_up_transitions": n_warm, "main_transitions": n_main, "max_tree_depth": depth,
-           "adapted_step_size": eps, "accept_stat": float(np.mean(acc)), "n_step": float(np.mean(nst)),
+           "adapted_step_size": eps, "init_step_size_search_quantiles": np.quantile(eps0, [0.05, 0.5, 0.95]).tolist(), "accept_stat": float(np.mean(acc)), "n_step": float(np.mean(nst)),
            "convergence_error": float(np.mean(cerr)), "non_reversible_step": float(np.mean(nrv)),
            "tree_depth": float(np.mean(dep)), "wall_s": round(time.time() - t0, 1),
            "warm_up_accept_stat_last20": float(np.mean(warm["accept_stat"][-20:])),
