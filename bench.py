@@ -298,7 +298,8 @@ def run_ours(args):
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, dt=args.dt, L=L, burnin=args.burnin,
+                                               burnin_dt=args.burnin_dt)
         emit(out)
     bc.close()
     if world > 1:
@@ -306,60 +307,69 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline: the oracle (port of the reference path) on the host cores, bounded sample
+# CPU baseline: the compiled (numba) restatement of the reference path on the host cores, bounded sample.
+# Same workload as the GPU arm: same data, same initialisation recipe, same burn-in (transitions x trajectory
+# length x burn-in step size), same step size, trajectory length, solver and tolerances, momentum refresh,
+# Metropolis accept and partition switch inside the timed region; only successful chain-steps are counted.
 # ---------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    chain, n_steps, dt = args
-    import torch
+PUBLISHED_STEPS_PER_S_PER_CHAIN = 71.6   # FitzHugh-Nagumo_example.ipynb raw lines 716, 752 (2.53 it/s x 28.3 steps/it)
 
-    torch.set_num_threads(1)
-    from oracle import torch_oracle as O
-    from oracle.models import fhn
+
+def _cpu_worker(args):
+    chain, seconds, dt, L, burnin, burnin_dt = args
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = os.environ["NUMBA_NUM_THREADS"] = "1"
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    from oracle import numba_chmc as N
 
     y = load_y()
-    sysm = O.OracleSystem(
-        OBS_INTERVAL, S, R, y, 4, 2, 2, fhn.forward_func, fhn.generate_x_0, fhn.generate_z, fhn.obs_func,
-        None, False, dim_v_0=2,
-    )
     rng = np.random.default_rng([SEED, 10_000 + chain])
-
-    def gen_init(rng_):
-        return np.concatenate((y, rng_.standard_normal(y.shape) * 0.5), -1)
-
-    q, xo = O.find_initial_state_by_linear_interpolation(
-        sysm, rng, gen_init, u=0.3 * rng.standard_normal(4), v_0=rng.standard_normal(2)
-    )
-    pt = sysm.point(q, xo, 0)
-    p = sysm.project_onto_cotangent_space(torch.tensor(rng.standard_normal(q.shape[0])), pt)
+    ch = N.NumbaChain(T, S, R, y, OBS_INTERVAL)
+    q, xo = N.linear_interpolation_init(T, S, y, OBS_INTERVAL, rng)     # u, v_0 ~ N(0, I) like init_inputs()
+    ch.set_state(q, xo, 0)
+    for _ in range(burnin):
+        ch.hmc_transition(burnin_dt, L, rng)
+    ch.n_steps_ok = 0
     t0 = time.perf_counter()
-    done = 0
-    for s in range(n_steps):
-        try:
-            q, p, pt, _ = O.leapfrog_step(sysm, q, p, xo, 0, dt, pt=pt)
-            done += 1
-        except (O.ConvergenceError, O.NonReversibleStepError):
-            break
-    return done, time.perf_counter() - t0
+    ntr = 0
+    while time.perf_counter() - t0 < seconds:
+        ch.hmc_transition(dt, L, rng)
+        ntr += 1
+    return ch.n_steps_ok, time.perf_counter() - t0, ntr
 
 
-def cpu_baseline(seconds_hint=20.0, steps_per_chain=1, dt=0.02):
+def cpu_baseline(seconds=15.0, dt=0.1, L=8, burnin=60, burnin_dt=0.05):
     import multiprocessing as mp
+    import warnings
 
+    warnings.filterwarnings("ignore")
+    from oracle import numba_chmc as N   # compile once here: the workers then load numba's on-disk cache
+
+    y = load_y()
+    ch = N.NumbaChain(T, S, R, y, OBS_INTERVAL)
+    q, xo = N.linear_interpolation_init(T, S, y, OBS_INTERVAL, np.random.default_rng(0))
+    ch.set_state(q, xo, 0)
+    ch.hmc_transition(burnin_dt, 1, np.random.default_rng(0))
     cores = os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(c, steps_per_chain, dt) for c in range(cores)])
+        res = pool.map(_cpu_worker, [(c, seconds, dt, L, burnin, burnin_dt) for c in range(cores)])
     wall = time.perf_counter() - t0
-    done = sum(r[0] for r in res)
-    busy = max(r[1] for r in res)
+    rate = sum(r[0] / r[1] for r in res)            # chains run concurrently, one per core
     return {
-        "value": done / busy if busy > 0 else 0.0,
+        "value": rate,
         "unit": UNIT,
         "cores": cores,
         "kind": "port",
-        "sample": f"{cores} chains x {steps_per_chain} leapfrog step(s), one process per core, torch.func float64 "
-                  f"oracle (oracle/torch_oracle.py), timed region {busy:.1f}s of {wall:.1f}s wall",
+        "same_config": True,
+        "per_core": rate / cores,
+        "reference_published_per_chain": PUBLISHED_STEPS_PER_S_PER_CHAIN,
+        "sample": f"{cores} chains (one process per core), each: linear-interpolation init, {burnin} untimed burn-in "
+                  f"transitions of {L} steps at dt={burnin_dt}, then {sum(r[2] for r in res)} timed transitions of {L} "
+                  f"steps at dt={dt} ({seconds:.0f} s per core; {wall:.0f} s wall incl. burn-in); numba-compiled "
+                  f"float64 restatement oracle/numba_chmc.py (quasi-Newton), successful chain-steps only",
     }
 
 
@@ -367,7 +377,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cb = cpu_baseline(steps_per_chain=max(1, args.steps // 8) if args.steps >= 8 else 1)
+    if args.solver != "quasi-newton":
+        raise SystemExit("the compiled CPU restatement implements the quasi-Newton solver only")
+    cb = cpu_baseline(seconds=max(2.0, min(60.0, 1.5 * args.steps)), dt=args.dt, L=args.traj_len, burnin=args.burnin,
+                      burnin_dt=args.burnin_dt)
     out = {
         "impl": "reference",
         "metric": METRIC,
@@ -382,7 +395,8 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD},
+        "config": {"workload": WORKLOAD, "step_size": args.dt, "traj_len": args.traj_len,
+                   "burnin_transitions": args.burnin},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -434,7 +448,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-pipeline", type=int, default=2,
                     help="number of BatchedChains objects the end-to-end loop alternates between (1 = no overlap)")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
