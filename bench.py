@@ -5,7 +5,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one ConstrainedLeapfrogIntegrator.step (both projection solves, reversibility check,
-grad log-det) for every chain of the rank (default 4096 chains per GPU, weak scaling).  Momentum
+grad log-det) for every chain of the rank.  Default workload = BASELINE.json config 5: a fixed population of
+65,536 chains sharded over the ranks (strong scaling; `--scaling weak --chains N` keeps N chains per GPU), with the
+reference scripts' traced scalars read back every transition, one NCCL all-gather of the traces at the end and
+rank-normalised split-R-hat / bulk ESS / ESS per second in the `diagnostics` object of the line.  Momentum
 refresh (Philox, on device), the Metropolis accept and the partition switch happen every
 `--traj-len` steps INSIDE the timed region; only successful chain-steps are counted.
 Prints ONE JSON line (see DESIGN.md "Measurement").
@@ -45,6 +48,42 @@ def init_inputs(n, rank):
     v0 = rng.standard_normal((n, 2))
     xo = np.concatenate((np.broadcast_to(y, (n, T, 1)), 0.5 * rng.standard_normal((n, T, 1))), -1)
     return y, u, v0, xo
+
+
+def init_inputs_global(lo, hi):
+    """The same recipe for a FIXED population of chains sharded over the ranks: generators are keyed by blocks of
+    4096 GLOBAL chain indices, so chain c gets the same initial state whatever the number of ranks."""
+    y = load_y()
+    n, blk = hi - lo, 4096
+    u, v0, xo = np.empty((n, 4)), np.empty((n, 2)), np.empty((n, T, 2))
+    for b in range(lo // blk, (hi - 1) // blk + 1):
+        g = np.random.default_rng([SEED, 7, b])
+        fu, fv, fx = g.standard_normal((blk, 4)), g.standard_normal((blk, 2)), g.standard_normal((blk, T, 1))
+        c0, c1 = max(lo, b * blk), min(hi, (b + 1) * blk)
+        src, dst = slice(c0 - b * blk, c1 - b * blk), slice(c0 - lo, c1 - lo)
+        u[dst], v0[dst] = fu[src], fv[src]
+        xo[dst] = np.concatenate((np.broadcast_to(y, (c1 - c0, T, 1)), 0.5 * fx[src]), -1)
+    return y, u, v0, xo
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank on the CPU cores next to its GPU (the page-locked staging buffers of the end-to-end
+    leg are then allocated on that NUMA node: with 8 ranks the host side of the uploads is the bottleneck)."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cores local to {bus}"
+    except Exception as e:   # noqa: BLE001 - affinity is an optimisation only
+        return f"unchanged ({type(e).__name__})"
+    return "unchanged"
 
 
 class ClockSampler(threading.Thread):
@@ -96,6 +135,49 @@ def leapfrog_bytes_per_chain_step(qn_iters, newton=False):
     return 8 * T * S * (project + qn + qn_final + point)
 
 
+def block_sizes(T_, R_, part):
+    """Observations per block of partition `part` (mici_extensions.py:321-351)."""
+    init = R_ if part == 0 else R_ // 2
+    nfull, nrem = divmod(T_ - init, R_)
+    nmid = nfull - 1 if nrem == 0 else nfull
+    return [init] + [R_] * nmid + [R_ if nrem == 0 else nrem]
+
+
+def work_model(iters_per_step, T_=T, S_=S, R_=R, X=2, V=2, U=4, Z=4, V0=2):
+    """SURVEY.md 8(d) "work model v1": algorithmic FP64 flops (FMA = 2) and the unavoidable HBM bytes of ONE constrained
+    leapfrog step of one chain, with the MEASURED number of projection iterations (forward + reverse), averaged over
+    the two partitions.  Constants of the model: F_f = 31 (FHN step), F_J = 15, F_Z = 20, F_2 = 100 (second-order
+    row-step), adj = 2X^2 + 2XV + 2XZ.  With 5 + 5 iterations and partition 0 this gives the survey's 4,006,468 flops."""
+    F_f, F_J, F_Z, F_2 = 31, 15, 20, 100
+    adj = 2 * X * X + 2 * X * V + 2 * X * Z
+    N = T_ * S_
+    dim_q = U + V0 + N * V
+    out = []
+    for part in (0, 1):
+        sizes = block_sizes(T_, R_, part)
+        rowsteps = nnzJ = gram = fact = n_c = 0
+        for b, n in enumerate(sizes):
+            last = b == len(sizes) - 1
+            r_b = n if last else (n - 1) + X
+            m_b = n * S_ * V + (V0 if b == 0 else 0)
+            ks = list(range(1, n + 1)) if last else list(range(1, n)) + [n] * X
+            rowsteps += sum(ks) * S_
+            nnzJ += r_b * (m_b + U)
+            gram += r_b * (r_b + 1) * m_b
+            fact += r_b ** 3 / 3 + 2 * r_b ** 2 * U + 2 * r_b * U ** 2
+            n_c += r_b
+        fact += U ** 3 / 3
+        solve = 4 * n_c * (6 + U)
+        constr = N * F_f + n_c
+        jac = N * (F_f + F_J + F_Z) + rowsteps * adj
+        chol_gram = gram + fact
+        nsc = 4 * nnzJ + solve
+        qn_iter = constr + solve + 2 * nnzJ
+        grad_logdet = jac + chol_gram + rowsteps * F_2 + 2 * gram
+        out.append(grad_logdet + iters_per_step * qn_iter + 3 * nsc + 20 * dim_q)
+    return {"flops": 0.5 * (out[0] + out[1]), "flops_partition0": out[0], "bytes_min": 8 * (4 * dim_q + T_ * X)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -110,19 +192,50 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from manifold_mcmc_for_diffusions_b200 import BatchedChains
 
-    n = args.chains
-    y, u, v0, xo = init_inputs(n, rank)
+    from manifold_mcmc_for_diffusions_b200 import diagnostics, example_models, parallel
+
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank"
+    strong = args.scaling == "strong"
+    if strong:
+        # BASELINE.json config 5: a fixed population sharded over the ranks (contiguous ranges, Philox streams and
+        # initial states keyed by the GLOBAL chain index)
+        lo, hi = parallel.shard_range(args.total_chains, rank, world)
+        n = hi - lo
+        y, u, v0, xo = init_inputs_global(lo, hi)
+        seed, chain0 = SEED, lo
+    else:
+        n = args.chains
+        y, u, v0, xo = init_inputs(n, rank)
+        seed, chain0 = SEED + rank, rank * n
     bc = BatchedChains("fhn", OBS_INTERVAL, S, R, y, 4, n, device=local_rank)
-    bc.set_chain_offset(rank * n)   # disjoint Philox streams per rank
+    bc.set_chain_offset(chain0)   # disjoint Philox streams per rank
     bc.opts.solver = 1 if args.solver == "newton" else 0
     if args.regroup:
         bc.set_chain_regrouping(True)   # per-chain results unchanged; chains with similar iteration counts share tiles
     bc.init_linear_interpolation(u, v0, xo, 0)
+    del u, v0, xo
     L = args.traj_len
-    # untimed burn-in towards the typical set (the linear-interpolation states are far in the tails)
-    for it in range(args.burnin):
-        bc.hmc_transition(args.burnin_dt, L, SEED + rank, it)
+    traces = []
+
+    def trace():
+        # the reference scripts' traced scalars (fhn_model_noiseless_obs_chmc_experiment.py:102-117): a D2H read of
+        # [u | v_0] of every chain after every transition
+        uu, vv = bc.get_head()
+        z = example_models.fhn.generate_z(uu)
+        traces.append(np.concatenate((z, example_models.fhn.generate_x_0(z, vv)), -1))
+
+    # untimed burn-in towards the typical set (the linear-interpolation states are far in the tails) ...
+    n_diag = min(args.diag_transitions, args.burnin) if not args.regroup else 0
+    for it in range(args.burnin - n_diag):
+        bc.hmc_transition(args.burnin_dt, L, seed, it)
     bc.synchronize()
+    # ... whose last transitions run at the bench step size with traces: the draws R-hat / ESS are computed on
+    t_diag = time.perf_counter()
+    for it in range(args.burnin - n_diag, args.burnin):
+        bc.hmc_transition(args.dt, L, seed, it)
+        trace()
+    bc.synchronize()
+    diag_wall = time.perf_counter() - t_diag
 
     def barrier():
         if world > 1:
@@ -132,13 +245,15 @@ def run_ours(args):
 
     it_counter = [args.burnin]
 
-    def do_steps(k):
+    def do_steps(k, traced=False):
         done = 0
         while done < k:
             m = min(L, k - done)
-            bc.transition_begin(SEED + rank, it_counter[0])
+            bc.transition_begin(seed, it_counter[0])
             bc.transition_steps(args.dt, m)          # m leapfrog steps, one fused launch
-            bc.transition_end(SEED + rank, it_counter[0], True)
+            bc.transition_end(seed, it_counter[0], True)
+            if traced and m == L and n_diag:
+                trace()
             it_counter[0] += 1
             done += m
 
@@ -151,7 +266,7 @@ def run_ours(args):
     bc.profile_enable(True, 64 * args.steps + 64)
     barrier()
     bc.timer_start()
-    do_steps(args.steps)
+    do_steps(args.steps, traced=True)       # trace read-backs stay inside the timed region
     ms = bc.timer_stop_ms()
     barrier()
     sampler.stop_flag = True
@@ -184,18 +299,22 @@ def run_ours(args):
         sl = slice(bounds[i], bounds[i + 1])
         pins.append([torch.from_numpy(np.ascontiguousarray(a[sl])).pin_memory().numpy() for a in (q_h, p_h, x_h)])
 
+    # page-locked result buffers: the step's RESULT (new q, p of every chain) comes back to the host every step
+    outs = [[torch.empty(a.shape, dtype=torch.float64).pin_memory().numpy() for a in pin[:2]] for pin in pins]
+
     def issue(i):
         qn_, pn_, xn_ = pins[i]
         parts[i].set_state(qn_, xn_, part, p=pn_, blocking=False)   # H2D of this step's inputs (async, own stream)
         parts[i].leapfrog_step(args.dt)
+        parts[i].get_state_into(outs[i][0], outs[i][1], None, blocking=False)   # D2H of the new q, p (async)
 
     def collect(i):
-        inf = parts[i].step_info()                # D2H of the step's result (status, iterations, reverse dist)
+        inf = parts[i].step_info()                # D2H of status / iterations / reverse distance; synchronises
         return int((inf["status"] == 0).sum())
 
     def e2e_loop(k):
         # software pipeline over the parts: as soon as a part's results are back its next upload + step are queued,
-        # so its copy runs while the other part computes
+        # so its copies run while the other part computes
         good = 0
         for i in range(n_parts):
             issue(i)
@@ -214,11 +333,44 @@ def run_ours(args):
         b.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert all(np.isfinite(o[0][0, :8]).all() for o in outs)
     h2d = int(sum(a.nbytes for pin in pins for a in pin))
-    d2h = int(n * (4 + 4 + 4 + 8))
+    d2h = int(sum(a.nbytes for o in outs for a in o) + n * (4 + 4 + 4 + 8))
     if n_parts > 1:
         for b in parts:
             b.close()
+
+    # ---- cross-chain diagnostics: ONE NCCL all-gather of the traced scalars, then rank-normalised split-R-hat and
+    # bulk ESS over the whole population on rank 0 (scripts/utils.py:351-381) ----
+    diag = None
+    if traces:
+        tr_local = np.stack(traces, 1)                                   # [chains, draws, 6]
+        t_g = time.perf_counter()
+        tr_all = parallel.allgather_chains(tr_local.reshape(n, -1))
+        if world > 1:
+            torch.cuda.synchronize()
+        gather_s = time.perf_counter() - t_g
+        dw = torch.tensor([diag_wall], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dw, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            tr_all = tr_all.reshape(tr_all.shape[0], len(traces), 6)
+            t_d = time.perf_counter()
+            names = ["sigma", "epsilon", "gamma", "beta", "x_0[0]", "x_0[1]"]
+            summ = diagnostics.summary({nm: tr_all[:, :, i] for i, nm in enumerate(names)})
+            ess_min = min(v["ess_bulk"] for v in summ.values())
+            # ESS/s: effective samples of ALL traced draws over the wall time of the traced transitions, scaled from
+            # the separately clocked diagnostic transitions (same step size, trajectory length, traces read back)
+            per_tr = dw.item() / max(n_diag, 1)
+            diag = {
+                "chains": int(tr_all.shape[0]), "draws_per_chain": len(traces),
+                "rhat_max": max(v["r_hat"] for v in summ.values()), "ess_bulk_min": ess_min,
+                "ess_per_s": ess_min / (per_tr * len(traces) + gather_s),
+                "wall_s_per_traced_transition": per_tr,
+                "allgather_ms": gather_s * 1e3, "allgather_backend": dist.get_backend() if world > 1 else "none (1 rank)",
+                "diagnostics_host_s": time.perf_counter() - t_d,
+                "summary": {k: {kk: round(vv, 5) for kk, vv in v.items()} for k, v in summ.items()},
+            }
 
     vals = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
     tot = torch.tensor([float(ok), float(ok_e2e), float(launches)], device="cuda", dtype=torch.float64)
@@ -236,14 +388,65 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        # roofline of the dominant kernel (k_leapfrog: every phase of the step fused in one launch).
-        # Algorithmic bytes: doubles moved per SDE time step and chain, summed over the
-        # phases of one leapfrog step, with the MEASURED number of quasi-Newton sweeps.
+        try:
+            fp64 = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_b200.json")))
+            fp64_peak = float(fp64["fp64_fma_peak_tflops"])
+            fp64_src = "measured FMA microbenchmark (profiles/fp64_peak_b200.json)"
+        except Exception:
+            fp64_peak, fp64_src = 37.2, "nominal 148 SM x 64 DFMA/clk x 1.965 GHz"
+        try:
+            traffic_rec = json.load(open(os.path.join(ROOT, "profiles", "r2_leapfrog_traffic.json")))
+        except Exception:
+            traffic_rec = None
+        # Roofline of the dominant kernel (k_leapfrog: every phase of the step fused in one launch), three views:
+        #  (1) SURVEY.md 8(d) work model: algorithmic FP64 flops with the MEASURED iteration counts vs the measured FP64
+        #      peak, and the unavoidable state traffic (read q, p, x_obs, write q, p) vs the measured HBM bandwidth;
+        #  (2) this implementation's streaming model (the compressed Jacobian is stored and re-read);
+        #  (3) DRAM bytes actually moved (ncu dram__bytes of the committed capture, per successful chain-step).
+        # `bound` follows from (1): arithmetic intensity = flops / unavoidable bytes against the ridge point.
         iters_per_step = qn_iters / max(ok, 1)          # forward + reverse iterations per successful step
+        wm = work_model(iters_per_step)
+        lf_s = ms_lf * 1e-3
+        lf_launch_s = lf_s / max(n_lf, 1)
+        steps_per_launch = ok / max(n_lf, 1)
+        tflops = wm["flops"] * ok / lf_s / 1e12 if lf_s > 0 else 0.0
+        floor_gbs = wm["bytes_min"] * ok / lf_s / 1e9 if lf_s > 0 else 0.0
         alg_bytes_step = leapfrog_bytes_per_chain_step(iters_per_step, newton=args.solver == "newton")
-        alg_bytes = alg_bytes_step * ok                   # over the timed region, this rank
-        lf_ms = ms_lf
-        achieved = alg_bytes / (lf_ms * 1e-3) / 1e9 if lf_ms > 0 else 0.0
+        impl_gbs = alg_bytes_step * ok / lf_s / 1e9 if lf_s > 0 else 0.0
+        intensity = wm["flops"] / wm["bytes_min"]
+        ridge = fp64_peak * 1e12 / (hbm_peak * 1e9)
+        bound = "fp64" if intensity > ridge else "hbm"
+        dram_step = traffic_rec["dram_bytes_per_chain_step"] if traffic_rec else None
+        roofline = {
+            "bound": bound,
+            "kernel": "k_leapfrog (fused constrained leapfrog step: projections, quasi-Newton solves, linearise + grad log-det)",
+            "achieved": tflops if bound == "fp64" else floor_gbs,
+            "peak": fp64_peak if bound == "fp64" else hbm_peak,
+            "unit": "TFLOP/s" if bound == "fp64" else "GB/s",
+            "frac": (tflops / fp64_peak) if bound == "fp64" else floor_gbs / hbm_peak,
+            "traffic": (dram_step * steps_per_launch) if dram_step else None,
+            "traffic_source": traffic_rec["source"] if traffic_rec else None,
+            "peak_source": fp64_src if bound == "fp64" else peak_src,
+            "bound_reason": "SURVEY 8(d) work model: %.1f flop per unavoidable byte vs ridge %.1f flop/B" % (intensity, ridge),
+            "flops_per_chain_step": wm["flops"],
+            "alg_bytes_floor_per_chain_step": wm["bytes_min"],
+            "alg_bytes_floor_per_launch": wm["bytes_min"] * steps_per_launch,
+            "fp64_frac": tflops / fp64_peak,
+            "hbm": {
+                "peak_gbs": hbm_peak, "peak_source": peak_src,
+                "floor_gbs": floor_gbs, "floor_frac": floor_gbs / hbm_peak,
+                "impl_model_bytes_per_chain_step": alg_bytes_step, "impl_model_gbs": impl_gbs,
+                "impl_model_frac": impl_gbs / hbm_peak,
+                "dram_bytes_per_chain_step_ncu": dram_step,
+                "dram_gbs": (dram_step * ok / lf_s / 1e9) if dram_step and lf_s > 0 else None,
+                "dram_frac": (dram_step * ok / lf_s / 1e9 / hbm_peak) if dram_step and lf_s > 0 else None,
+                "traffic_over_floor": (dram_step / wm["bytes_min"]) if dram_step else None,
+            },
+            "kernel_ms_per_launch": lf_launch_s * 1e3,
+            "chain_steps_per_launch": steps_per_launch,
+            "launches": n_lf,
+            "share_of_timed_region": ms_lf / ms,
+        }
         out = {
             "metric": METRIC,
             "value": ok_tot / (ms_max * 1e-3),
@@ -253,50 +456,43 @@ def run_ours(args):
             "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
             "config": {
-                "workload": WORKLOAD if args.solver == "quasi-newton" else WORKLOAD.replace("quasi-Newton", "Newton"),
+                "workload": (WORKLOAD if args.solver == "quasi-newton" else WORKLOAD.replace("quasi-Newton", "Newton"))
+                + ("; BASELINE config 5: %d chains sharded over the GPUs" % args.total_chains if strong else ""),
+                "total_chains": args.total_chains if strong else n * world,
                 "chains_per_gpu": n,
+                "cpu_affinity": affinity,
                 "chains_per_cta_tile": bc.chains_per_tile(),
                 "chain_regrouping": bool(args.regroup),
                 "step_size": args.dt,
                 "traj_len": L,
                 "burnin_transitions": args.burnin,
-                "l2": "per-step working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2)"
+                "l2": "per-step working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)"
                 % (n * 450e3 / 1e9),
                 "step_success_frac": ok_tot / (n * world * args.steps),
                 "accept_stat_last": float(st["accept_stat"].mean()),
                 "qn_iters_per_step": iters_per_step,
             },
-            "roofline": {
-                "bound": "hbm",
-                "kernel": "k_leapfrog (fused constrained leapfrog step: projections, quasi-Newton solves, linearise + grad log-det)",
-                "achieved": achieved,
-                "peak": hbm_peak,
-                "unit": "GB/s",
-                "frac": achieved / hbm_peak,
-                "traffic": None,
-                "peak_source": peak_src,
-                "alg_bytes_per_chain_step": alg_bytes_step,
-                "kernel_ms_per_launch": lf_ms / max(n_lf, 1),
-                "launches": n_lf,
-                "share_of_timed_region": lf_ms / ms,
-            },
+            "roofline": roofline,
             "e2e": {
                 "value": ok_e2e_tot / (e2e_ms_max * 1e-3),
                 "unit": UNIT,
                 "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps,
-                "pipeline": "%d BatchedChains objects of %d chains, upload of one overlapped with compute of the other"
+                "result_read_back": "new q and p of every chain (page-locked host arrays) + status words, every step",
+                "pipeline": "%d BatchedChains objects of %d chains, copies of one overlapped with compute of the other"
                 % (n_parts, n // n_parts) if n_parts > 1 else "none",
             },
             "gpu_launches": int(launches_tot),
             "clocks": sampler.summary(),
         }
+        if diag is not None:
+            out["diagnostics"] = diag
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, dt=args.dt, L=L, burnin=args.burnin,
                                                burnin_dt=args.burnin_dt)
@@ -433,7 +629,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chains", type=int, default=16384, help="chains per GPU")
+    ap.add_argument("--chains", type=int, default=16384, help="chains per GPU (with --scaling weak)")
     ap.add_argument("--dt", type=float, default=0.1)
     ap.add_argument("--traj-len", type=int, default=8)
     ap.add_argument("--burnin", type=int, default=60)
@@ -448,6 +644,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-pipeline", type=int, default=2,
                     help="number of BatchedChains objects the end-to-end loop alternates between (1 = no overlap)")
+    ap.add_argument("--scaling", choices=("weak", "strong"), default="strong",
+                    help="strong (default): BASELINE.json config 5, --total-chains sharded over the ranks; weak: --chains "
+                         "per GPU")
+    ap.add_argument("--total-chains", type=int, default=65536)
+    ap.add_argument("--diag-transitions", type=int, default=24,
+                    help="last burn-in transitions run at --dt with traces (R-hat / ESS are computed on them and on the "
+                         "timed transitions)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

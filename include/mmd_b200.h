@@ -79,6 +79,25 @@ int mmd_set_momentum(mmd_handle h, const double* p);
 int mmd_set_state_dev(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_obs_seq_dev,
                       int partition);
 int mmd_get_state_dev(mmd_handle h, double* q_dev, double* p_dev, double* x_obs_seq_dev);
+/* Stream ordering for the device-pointer path.  All work of a handle runs on its own non-blocking CUDA stream.
+ *   mmd_get_stream   the handle's cudaStream_t: a DLPack consumer passes it to the producer's
+ *                    __dlpack__(stream=...) so that the producer orders its pending writes before our reads;
+ *   mmd_wait_stream  the handle's stream waits for everything queued so far on `other_stream` (producer side,
+ *                    for callers that hand over raw pointers instead of going through the DLPack protocol);
+ *   mmd_stream_wait  `other_stream` waits for everything queued so far on the handle's stream (consumer side of
+ *                    mmd_get_state_dev).
+ * Without one of these (or mmd_synchronize) the device-pointer calls are NOT ordered against other streams. */
+void* mmd_get_stream(mmd_handle h);
+int mmd_get_device(mmd_handle h);
+int mmd_wait_stream(mmd_handle h, void* other_stream);
+int mmd_stream_wait(mmd_handle h, void* other_stream);
+/* [u | v_0] of every chain's current position, [n_chains][dim_u + dim_v_0] (host array): the inputs of the reference
+ * scripts' trace functions (generate_z(u), generate_x_0(z, v_0); fhn_model_noiseless_obs_chmc_experiment.py:102-117)
+ * without reading back the whole position.  Blocking. */
+int mmd_get_head(mmd_handle h, double* out);
+/* mmd_get_state without the final synchronisation (separate staging buffers per array; the host arrays are valid
+ * after mmd_synchronize or any blocking call; page-locked arrays overlap the copies with other handles' work) */
+int mmd_get_state_async(mmd_handle h, double* q, double* p, double* x_obs_seq);
 int mmd_get_partition(mmd_handle h);
 /* chains per CTA tile chosen at create time (tuning knob MMD_CPB; informational) */
 int mmd_chains_per_tile(mmd_handle h);

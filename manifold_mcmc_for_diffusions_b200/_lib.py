@@ -66,6 +66,12 @@ SIGNATURES = {
     "mmd_set_momentum": (C.c_int, [_H, _dp]),
     "mmd_set_state_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "mmd_get_state_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mmd_get_stream": (C.c_void_p, [_H]),
+    "mmd_get_device": (C.c_int, [_H]),
+    "mmd_wait_stream": (C.c_int, [_H, C.c_void_p]),
+    "mmd_stream_wait": (C.c_int, [_H, C.c_void_p]),
+    "mmd_get_state_async": (C.c_int, [_H, _dp, _dp, _dp]),
+    "mmd_get_head": (C.c_int, [_H, _dp]),
     "mmd_chains_per_tile": (C.c_int, [_H]),
     "mmd_set_chain_offset": (C.c_int, [_H, C.c_int]),
     "mmd_get_partition": (C.c_int, [_H]),

@@ -62,6 +62,8 @@ class BatchedChains:
         self._h = C.c_void_p()
         check(self._L.mmd_create(C.byref(cfg), C.byref(self._h)))
         self.n_chains = int(n_chains)
+        self._dim_u = int(dim_u)
+        self._dim_v_0 = {"fhn": 2, "fhn_notebook": 2, "sir": 1}[model]
         self._sigma_fixed = float(sigma_fixed)
         self.dim_q = self._L.mmd_dim_q(self._h)
         self.num_partition = self._L.mmd_num_partition(self._h)
@@ -114,6 +116,75 @@ class BatchedChains:
         check(fn(self._h, _dp(q), None if pp is None else _dp(pp), _dp(x), int(partition)))
         self._dim_x = x.shape[2]
 
+    # ---- zero-copy device path (DLPack) ---------------------------------------------------
+    @property
+    def stream(self):
+        """The handle's cudaStream_t as an int (what a DLPack producer expects in ``__dlpack__(stream=...)``)."""
+        return int(self._L.mmd_get_stream(self._h) or 0)
+
+    def set_state_dlpack(self, q, x_obs_seq, partition=0, p=None):
+        """`set_state` from CUDA float64 arrays of any DLPack producer (torch, CuPy, JAX ...) in the reference layout
+        (`q`, `p`: [n_chains, dim_q]; `x_obs_seq`: [n_chains, T, dim_x]) without a host round trip: the device
+        pointers go to ``mmd_set_state_dev``, which re-tiles on the GPU.  Ordering follows the DLPack protocol: the
+        producers are handed this object's stream and make their pending writes visible to it; the borrowed tensors
+        are released after the packing kernels have been queued and the stream has been synchronised."""
+        from ._dlpack import DeviceArray
+
+        dev = int(self._L.mmd_get_device(self._h))
+        st = self.stream or 1
+        arrs = []
+        try:
+            qa = DeviceArray(q, st, dev, (self.n_chains, self.dim_q), "q")
+            arrs.append(qa)
+            xa = DeviceArray(x_obs_seq, st, dev, None, "x_obs_seq")
+            arrs.append(xa)
+            if xa.shape[0] != self.n_chains or len(xa.shape) != 3 or xa.shape[1] != self.num_obs:
+                raise ValueError(f"x_obs_seq: shape {xa.shape} is not [n_chains, num_obs, dim_x]")
+            pa = None
+            if p is not None:
+                pa = DeviceArray(p, st, dev, (self.n_chains, self.dim_q), "p")
+                arrs.append(pa)
+            check(self._L.mmd_set_state_dev(self._h, qa.ptr, None if pa is None else pa.ptr, xa.ptr, int(partition)))
+            self._dim_x = int(xa.shape[2])
+            self.synchronize()      # the producers may reuse their buffers as soon as we return
+        finally:
+            for a in arrs:
+                a.release()
+
+    def get_state_dlpack(self, q_out=None, p_out=None, x_out=None):
+        """`get_state` into caller-provided CUDA float64 arrays (DLPack producers, reference layout): device-to-device
+        un-tiling via ``mmd_get_state_dev``, no host copy.  Returns after the handle's stream has finished."""
+        from ._dlpack import DeviceArray
+
+        dev = int(self._L.mmd_get_device(self._h))
+        st = self.stream or 1
+        arrs = []
+        try:
+            ptrs = []
+            for obj, shape, nm in ((q_out, (self.n_chains, self.dim_q), "q_out"), (p_out, (self.n_chains, self.dim_q), "p_out"),
+                                   (x_out, (self.n_chains, self.num_obs, self._dim_x), "x_out")):
+                if obj is None:
+                    ptrs.append(None)
+                else:
+                    a = DeviceArray(obj, st, dev, shape, nm)
+                    arrs.append(a)
+                    ptrs.append(a.ptr)
+            check(self._L.mmd_get_state_dev(self._h, *ptrs))
+            self.synchronize()
+        finally:
+            for a in arrs:
+                a.release()
+
+    def get_state_into(self, q, p, x_obs_seq, blocking=True):
+        """`get_state` into caller-owned host arrays (C-contiguous float64; page-locked for real overlap).
+        blocking=False queues the copies on the handle's stream and returns: valid after `synchronize()`."""
+        for a in (q, p, x_obs_seq):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("get_state_into needs C-contiguous float64 arrays")
+        fn = self._L.mmd_get_state if blocking else self._L.mmd_get_state_async
+        check(fn(self._h, None if q is None else _dp(q), None if p is None else _dp(p),
+                 None if x_obs_seq is None else _dp(x_obs_seq)))
+
     def set_chain_regrouping(self, on=True):
         """Throughput option: at every partition switch re-assign the chains to CTA tiles sorted by the projection
         iteration count of their last step (slow chains then delay only each other).  Per-chain results are
@@ -141,6 +212,18 @@ class BatchedChains:
         x = np.empty((self.n_chains, self.num_obs, self._dim_x))
         check(self._L.mmd_get_state(self._h, _dp(q), _dp(p), _dp(x)))
         return q, p, x
+
+    def get_head(self, dim_v_0=None):
+        """(u, v_0) of every chain's current position -- what the reference scripts' trace functions need
+        (`generate_z(u)`, `generate_x_0(z, v_0)`) -- without reading back the whole position."""
+        rows = self.dim_q - self._body_and_noise_rows()
+        out = np.empty((self.n_chains, rows))
+        check(self._L.mmd_get_head(self._h, _dp(out)))
+        du = self._dim_u
+        return out[:, :du], out[:, du:]
+
+    def _body_and_noise_rows(self):
+        return self.dim_q - (self._dim_u + self._dim_v_0)
 
     # ---- system ops --------------------------------------------------------------------
     def linearize(self, with_grad=True):

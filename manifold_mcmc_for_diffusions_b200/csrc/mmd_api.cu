@@ -13,6 +13,20 @@ std::string& mmd_err() {
 
 namespace {
 
+// Every entry point runs with the handle's device current and restores the caller's device on exit: handles of
+// several GPUs can be driven from one host thread, and a caller (torch, ...) that switched devices is unaffected.
+struct DevGuard {
+  int prev, dev;
+  explicit DevGuard(int d) : prev(-1), dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DevGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+#define MMD_GUARD(h) DevGuard guard_((h)->device)
+
 template <class T>
 int dalloc(mmd_handle h, T** p, size_t n) {
   if (n == 0) n = 1;
@@ -124,8 +138,17 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
                        : cfg->model == MMD_MODEL_SIR ? mmd_ops_sir()
                        : cfg->model == MMD_MODEL_FHN_NOTEBOOK ? mmd_ops_fhn_notebook() : nullptr;
   if (!ops) FAIL("unknown model id");
+  {
+    // the smallest instantiation that holds the problem's blocks (fewer rows = less per-thread state)
+    const int T_ = cfg->num_obs, R_ = cfg->num_obs_per_subseq;
+    const int nz_ = cfg->noise != MMD_NOISE_NONE;
+    if (cfg->model == MMD_MODEL_FHN && R_ > 0 && R_ < T_ && !getenv("MMD_FHN_WIDE")) {
+      const mmd_ops* small = mmd_ops_fhn_r5();
+      if (R_ - 1 + nz_ + small->X <= small->nrmax && R_ <= small->rmax) ops = small;
+    }
+  }
   if (cfg->device < 0 || cfg->device >= ndev) FAIL("bad device ordinal");
-  CK(cudaSetDevice(cfg->device));
+  DevGuard guard_(cfg->device);
   const int NRMAX = ops->nrmax, RMAX = ops->rmax;
   const int T = cfg->num_obs, S = cfg->num_steps_per_obs;
   int R = cfg->num_obs_per_subseq;
@@ -140,6 +163,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   mmd_handle h = new mmd_handle_s();
   memset(&h->d, 0, sizeof(Dims));
   h->model = cfg->model;
+  h->device = cfg->device;
   h->ops = ops;
   h->X = ops->X; h->V = ops->V; h->Z = ops->Z; h->V0 = ops->V0;
   h->nrmax = NRMAX;
@@ -199,6 +223,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
+  CK(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
   h->launches = 0;
   h->prof_on = false;
   h->prof_used = 0;
@@ -232,6 +257,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   rc |= dalloc(h, &Sx.kap, 2 * Sx.s_xend);
   rc |= dalloc(h, &Sx.A, 2 * Sx.s_A);
   rc |= dalloc(h, &Sx.L, 2 * Sx.s_L);
+  rc |= dalloc(h, &Sx.Dinv, 2 * Sx.s_L);
   rc |= dalloc(h, &Sx.DinvA, 2 * Sx.s_A);
   rc |= dalloc(h, &Sx.LC, 2 * Sx.s_LC);
   rc |= dalloc(h, &Sx.gradld, 2 * Sx.s_q);
@@ -267,6 +293,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   const size_t stage_n = (size_t)d.n_chains * (size_t)(d.dim_q > (int)(T * X) ? d.dim_q : T * X);
   rc |= dalloc(h, &h->stage, stage_n);
   rc |= dalloc(h, &h->stage2, stage_n);
+  rc |= dalloc(h, &h->stage3, (size_t)d.n_chains * (T * X > (size_t)d.rows_head ? T * X : (size_t)d.rows_head));
   rc |= dalloc(h, &h->tpbuf, (size_t)NRMAX * tpu);
   rc |= dalloc(h, &h->hbuf, nc);
   rc |= dalloc(h, &h->h0buf, nc);
@@ -284,12 +311,14 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
 }
 
 int mmd_destroy(mmd_handle h) {
+  MMD_GUARD(h);
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->ev_order);
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -308,6 +337,9 @@ int mmd_set_chain_offset(mmd_handle h, int chain0) { h->chain0 = chain0; return 
 static int set_state_dev_impl(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_dev,
                               int partition) {
   if (partition < 0 || partition >= h->d.num_partition) FAIL("bad partition");
+  if (!q_dev && partition != h->partition)
+    FAIL("set_state: the partition can only change together with a new position (the resident q is tiled for the "
+         "current partition; use mmd_switch_partition)");
   if (reset_flags(h)) return -2;
   h->partition = partition;
   h->lin_valid = false;
@@ -336,23 +368,28 @@ static int set_state_host(mmd_handle h, const double* q, const double* p, const 
 }
 
 int mmd_set_state(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition) {
+  MMD_GUARD(h);
   return set_state_host(h, q, p, x_obs_seq, partition, true);
 }
 
 int mmd_set_state_async(mmd_handle h, const double* q, const double* p, const double* x_obs_seq, int partition) {
+  MMD_GUARD(h);
   return set_state_host(h, q, p, x_obs_seq, partition, false);
 }
 
 int mmd_set_state_dev(mmd_handle h, const double* q_dev, const double* p_dev, const double* x_dev, int partition) {
+  MMD_GUARD(h);
   return set_state_dev_impl(h, q_dev, p_dev, x_dev, partition);
 }
 
 int mmd_set_momentum(mmd_handle h, const double* p) {
+  MMD_GUARD(h);
   if (h2d_stage(h, p, h->stage2, (size_t)h->d.n_chains * h->d.dim_q)) return -2;
   return DISPATCH(h, pack(h, h->stage2, h->S.p, h->S.s_q, 0));
 }
 
 int mmd_get_state(mmd_handle h, double* q, double* p, double* x_obs_seq) {
+  MMD_GUARD(h);
   const size_t nq = (size_t)h->d.n_chains * h->d.dim_q;
   if (q) {
     if (DISPATCH(h, unpack(h, h->stage, h->S.q, h->S.s_q, 0))) return -2;
@@ -369,7 +406,70 @@ int mmd_get_state(mmd_handle h, double* q, double* p, double* x_obs_seq) {
   return 0;
 }
 
+// Same as mmd_get_state without the final synchronisation: the three results go through separate staging buffers,
+// the copies are queued on the handle's stream and the host arrays (page-locked for real overlap) are valid after
+// mmd_synchronize or any blocking call.
+int mmd_get_state_async(mmd_handle h, double* q, double* p, double* x_obs_seq) {
+  MMD_GUARD(h);
+  const size_t nq = (size_t)h->d.n_chains * h->d.dim_q;
+  if (q) {
+    if (DISPATCH(h, unpack(h, h->stage, h->S.q, h->S.s_q, 0))) return -2;
+    CK(cudaMemcpyAsync(q, h->stage, nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (p) {
+    if (DISPATCH(h, unpack(h, h->stage2, h->S.p, h->S.s_q, 0))) return -2;
+    CK(cudaMemcpyAsync(p, h->stage2, nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (x_obs_seq) {
+    if (unpack_chain(h, h->d.T * h->X, h->stage3, h->W.xobs)) return -2;
+    CK(cudaMemcpyAsync(x_obs_seq, h->stage3, (size_t)h->d.n_chains * h->d.T * h->X * sizeof(double),
+                       cudaMemcpyDeviceToHost, h->stream));
+  }
+  return 0;
+}
+
+// Ordering against other CUDA streams (DLPack producers / consumers).  mmd_get_stream returns the handle's
+// cudaStream_t: a DLPack consumer passes it to the producer's __dlpack__(stream=...).  mmd_wait_stream makes the
+// handle's stream wait for the work queued so far on `other`; mmd_stream_wait makes `other` wait for the handle.
+void* mmd_get_stream(mmd_handle h) { return (void*)h->stream; }
+int mmd_get_device(mmd_handle h) { return h->device; }
+int mmd_wait_stream(mmd_handle h, void* other) {
+  MMD_GUARD(h);
+  CK(cudaEventRecord(h->ev_order, (cudaStream_t)other));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_order, 0));
+  return 0;
+}
+int mmd_stream_wait(mmd_handle h, void* other) {
+  MMD_GUARD(h);
+  CK(cudaEventRecord(h->ev_order, h->stream));
+  CK(cudaStreamWaitEvent((cudaStream_t)other, h->ev_order, 0));
+  return 0;
+}
+
+// [u | v_0] of every chain's current position (the traced quantities of the reference's scripts are functions of
+// these: generate_z(u), generate_x_0(z, v_0), scripts/fhn_model_noiseless_obs_chmc_experiment.py:102-117), without
+// un-tiling the whole position: dim_u + dim_v_0 doubles per chain instead of dim_q.
+static __global__ void k_get_head(mmd::Dims d, const double* __restrict__ qbase, long long s_q,
+                                  const int* __restrict__ cur, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.n_chains) return;
+  const int tile = c >> d.lcpb, cl = c & (d.cpb - 1);
+  const double* src = qbase + (long long)cur[c] * s_q + ((long long)tile * d.rows_head) * d.cpb + cl;
+  for (int r = 0; r < d.rows_head; ++r) out[(long long)c * d.rows_head + r] = src[r * d.cpb];
+}
+int mmd_get_head(mmd_handle h, double* out) {
+  MMD_GUARD(h);
+  if (!out) FAIL("null argument");
+  if (h->regroup) FAIL("mmd_get_head: not available with chain regrouping (slot order)");
+  const int n = h->d.n_chains;
+  k_get_head<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d, h->S.q, h->S.s_q, h->S.cur, h->stage3);
+  h->launches++;
+  CK(cudaGetLastError());
+  return d2h_sync(h, out, h->stage3, (size_t)n * h->d.rows_head);
+}
+
 int mmd_get_state_dev(mmd_handle h, double* q_dev, double* p_dev, double* x_dev) {
+  MMD_GUARD(h);
   if (q_dev) { if (DISPATCH(h, unpack(h, q_dev, h->S.q, h->S.s_q, 0))) return -2; }
   if (p_dev) { if (DISPATCH(h, unpack(h, p_dev, h->S.p, h->S.s_q, 0))) return -2; }
   if (x_dev) { if (unpack_chain(h, h->d.T * h->X, x_dev, h->W.xobs)) return -2; }
@@ -377,6 +477,7 @@ int mmd_get_state_dev(mmd_handle h, double* q_dev, double* p_dev, double* x_dev)
 }
 
 int mmd_linearize(mmd_handle h, int with_grad) {
+  MMD_GUARD(h);
   CK(cudaMemsetAsync(h->W.status, 0, (size_t)h->d.n_tiles * h->d.cpb * sizeof(int), h->stream));
   int rc = DISPATCH(h, point(h, 0, with_grad));
   if (rc) return rc;
@@ -385,6 +486,7 @@ int mmd_linearize(mmd_handle h, int with_grad) {
 }
 
 int mmd_constr(mmd_handle h, double* c_out) {
+  MMD_GUARD(h);
   int rc = DISPATCH(h, constr(h));
   if (rc) return rc;
   std::vector<double> buf((size_t)h->d.n_tiles * h->nrmax * h->d.nta);
@@ -394,6 +496,7 @@ int mmd_constr(mmd_handle h, double* c_out) {
 }
 
 int mmd_log_det_sqrt_gram(mmd_handle h, double* out) {
+  MMD_GUARD(h);
   if (!h->lin_valid) FAIL("call mmd_linearize first");
   const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
   std::vector<double> ld(2 * nc);
@@ -406,12 +509,14 @@ int mmd_log_det_sqrt_gram(mmd_handle h, double* out) {
 }
 
 int mmd_grad_log_det_sqrt_gram(mmd_handle h, double* out) {
+  MMD_GUARD(h);
   if (!h->lin_valid) FAIL("call mmd_linearize(with_grad=1) first");
   if (DISPATCH(h, unpack(h, h->stage, h->S.gradld, h->S.s_q, 0))) return -2;
   return d2h_sync(h, out, h->stage, (size_t)h->d.n_chains * h->d.dim_q);
 }
 
 int mmd_hamiltonian(mmd_handle h, double* out) {
+  MMD_GUARD(h);
   if (!h->lin_valid) FAIL("call mmd_linearize first");
   int rc = DISPATCH(h, hamiltonian(h, 0, h->hbuf));
   if (rc) return rc;
@@ -421,11 +526,13 @@ int mmd_hamiltonian(mmd_handle h, double* out) {
 static const FlowCoef NOFLOW = {0, 1.0, 0.0, 0.0};
 
 int mmd_project_momentum(mmd_handle h) {
+  MMD_GUARD(h);
   if (!h->lin_valid) FAIL("call mmd_linearize first");
   return DISPATCH(h, project(h, 0, PSEL_CUR, PSEL_CUR, 0.0, 0.0, NOFLOW));
 }
 
 int mmd_normal_space_component(mmd_handle h, const double* vct, double* out) {
+  MMD_GUARD(h);
   if (!h->lin_valid) FAIL("call mmd_linearize first");
   // use the work momentum as scratch: proj(vct) -> pw; nsc = vct - proj(vct)
   const size_t n = (size_t)h->d.n_chains * h->d.dim_q;
@@ -440,12 +547,14 @@ int mmd_normal_space_component(mmd_handle h, const double* vct, double* out) {
 }
 
 int mmd_update_x_obs_seq(mmd_handle h) {
+  MMD_GUARD(h);
   int rc = DISPATCH(h, gen_xobs(h));
   h->lin_valid = false;
   return rc;
 }
 
 int mmd_switch_partition(mmd_handle h) {
+  MMD_GUARD(h);
   // SwitchPartitionTransition.sample (:1279-1282): next partition, regenerate x_obs_seq from the position
   const int pa = h->partition, pb = (h->partition + 1) % h->d.num_partition;
   if (h->regroup) {
@@ -470,6 +579,7 @@ int mmd_switch_partition(mmd_handle h) {
 }
 
 int mmd_set_chain_regrouping(mmd_handle h, int on) {
+  MMD_GUARD(h);
   if (on && (h->adapting || h->W.use_dt_chain || !h->aux.empty()))
     FAIL("chain regrouping cannot be combined with per-chain step sizes / adaptation / NUTS work vectors");
   if (on && !h->slot_chain) {
@@ -492,17 +602,20 @@ int mmd_set_chain_regrouping(mmd_handle h, int on) {
 }
 
 int mmd_get_slot_chains(mmd_handle h, int* out) {
+  MMD_GUARD(h);
   for (int c = 0; c < h->d.n_chains; ++c) out[c] = h->regroup ? h->slot_chain_host[c] : c;
   return 0;
 }
 
 int mmd_sample_momentum(mmd_handle h, uint64_t seed, uint64_t offset) {
+  MMD_GUARD(h);
   if (!h->lin_valid) FAIL("call mmd_linearize first");
   if (DISPATCH(h, philox(h, seed, offset))) return -2;
   return DISPATCH(h, project(h, 0, PSEL_CUR, PSEL_CUR, 0.0, 0.0, NOFLOW));
 }
 
 int mmd_get_factor(mmd_handle h, const char* name, double* out, int* rows_out) {
+  MMD_GUARD(h);
   const Dims& d = h->d;
   const double* arr = nullptr;
   long long stride = 0;
@@ -581,10 +694,12 @@ static int leapfrog_impl(mmd_handle h, double dt, const mmd_integrator_opts* opt
 }
 
 int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts) {
+  MMD_GUARD(h);
   return leapfrog_impl(h, dt, opts, true);
 }
 
 int mmd_transition_begin(mmd_handle h, uint64_t seed, uint64_t iter) {
+  MMD_GUARD(h);
   int rc = mmd_linearize(h, 1); if (rc) return rc;               // also clears status
   rc = mmd_sample_momentum(h, seed, 2 * iter); if (rc) return rc;
   rc = DISPATCH(h, hamiltonian(h, 0, h->h0buf)); if (rc) return rc;
@@ -595,10 +710,12 @@ int mmd_transition_begin(mmd_handle h, uint64_t seed, uint64_t iter) {
 }
 
 int mmd_transition_steps(mmd_handle h, double dt, int n_steps, const mmd_integrator_opts* opts) {
+  MMD_GUARD(h);
   return leapfrog_impl(h, dt, opts, false, n_steps);
 }
 
 int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_partition) {
+  MMD_GUARD(h);
   int rc = DISPATCH(h, hamiltonian(h, 0, h->hbuf)); if (rc) return rc;
   k_decide<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->S, h->W, h->h0buf, h->hbuf, h->cur0, seed,
                                                               2 * iter + 1, h->chain0, h->accepted, h->accp,
@@ -621,6 +738,7 @@ int mmd_transition_end(mmd_handle h, uint64_t seed, uint64_t iter, int switch_pa
 }
 
 int mmd_set_step_sizes(mmd_handle h, const double* dt) {
+  MMD_GUARD(h);
   if (!dt) { h->W.use_dt_chain = 0; return 0; }
   if (h->regroup) FAIL("per-chain step sizes cannot be combined with chain regrouping");
   CK(cudaMemcpyAsync(h->W.dt_chain, dt, h->d.n_chains * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -630,6 +748,7 @@ int mmd_set_step_sizes(mmd_handle h, const double* dt) {
 }
 
 int mmd_get_step_sizes(mmd_handle h, double* dt) {
+  MMD_GUARD(h);
   CK(cudaMemcpyAsync(dt, h->W.dt_chain, h->d.n_chains * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -657,16 +776,19 @@ static int adapt_start_impl(mmd_handle h, const double* init_per_chain, double i
 
 int mmd_adapt_start(mmd_handle h, double init_step_size, double target, double reg_coefficient, double iter_decay,
                     double iter_offset) {
+  MMD_GUARD(h);
   return adapt_start_impl(h, nullptr, init_step_size, target, reg_coefficient, iter_decay, iter_offset);
 }
 
 int mmd_adapt_start_per_chain(mmd_handle h, const double* init_step_sizes, double target, double reg_coefficient,
                               double iter_decay, double iter_offset) {
+  MMD_GUARD(h);
   if (!init_step_sizes) FAIL("init_step_sizes is NULL");
   return adapt_start_impl(h, init_step_sizes, 1.0, target, reg_coefficient, iter_decay, iter_offset);
 }
 
 int mmd_adapt_stop(mmd_handle h, int pool) {
+  MMD_GUARD(h);
   if (!h->adapting) FAIL("mmd_adapt_start was not called");
   const long long nc = (long long)h->d.n_tiles * h->d.cpb;
   k_dual_averaging_finalize<<<1, 256, 0, h->stream>>>(h->d, h->ad_state, nc, pool, h->W.dt_chain);
@@ -693,6 +815,7 @@ static int resolve_vec(mmd_handle h, int id, double** ptr, int* live) {
 }
 
 int mmd_aux_reserve(mmd_handle h, int n_arrays) {
+  MMD_GUARD(h);
   if (h->regroup && n_arrays > 0) FAIL("work vectors cannot be combined with chain regrouping");
   while ((int)h->aux.size() < n_arrays) {
     double* p = nullptr;
@@ -703,6 +826,7 @@ int mmd_aux_reserve(mmd_handle h, int n_arrays) {
 }
 
 int mmd_vec_axpby(mmd_handle h, int dst, int src, double alpha, double beta, const int* mask) {
+  MMD_GUARD(h);
   double *pd, *ps;
   int ld, ls;
   if (resolve_vec(h, dst, &pd, &ld) || resolve_vec(h, src, &ps, &ls)) return -1;
@@ -716,6 +840,7 @@ int mmd_vec_axpby(mmd_handle h, int dst, int src, double alpha, double beta, con
 }
 
 int mmd_vec_uturn(mmd_handle h, int a, int dd, int c, int e, double* out1, double* out2) {
+  MMD_GUARD(h);
   double *pa, *pd, *pc, *pe;
   int la, ldd, lc, le;
   if (resolve_vec(h, a, &pa, &la) || resolve_vec(h, dd, &pd, &ldd) || resolve_vec(h, c, &pc, &lc) ||
@@ -731,6 +856,7 @@ int mmd_vec_uturn(mmd_handle h, int a, int dd, int c, int e, double* out1, doubl
 }
 
 int mmd_set_inactive(mmd_handle h, const int* mask, int clear_errors) {
+  MMD_GUARD(h);
   const int* m = upload_mask(h, mask);
   if (mask && !m) FAIL("mask upload failed");
   k_set_inactive<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->W, m, clear_errors);
@@ -740,6 +866,7 @@ int mmd_set_inactive(mmd_handle h, const int* mask, int clear_errors) {
 }
 
 int mmd_relinearize(mmd_handle h) {
+  MMD_GUARD(h);
   int rc = DISPATCH(h, point(h, 0, 1));
   if (rc) return rc;
   h->lin_valid = true;
@@ -747,6 +874,7 @@ int mmd_relinearize(mmd_handle h) {
 }
 
 int mmd_adapt_update(mmd_handle h, const double* accept_stat) {
+  MMD_GUARD(h);
   if (!h->adapting) FAIL("mmd_adapt_start was not called");
   CK(cudaMemcpyAsync(h->accp, accept_stat, h->d.n_chains * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   const long long nc = (long long)h->d.n_tiles * h->d.cpb;
@@ -760,6 +888,7 @@ int mmd_adapt_update(mmd_handle h, const double* accept_stat) {
 
 int mmd_hmc_transition(mmd_handle h, double dt, int n_leapfrog, uint64_t seed, uint64_t iter,
                        const mmd_integrator_opts* opts, int switch_partition) {
+  MMD_GUARD(h);
   // IndependentMomentumTransition + static-trajectory integration with Metropolis accept +
   // SwitchPartitionTransition (scripts/utils.py:292-301 with a static instead of dynamic trajectory)
   int rc = mmd_transition_begin(h, seed, iter); if (rc) return rc;
@@ -769,6 +898,7 @@ int mmd_hmc_transition(mmd_handle h, double dt, int n_leapfrog, uint64_t seed, u
 }
 
 int mmd_profile_enable(mmd_handle h, int on, int max_launches) {
+  MMD_GUARD(h);
   if (on) {
     while ((int)h->prof_ev.size() < 2 * max_launches) {
       cudaEvent_t e;
@@ -783,6 +913,7 @@ int mmd_profile_enable(mmd_handle h, int on, int max_launches) {
 }
 
 int mmd_profile_summary(mmd_handle h, int kid, int* count, double* total_ms) {
+  MMD_GUARD(h);
   CK(cudaStreamSynchronize(h->stream));
   int n = 0;
   double tot = 0.0;
@@ -810,10 +941,11 @@ static long long sum_counter(mmd_handle h, long long* dev, int reset) {
   return tot;
 }
 
-long long mmd_successful_steps(mmd_handle h, int reset) { return sum_counter(h, h->n_ok, reset); }
-long long mmd_total_qn_iterations(mmd_handle h, int reset) { return sum_counter(h, h->W.itsum, reset); }
+long long mmd_successful_steps(mmd_handle h, int reset) { MMD_GUARD(h); return sum_counter(h, h->n_ok, reset); }
+long long mmd_total_qn_iterations(mmd_handle h, int reset) { MMD_GUARD(h); return sum_counter(h, h->W.itsum, reset); }
 
 int mmd_debug_phase_cycles(mmd_handle h, unsigned long long* out32, int reset) {
+  MMD_GUARD(h);
   if (!h->W.phase) FAIL("phase clocks are compiled in only with -DMMD_PHASE_CLOCK (tools/phase_times.py)");
   CK(cudaMemcpyAsync(out32, h->W.phase, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -822,6 +954,7 @@ int mmd_debug_phase_cycles(mmd_handle h, unsigned long long* out32, int reset) {
 }
 
 int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, int* status) {
+  MMD_GUARD(h);
   const int n = h->d.n_chains;
   if (accepted) CK(cudaMemcpyAsync(accepted, h->accepted, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (accept_prob) CK(cudaMemcpyAsync(accept_prob, h->accp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -831,6 +964,7 @@ int mmd_get_transition_stats(mmd_handle h, int* accepted, double* accept_prob, i
 }
 
 int mmd_get_step_info(mmd_handle h, int* status, int* iters_fwd, int* iters_rev, double* rev_dist) {
+  MMD_GUARD(h);
   const int n = h->d.n_chains;
   const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
   if (status) CK(cudaMemcpyAsync(status, h->W.status, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -843,6 +977,7 @@ int mmd_get_step_info(mmd_handle h, int* status, int* iters_fwd, int* iters_rev,
 
 int mmd_project_quasi_newton(mmd_handle h, const double* q_in, double dt, const mmd_integrator_opts* opts,
                              double* q_out, int* status, int* iters) {
+  MMD_GUARD(h);
   mmd_integrator_opts o;
   if (opts) o = *opts; else mmd_default_integrator_opts(&o);
   if (!h->lin_valid) FAIL("call mmd_linearize first");
@@ -860,6 +995,7 @@ int mmd_project_quasi_newton(mmd_handle h, const double* q_in, double dt, const 
 
 int mmd_init_linear_interpolation(mmd_handle h, const double* u, const double* v_0, const double* x_obs_seq,
                                   int partition) {
+  MMD_GUARD(h);
   // find_initial_state_by_linear_interpolation (:1479-1547) for all chains at once
   if (partition < 0 || partition >= h->d.num_partition) FAIL("bad partition");
   const Dims& d = h->d;
@@ -883,13 +1019,14 @@ int mmd_init_linear_interpolation(mmd_handle h, const double* u, const double* v
   return 0;
 }
 
-int mmd_timer_start(mmd_handle h) { CK(cudaEventRecord(h->ev0, h->stream)); return 0; }
+int mmd_timer_start(mmd_handle h) { MMD_GUARD(h); CK(cudaEventRecord(h->ev0, h->stream)); return 0; }
 int mmd_timer_stop_ms(mmd_handle h, float* ms) {
+  MMD_GUARD(h);
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaEventSynchronize(h->ev1));
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return 0;
 }
-int mmd_synchronize(mmd_handle h) { CK(cudaStreamSynchronize(h->stream)); return 0; }
+int mmd_synchronize(mmd_handle h) { MMD_GUARD(h); CK(cudaStreamSynchronize(h->stream)); return 0; }
 
 }  // extern "C"

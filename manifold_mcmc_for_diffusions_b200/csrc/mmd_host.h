@@ -51,11 +51,13 @@ struct mmd_handle_s {
   mmd::Slots S;
   mmd::Work W;
   int model;
+  int device;     // CUDA device ordinal the handle lives on (made current inside every entry point)
   int X, V, Z, V0;
   int nrmax;      // constraint rows per block the kernels are instantiated for
   double* y;      // [T]
   double* stage;  // [n_chains * dim_q] canonical staging (device)
   double* stage2;
+  double* stage3; // [n_chains * T * X] third staging buffer (asynchronous read-back of x_obs_seq)
   double* tpbuf;  // thread-private scratch [n_tiles][nrmax][nta] (constraint values)
   double* hbuf;   // [chains]
   double* h0buf;  // [chains]
@@ -79,6 +81,7 @@ struct mmd_handle_s {
   const mmd_ops* ops;  // kernel launchers of the handle's model
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
+  cudaEvent_t ev_order;   // cross-stream ordering (mmd_wait_stream / mmd_stream_wait)
   long long launches;
   bool lin_valid;
   std::vector<void*> allocs;
@@ -138,5 +141,6 @@ struct mmd_ops {
   void (*constr_rows)(mmd_handle, const std::vector<double>&, double*);
 };
 const mmd_ops* mmd_ops_fhn();
+const mmd_ops* mmd_ops_fhn_r5();   // blocks of <= 5 observations / 6 constraint rows
 const mmd_ops* mmd_ops_sir();
 const mmd_ops* mmd_ops_fhn_notebook();

@@ -35,6 +35,12 @@
 #ifndef MMD_SMEM_RELOAD
 #define MMD_SMEM_RELOAD asm volatile("" ::: "memory")
 #endif
+// L2 residency hints (mmd_sweeps.cuh): evict_last for the per-iteration block factors, evict_first for the streams of
+// the solver sweeps.  Measured on B200 (16,384 chains): 784 -> 790 k chain-steps/s, DRAM bytes per launch -2 %.
+#if !defined(MMD_NO_L2_HINTS)
+#define MMD_HINT_KEEP 1
+#define MMD_HINT_STREAM 1
+#endif
 #ifndef MMD_L2_PREFETCH_STEPS
 #define MMD_L2_PREFETCH_STEPS 8   // additional look-ahead of the HBM -> L2 prefetch (0 = off)
 #endif
@@ -96,6 +102,7 @@ struct Slots {
   double* kap;     // thread-private [rmax*X]      kap_k[i] = max_{t in interval k, j} |K_t[i][j]| (update-norm bound)
   double* A;       // thread-private [NRMAX*U]     dc/du rows
   double* L;       // thread-private [NRTRI]       packed lower Cholesky factor of D_b (diagonal stored inverted)
+  double* Dinv;    // thread-private [NRTRI]       packed lower triangle of D_b^{-1} (the Woodbury solves multiply by it)
   double* DinvA;   // thread-private [NRMAX*U]
   double* LC;      // per-chain [U(U+1)/2]         packed lower Cholesky factor of C (diagonal stored inverted)
   double* ldv;     // per-chain [1]

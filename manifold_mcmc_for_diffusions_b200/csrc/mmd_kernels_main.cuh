@@ -12,7 +12,11 @@ struct SmemPlan {
   static constexpr int NRED = UMAX * (UMAX + 1) / 2 + 1;
   static constexpr int NRING = (MMD_PREFETCH_STEPS + 1) * RingRec<M>::NWP;
   static constexpr int NSCR = NRED > NRING ? NRED : NRING;
-  static constexpr int PER_THREAD = NSCR + 2 * NRMAX;  // doubles per thread
+  // rows behind the scratch: residuals + multipliers of the projection solves (2 * NRMAX), reused by the linearisation
+  // sweeps for the per-interval constants M_k, Lambda_k and the parameter-gradient accumulator
+  static constexpr int NCONST = M::X * M::X + M::Z * M::X + M::Z;
+  static constexpr int NROWS = 2 * NRMAX > NCONST ? 2 * NRMAX : NCONST;
+  static constexpr int PER_THREAD = NSCR + NROWS;  // doubles per thread
 };
 
 #define MMD_SMEM_SETUP                                                  \
@@ -50,6 +54,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
   double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
   double* DinvAc = tp(S.DinvA + sl * S.s_A, NRMAX * U, t);
   double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
+  double* Dic = tp(S.Dinv + sl * S.s_L, NTRI, t);
   double* LCc = pc(S.LC + sl * S.s_LC, UTRI, t);
   const double* xoc = pc(W.xobs, d.T * X, t);
   double* xsc = tpr<X>(W.xs, d.rmax * d.S * X, t);
@@ -73,7 +78,7 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
   // the per-thread regions; the per-thread constants in the rows the projection solves use for residuals and
   // multipliers) and read where they are used; MMD_SMEM_RELOAD keeps the compiler from hoisting those loads out
   // of the loops (which would put them back into registers / local memory).
-  static_assert(X * X + Z * X + Z <= 2 * NRMAX, "per-interval constants must fit the residual + multiplier rows");
+  static_assert(X * X + Z * X + Z <= SmemPlan<M, NRMAX, UMAX>::NROWS, "per-interval constants must fit the rows behind the scratch");
   typename M::Coef* const sm_coef = reinterpret_cast<typename M::Coef*>(smem + SmemPlan<M, NRMAX, UMAX>::PER_THREAD * NT);
   if (t.slot == 0) sm_coef[t.cl] = P.C;
   __syncthreads();
@@ -249,6 +254,14 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
       for (int j = 0; j < U; ++j) Ac[(r * U + j) * nta] = Am[r * UMAX + j];
     const double ldpart = chol_packed_invdiag(Dm, B.nrows);
     for (int i = 0; i < B.nrows * (B.nrows + 1) / 2; ++i) Lc[i * nta] = Dm[i];
+    // explicit inverse of the block (lower triangle), column by column from the factor: what the Woodbury solves of
+    // the projections use (inv_gram_block)
+    for (int c2 = 0; c2 < B.nrows; ++c2) {
+      double e[NRMAX];
+      for (int r = 0; r < B.nrows; ++r) e[r] = (r == c2) ? 1.0 : 0.0;
+      chol_solve_invdiag(Dm, B.nrows, e);
+      for (int r = c2; r < B.nrows; ++r) Dic[tri(r, c2) * nta] = e[r];
+    }
     // DinvA and C_b = A_b^T D_b^{-1} A_b
     for (int j = 0; j < U; ++j) {
       double col[NRMAX];
@@ -324,28 +337,16 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
         for (int l = 0; l < UMAX; ++l) s = fma(DiA[r * UMAX + l], Cinv[l * UMAX + j], s);
         Om[r * UMAX + j] = s;
       }
-    {
-      double Lm[NTRI];
+    // E = D^{-1} - Om DiA^T from the stored block inverse (rows / columns beyond nr: identity, they are never used)
 #pragma unroll UR
-      for (int r = 0; r < NRL; ++r)
-#pragma unroll
-        for (int c2 = 0; c2 <= r; ++c2) Lm[tri(r, c2)] = (r < nr) ? Lc[tri(r, c2) * nta] : (r == c2 ? 1.0 : 0.0);
+    for (int r = 0; r < NRL; ++r)
 #pragma unroll UR
-      for (int c2 = 0; c2 < NRL; ++c2) {  // E[:, c2] = D^{-1} e_c2 - Om DiA[c2]^T
-        double e[NRMAX];
+      for (int c2 = 0; c2 < NRL; ++c2) {
+        double sv = (r < nr && c2 < nr) ? Dic[(r >= c2 ? tri(r, c2) : tri(c2, r)) * nta] : (r == c2 ? 1.0 : 0.0);
 #pragma unroll
-        for (int i = 0; i < NRMAX; ++i) e[i] = (i == c2) ? 1.0 : 0.0;
-        if constexpr (STATIC_ROWS) chol_solve_invdiag_fixed<NRMAX>(Lm, NRMAX, e);
-        else chol_solve_invdiag(Lm, nr, e);
-#pragma unroll UR
-        for (int r = 0; r < NRL; ++r) {
-          double s = e[r];
-#pragma unroll
-          for (int j = 0; j < UMAX; ++j) s = fma(-Om[r * UMAX + j], DiA[c2 * UMAX + j], s);
-          E[r * NRMAX + c2] = s;
-        }
+        for (int j = 0; j < UMAX; ++j) sv = fma(-Om[r * UMAX + j], DiA[c2 * UMAX + j], sv);
+        E[r * NRMAX + c2] = sv;
       }
-    }
     // noise-scale terms (sigma = exp(u_Z) inferred): d/du_Z and d/dn of 1/2 <E, sigma^2 P_y> + <Om[:, Z], sigma n>
     if (d.noisy) {
 #pragma unroll
@@ -758,7 +759,7 @@ MMD_D void dev_constr(const Dims& d, const Slots& S, const Work& W, const double
 
 template <class M, int NRMAX, int RMAXP, int UMAX>
 MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, int lin_sel, int src_sel,
-                       int dst_sel, double h, double qcoef, FlowCoef fl) {
+                       int dst_sel, double h, double qcoef, FlowCoef fl, int force = -1) {
   const Tid t = thread_id(d);
   MMD_SMEM_SETUP
   constexpr int X = M::X, V = M::V, Z = M::Z, XV = M::X * M::V;
@@ -766,7 +767,9 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
   constexpr int UTRI = UMAX * (UMAX + 1) / 2;
   const int U = d.U, nta = t.nta, cpb = t.cpb;
   const int cur = S.cur[t.cix];
-  const bool skip = !t.act || (W.status[t.cix] != 0);
+  // force >= 0: the caller names the chains to work on (the deferred half kick of chains that failed later in a
+  // multi-step launch); otherwise every chain without an error status
+  const bool skip = !t.act || (force >= 0 ? force == 0 : (W.status[t.cix] != 0));
   const int sl = lin_sel ? 1 - cur : cur;
   auto psel = [&](int sel) -> double* {
     return sel == PSEL_WORK ? W.pw : S.p + (sel == PSEL_OTHER ? 1 - cur : cur) * S.s_q;
@@ -781,7 +784,7 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
   const double* xendc = tp(S.xend + sl * S.s_xend, d.rmax * X, t);
   const double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
   const double* DinvAc = tp(S.DinvA + sl * S.s_A, NRMAX * U, t);
-  const double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
+  const double* Dic = tp(S.Dinv + sl * S.s_L, NTRI, t);
   const double* LCc = pc(S.LC + sl * S.s_LC, UTRI, t);
   double* alph = tp(W.alpha, d.rmax * X, t);
   const bool has_blk = t.slot < d.nb[part] && !skip;
@@ -892,7 +895,7 @@ MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, i
   double rr[NRMAX];
 #pragma unroll
   for (int i = 0; i < NRMAX; ++i) rr[i] = has_blk ? sm_c[i * NT] : 0.0;
-  inv_gram_block<M, NRMAX, UMAX>(d, B, has_blk, Ac, Lc, DinvAc, LCc, rr, sres, nullptr, sm_red, t);
+  inv_gram_block<M, NRMAX, UMAX>(d, B, has_blk, Dic, DinvAc, LCc, rr, sres, nullptr, sm_red, t);
   if (has_blk) {
     // pass 2: p'' = p' - J^T lambda  (rmult_by_jacob_constr :879-913), fused h2_flow
     double a0[X];
@@ -1321,7 +1324,7 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
   const double* kapc = tp(S.kap + sl * S.s_xend, d.rmax * X, t);
   const double* Ac = tp(S.A + sl * S.s_A, NRMAX * U, t);
   const double* DinvAc = tp(S.DinvA + sl * S.s_A, NRMAX * U, t);
-  const double* Lc = tp(S.L + sl * S.s_L, NTRI, t);
+  const double* Dic = tp(S.Dinv + sl * S.s_L, NTRI, t);
   const double* LCc = pc(S.LC + sl * S.s_LC, UTRI, t);
   const QPtr qw = qptr<M>(W.qw, d, t);
   const QPtr qlin = qptr<M>(S.q + sl * S.s_q, d, t);
@@ -1393,7 +1396,7 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
         a.xs_out = NEWTON ? tpr<X>(W.xs, d.rmax * d.S * X, t) : nullptr;
         if (NEWTON && !M::OBS_LINEAR) a.xend_out = tp(W.Yb, d.rmax * X * X, t);
         a.nta = nta; a.cpb = cpb; a.NT = NT; a.tid = t.tid;
-        constr_sweep<M, true>(d, B, a);
+        constr_sweep<M, true, NEWTON>(d, B, a);
       }
       if (NEWTON) Pkeep = P;
     }
@@ -1419,7 +1422,7 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
                                                 sm_l, W, rr, sres, &err, sm_red, t, NT);
     else
       // (no trailing barrier: the next write to the scratch comes after the __syncthreads_or below)
-      inv_gram_block<M, NRMAX, UMAX, false>(d, B, work, Ac, Lc, DinvAc, LCc, rr, sres, &err, sm_red, t);
+      inv_gram_block<M, NRMAX, UMAX, false>(d, B, work, Dic, DinvAc, LCc, rr, sres, &err, sm_red, t);
     // Convergence test of the reference (:1047-1055): |c| < constraint_tol AND |delta_q|_inf < position_tol for THIS
     // iteration's update delta_q = J_lin^T (increment of the multipliers).  The exact norm needs a pass over K; a
     // cheap upper bound (per-interval row maxima kap of K from the linearisation, exact for the head / noise
@@ -1582,11 +1585,20 @@ k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, doub
   const FlowCoef noflow = {0, 1.0, 0.0, 0.0};
   // per-chain step sizes may be signed (per-chain integration direction); a negative scalar flips them all
   const StepCoef sc = make_step_coef(d.gaussian, W.use_dt_chain ? (dt < 0.0 ? -W.dt_chain[t.cix] : W.dt_chain[t.cix]) : dt);
+  // Consecutive steps of one launch share a half kick: A(dt/2) at the end of step s and A(dt/2) at the start of step
+  // s + 1 act at the same point with the same linearisation, and the cotangent projection P is linear and idempotent,
+  // so P(P(p - h g) - h g) = P(p - 2 h g): one kick + projection instead of two (one block solve and ~20 doubles per
+  // SDE step less).  A chain that fails in step s + 1 must be left exactly as Mici leaves it after step s, i.e. with
+  // the second half kick applied: `owed` remembers that and the kick is made up after the loop.
+  const bool fuse = (n_steps > 1) && !reset_status;
+  int owed = 0;
   for (int s = 0; s < n_steps; ++s) {
     if (reset_status && t.slot == 0) W.status[t.cix] = 0;
     __syncthreads();
     PH_T0
-    dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 0, PSEL_CUR, PSEL_WORK, sc.half_dt, sc.qcoef, sc.fwd);
+    const bool first = !(fuse && s > 0), last = !(fuse && s + 1 < n_steps);
+    dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 0, PSEL_CUR, PSEL_WORK, first ? sc.half_dt : 2.0 * sc.half_dt,
+                                      sc.qcoef, sc.fwd);
     __syncthreads();
     PH(0);
     dev_qn<M, NRMAX, RMAX, UMAX, NEWTON>(d, S, W, y, part, 0, sc.mom_coef, ctol, ptol, dtol, max_iters);
@@ -1601,13 +1613,23 @@ k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, doub
     dev_qn<M, NRMAX, RMAX, UMAX, NEWTON>(d, S, W, y, part, 1, 0.0, ctol, ptol, dtol, max_iters);
     __syncthreads();
     PH(4);
-    dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 1, PSEL_OTHER, PSEL_OTHER, sc.half_dt, sc.qcoef, noflow);
-    __syncthreads();
+    if (last) {
+      dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 1, PSEL_OTHER, PSEL_OTHER, sc.half_dt, sc.qcoef, noflow);
+      __syncthreads();
+    }
     PH(5);
     if (t.slot == 0 && t.act) dev_commit(d, S, W, rev_tol, n_ok, t.cix);
     __syncthreads();
+    // the chain now sits at the new point; without the closing half kick it owes one (paid by the next step's
+    // opening kick, or below if that step fails)
+    if (t.act && W.status[t.cix] == 0) owed = last ? 0 : 1;
     PH(6);
     PH_ADD(7, 1);
+  }
+  if (fuse) {
+    const int pay = (t.act && owed && W.status[t.cix] != 0) ? 1 : 0;
+    if (__syncthreads_or(pay))
+      dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, 0, PSEL_CUR, PSEL_CUR, sc.half_dt, sc.qcoef, noflow, pay);
   }
 }
 

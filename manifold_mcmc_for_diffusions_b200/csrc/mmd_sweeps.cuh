@@ -50,12 +50,47 @@ MMD_D void block_start(const Dims& d, const Blk& B, const double* z, const doubl
 // ------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
 MMD_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// L2 residency hints.  The per-iteration block factors (L, A, D^-1 A, Psi_k, kappa_k, alpha_k: ~100 doubles per
+// thread) are re-read by every solver iteration while the streams (work position, compressed Jacobian: 6 KB per
+// thread and sweep) flush the L2 in between; evict_last keeps the factors resident, evict_first marks the streams
+// as the first candidates for replacement.
+MMD_D unsigned long long l2_policy_keep() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+MMD_D unsigned long long l2_policy_stream() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+MMD_D double ldg_keep(const double* g) {
+#if defined(MMD_HINT_KEEP)
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;\n" : "=d"(v) : "l"(g), "l"(l2_policy_keep()));
+  return v;
+#else
+  return *g;
+#endif
+}
 template <int BYTES>
 MMD_D void cp_async(unsigned sdst, const void* gsrc) {
+#if defined(MMD_HINT_STREAM)
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sdst), "l"(gsrc), "l"(l2_policy_stream()) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;\n" ::"r"(sdst), "l"(gsrc), "l"(l2_policy_stream()) : "memory");
+#else
   if (BYTES == 16)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst), "l"(gsrc) : "memory");
   else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+#endif
+}
+template <int N>
+MMD_D void ldcol_keep(const double* g, int ld, double* r) {  // ldcol with the evict_last hint
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = ldg_keep(g + i * ld);
 }
 MMD_D void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(g)); }
 MMD_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
@@ -124,7 +159,7 @@ struct SweepArgs {
   int nta, cpb, NT, tid;
 };
 
-template <class M, bool WITH_K>
+template <class M, bool WITH_K, bool WITH_XS = false>
 __device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const SweepArgs<M>& a) {
   constexpr int X = M::X, V = M::V, XV = M::X * M::V;
   constexpr int PF = MMD_PREFETCH_STEPS, NSL = PF + 1, NWP = RingRec<M>::NWP;
@@ -158,7 +193,7 @@ __device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const Swe
   for (int s = 0; s < ns; ++s) {
     cp_async_wait<PF - 1>();
     double v[V], xn[X];
-    if (a.xs_out) strec<X>(a.xs_out + s * X * nta, x);
+    if (WITH_XS && a.xs_out) strec<X>(a.xs_out + s * X * nta, x);   // (Newton only: keeps the test out of the loop)
     lds_rec<V>(rd, v);
     if (WITH_K) {
       double Kt[XV];
@@ -190,7 +225,7 @@ __device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const Swe
     for (int i = 0; i < X; ++i) x[i] = xn[i];
     if (++t == S) {  // end of observation interval k
       t = 0;
-      if (a.xend_out) stcol<X>(a.xend_out + k * X * nta, nta, x);
+      if (WITH_XS && a.xend_out) stcol<X>(a.xend_out + k * X * nta, nta, x);
       if (k < B.ny) {
         double cy = M::obs(x) - a.y[B.o + k];
         if (d.noisy) {
@@ -271,7 +306,7 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
     if (k < B.n) {
       if (k < B.n - 1) {
         double Ps[X * X], t[X];
-        ldcol<X * X>(Psibc + (k + 1) * X * X * nta, nta, Ps);
+        ldcol_keep<X * X>(Psibc + (k + 1) * X * X * nta, nta, Ps);
         mtv<X, X>(Ps, al, t);
 #pragma unroll
         for (int i = 0; i < X; ++i) al[i] = t[i];
@@ -296,7 +331,7 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
       if (kapc) {
         // |(J^T lam)_{v_t, j}| = |sum_i K_t[i][j] al[i]| <= sum_i kap_k[i] |al[i]| for every step t of interval k
         double kp[X], sb = 0.0;
-        ldcol<X>(kapc + k * X * nta, nta, kp);
+        ldcol_keep<X>(kapc + k * X * nta, nta, kp);
 #pragma unroll
         for (int i = 0; i < X; ++i) sb = fma(kp[i], fabs(al[i]), sb);
         bnd = (sb > bnd || sb != sb) ? sb : bnd;
@@ -305,7 +340,7 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
   }
   {
     double Ps[X * X];
-    ldcol<X * X>(Psibc, nta, Ps);
+    ldcol_keep<X * X>(Psibc, nta, Ps);
     mtv<X, X>(Ps, al, alpha_start);
   }
   if (body_bound) *body_bound = bnd;
@@ -313,49 +348,41 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
 
 // Woodbury solve G^{-1} r for this thread's block (lmult_by_inv_gram :915-942):
 //   t_b = D_b^{-1} r_b ; s = C^{-1} sum_b A_b^T t_b ; lam_b = t_b - (D_b^{-1} A_b) s
-// `r` (registers, NRMAX entries, entries >= nrows ignored) is overwritten by lam_b; s (= u-part of
-// J^T G^{-1} r) is returned in `s_out`.  `extra_max` rides along the same cross-block reduction as a
-// maximum (the solver's |c|_inf).  Everything is unrolled over NRMAX x UMAX with guards so that the
-// factor loads (L, A, D^{-1}A: thread-private, L2-resident) are issued up front, not one per
-// dependent multiply-add.
+// evaluated with the explicit block inverse and sum_b A_b^T D_b^{-1} r_b = sum_b (D_b^{-1} A_b)^T r_b (D_b symmetric):
+// both products take `r` directly, so every factor load (D^-1: NRMAX (NRMAX + 1) / 2, D^-1 A: NRMAX x U values per
+// thread, thread-private columns) is independent of the arithmetic and can be in flight at once -- the triangular
+// solves this replaces were a chain of dependent loads and multiply-adds, and the solver calls this once per
+// iteration.  `r` (registers, NRMAX entries, entries >= nrows ignored) is overwritten by lam_b; s (= u-part of
+// J^T G^{-1} r) is returned in `s_out`.  `extra_max` rides along the same cross-block reduction as a maximum (the
+// solver's |c|_inf).
 template <class M, int NRMAX, int UMAX, bool TAIL_SYNC = true>
-MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const double* __restrict__ Ac,
-                          const double* __restrict__ Lc, const double* __restrict__ DinvAc,
-                          const double* __restrict__ LCc, double* r, double* s_out, double* extra_max,
-                          double* smem_red, const Tid& t) {
+MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const double* __restrict__ Dic,
+                          const double* __restrict__ DinvAc, const double* __restrict__ LCc, double* r, double* s_out,
+                          double* extra_max, double* smem_red, const Tid& t) {
   const int U = d.U, nta = t.nta;
   const int n = has_blk ? B.nrows : 0;
-  double g[UMAX + 1];
+  double g[UMAX + 1], tb[NRMAX];
 #pragma unroll
   for (int j = 0; j < UMAX; ++j) g[j] = 0.0;
   g[UMAX] = extra_max ? *extra_max : 0.0;
+#pragma unroll
+  for (int i = 0; i < NRMAX; ++i) tb[i] = 0.0;
   if (has_blk) {
-    // forward / backward substitution with the packed factor (diagonal stored inverted)
     MMD_SOLVE_UNROLL
     for (int i = 0; i < NRMAX; ++i) {
       if (i < n) {
-        double s = r[i];
+        const double ri = r[i];
+        // column i of the packed symmetric inverse: entries (k, i), k >= i, and by symmetry (i, k)
         MMD_SOLVE_UNROLL
-        for (int k = 0; k < i; ++k) s = fma(-Lc[tri(i, k) * nta], r[k], s);
-        r[i] = s * Lc[tri(i, i) * nta];
-      }
-    }
-    MMD_SOLVE_UNROLL
-    for (int i = NRMAX - 1; i >= 0; --i) {
-      if (i < n) {
-        double s = r[i];
-        MMD_SOLVE_UNROLL
-        for (int k = i + 1; k < NRMAX; ++k)
-          if (k < n) s = fma(-Lc[tri(k, i) * nta], r[k], s);
-        r[i] = s * Lc[tri(i, i) * nta];
-      }
-    }
-    MMD_SOLVE_UNROLL
-    for (int i = 0; i < NRMAX; ++i) {
-      if (i < n) {
+        for (int k = i; k < NRMAX; ++k)
+          if (k < n) {
+            const double dv = Dic[tri(k, i) * nta];
+            tb[k] = fma(dv, ri, tb[k]);
+            if (k != i) tb[i] = fma(dv, r[k], tb[i]);
+          }
 #pragma unroll
         for (int j = 0; j < UMAX; ++j)
-          if (j < U) g[j] = fma(Ac[(i * U + j) * nta], r[i], g[j]);
+          if (j < U) g[j] = fma(DinvAc[(i * U + j) * nta], ri, g[j]);
       }
     }
   }
@@ -371,7 +398,7 @@ MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const doubl
     MMD_SOLVE_UNROLL
     for (int i = 0; i < NRMAX; ++i) {
       if (i < n) {
-        double ti = r[i];
+        double ti = tb[i];
 #pragma unroll
         for (int j = 0; j < UMAX; ++j)
           if (j < U) ti = fma(-DinvAc[(i * U + j) * nta], g[j], ti);

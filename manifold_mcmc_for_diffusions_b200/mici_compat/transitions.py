@@ -46,8 +46,9 @@ class MultinomialDynamicIntegrationTransition(Transition):
 
     def __init__(self, system, integrator, max_tree_depth=10, max_delta_h=1000,
                  termination_criterion=riemannian_no_u_turn_criterion, do_extra_subtree_checks=True,
-                 error_accept_stat="zero"):
-        # error_accept_stat: see nuts.BatchedNUTS (accept_stat of a transition that ended in an integrator error)
+                 error_accept_stat="partial"):
+        # error_accept_stat: see nuts.BatchedNUTS (accept_stat of a transition that ended in an integrator error);
+        # "partial" = sum_acc_prob / n_step, Mici's rule
         self.error_accept_stat = error_accept_stat
         self.system = system
         self.integrator = integrator

@@ -60,13 +60,28 @@ def split_and_reshape(array, shapes):
                  zip(split(array, lengths), shapes))
 
 
+class DeviceArray(np.ndarray):
+    """Result type of the batched private handles (the role `jax.numpy.DeviceArray` plays for the reference's jitted
+    closures): a NumPy array whose computation has already been synchronised, or a zero-size ticket for block
+    factors that stay on the device."""
+
+    def block_until_ready(self):
+        return self
+
+
 def standard_normal_neg_log_dens(q):
-    """Unnormalised negative log density of standard normal vector (:56-58)."""
+    """Unnormalised negative log density of standard normal vector (:56-58); a leading batch axis is mapped."""
+    q = np.asarray(q)
+    if q.ndim > 1:
+        return (0.5 * np.sum(np.square(q), axis=-1)).view(DeviceArray)
     return 0.5 * float(np.sum(np.square(q)))
 
 
 def standard_normal_grad_neg_log_dens(q):
     """Gradient and value of negative log density of standard normal vector (:61-63)."""
+    q = np.asarray(q)
+    if q.ndim > 1:
+        return q.view(DeviceArray), (0.5 * np.sum(np.square(q), axis=-1)).view(DeviceArray)
     return q, 0.5 * float(np.sum(np.square(q)))
 
 
@@ -120,6 +135,21 @@ class ConditionedDiffusionConstrainedSystem(System):
             "generate_z": generate_z, "generate_x_0": generate_x_0, "generate_σ": generate_σ,
             "forward_func": forward_func, "obs_func": obs_func, "y_seq": y_seq,
         }
+        # y_subseqs (:321-356): the observations split per partition into (first, stacked middle, last) blocks
+        if num_obs_per_subseq is None or num_obs_per_subseq == num_obs:
+            y_subseq_shapes = [((num_obs,),)]
+        else:
+            y_subseq_shapes = []
+            for init in (num_obs_per_subseq, num_obs_per_subseq // 2):
+                num_full, num_rem = divmod(num_obs - init, num_obs_per_subseq)
+                num_middle = num_full - 1 if num_rem == 0 else num_full
+                fin = num_obs_per_subseq if num_rem == 0 else num_rem
+                y_subseq_shapes.append(((init,),) + (((num_middle, num_obs_per_subseq),) if num_middle > 0 else ())
+                                       + ((fin,),))
+        self.y_subseqs = [split_and_reshape(y_seq, shapes) for shapes in y_subseq_shapes]
+        self._ctor = dict(model=model, obs_interval=obs_interval, S=num_steps_per_obs, R=num_obs_per_subseq, y=y_seq,
+                          dim_u=dim_u, noise=noise, sigma=sigma, gaussian=use_gaussian_splitting, device=device)
+        self._batch = {}          # n_states -> BatchedChains used by the batched private handles below
         self._dims = (num_obs, num_steps_per_obs, num_obs_per_subseq, dim_u, dim_x, dim_v, dim_v_0, noise)
         self._resident = None     # (pos bytes, x_obs bytes, partition) of the chain resident on the device
         self._linearised = False
@@ -172,6 +202,106 @@ class ConditionedDiffusionConstrainedSystem(System):
     def grad_log_det_sqrt_gram(self, state):
         self._linearise(state)
         return np.array(self._grad, copy=True), self._ld
+
+    # ---- private handles with a leading batch axis (:1137-1149) --------------------------------------
+    # The reference exposes its jitted closures as `system._constr(q, x_obs_seq, partition)` etc.; the
+    # operation-time script maps them over 1000 states with `lax.map`
+    # (scripts/fhn_model_noiseless_obs_chmc_operation_times.py:30-65).  Here they take either one state (1-D q) or a
+    # batch (2-D q, leading axis = states) and run ONE device launch for the whole batch.  Block factors stay on the
+    # device: the Jacobian / Cholesky "blocks" they return are tickets (DeviceArray, zero host bytes) that the
+    # follow-up handles accept in place of the dense blocks.  Jacobian, Gram matrices and Cholesky factors are
+    # produced by the same fused kernel (k_point), so `_chol_gram_blocks` / `_lu_jacob_product_blocks` of a ticket
+    # that is still current cost nothing; the LU products of the Newton solver exist only inside its iteration.
+    def _batch_chains(self, n):
+        bc = self._batch.get(n)
+        if bc is None:
+            c = self._ctor
+            bc = BatchedChains(c["model"], c["obs_interval"], c["S"], c["R"], c["y"], c["dim_u"], n, noise=c["noise"],
+                               sigma_fixed=c["sigma"], use_gaussian_splitting=c["gaussian"], device=c["device"])
+            bc._ticket = 0
+            self._batch[n] = bc
+        return bc
+
+    def _batch_load(self, q, x_obs_seq, partition):
+        q = np.asarray(q, dtype=np.float64)
+        single = q.ndim == 1
+        q2 = q[None] if single else q
+        x2 = np.asarray(x_obs_seq, dtype=np.float64)
+        x2 = x2[None] if single else x2
+        bc = self._batch_chains(q2.shape[0])
+        bc.set_state(q2, x2, int(partition))
+        bc._ticket += 1
+        return bc, single
+
+    @staticmethod
+    def _out(a, single):
+        a = np.asarray(a)
+        return (a[0] if single else a).view(DeviceArray)
+
+    def _tickets(self, bc, single, k):
+        out = []
+        for _ in range(k):
+            t = np.empty((0,) if single else (bc.n_chains, 0)).view(DeviceArray)
+            t._mmd_ticket = (bc, bc._ticket, single)
+            out.append(t)
+        return tuple(out)
+
+    @staticmethod
+    def _redeem(*tickets):
+        for t in tickets:
+            tk = getattr(t, "_mmd_ticket", None)
+            if tk is not None:
+                bc, version, single = tk
+                if version != bc._ticket:
+                    raise ValueError("stale block ticket: the states it was computed for are no longer resident")
+                return bc, single
+        raise TypeError("expected the block tickets returned by _jacob_constr_blocks / _chol_gram_blocks "
+                        "(dense blocks are not accepted: the factors live on the device)")
+
+    def _constr(self, q, x_obs_seq, partition):
+        bc, single = self._batch_load(q, x_obs_seq, partition)
+        return self._out(bc.constr(), single)
+
+    def _generate_x_obs_seq(self, q):
+        q = np.asarray(q, dtype=np.float64)
+        single = q.ndim == 1
+        q2 = q[None] if single else q
+        T, X = self._dims[0], self._dims[4]
+        bc, _ = self._batch_load(q2, np.zeros((q2.shape[0], T, X)), 0)
+        bc.update_x_obs_seq()
+        return self._out(bc.get_state()[2], single)
+
+    def _jacob_constr_blocks(self, q, x_obs_seq, partition):
+        bc, single = self._batch_load(q, x_obs_seq, partition)
+        bc.linearize(False)
+        bc.synchronize()
+        return self._tickets(bc, single, 3)
+
+    def _chol_gram_blocks(self, dc_du_blocks, dc_dv_blocks, dc_dn_blocks=None):
+        bc, single = self._redeem(dc_du_blocks, dc_dv_blocks, dc_dn_blocks)
+        return self._tickets(bc, single, 2)
+
+    def _lu_jacob_product_blocks(self, *blocks):
+        bc, single = self._redeem(*blocks)
+        return self._tickets(bc, single, 2)
+
+    def _log_det_sqrt_gram_from_chol(self, chol_C, chol_D_blocks):
+        bc, single = self._redeem(chol_C, chol_D_blocks)
+        return self._out(bc.log_det_sqrt_gram(), single)
+
+    def _grad_log_det_sqrt_gram(self, q, x_obs_seq, partition):
+        """((log_det_sqrt_gram, (jacob_constr_blocks, chol_gram_blocks)), grad), the layout of
+        jax.value_and_grad(..., has_aux=True) at :1143-1146."""
+        bc, single = self._batch_load(q, x_obs_seq, partition)
+        bc.linearize(True)
+        val = self._out(bc.log_det_sqrt_gram(), single)
+        grad = self._out(bc.grad_log_det_sqrt_gram(), single)
+        return (val, (self._tickets(bc, single, 3), self._tickets(bc, single, 2))), grad
+
+    def _normal_space_component(self, vct, jacob_constr_blocks, chol_gram_blocks):
+        bc, single = self._redeem(*jacob_constr_blocks, *chol_gram_blocks)
+        v = np.asarray(vct, dtype=np.float64)
+        return self._out(bc.normal_space_component(v[None] if single else v), single)
 
     # ---- Hamiltonian components (:1186-1238) -----------------------------------------------------
     def h1(self, state):
@@ -249,9 +379,14 @@ def _solve_projection(state, state_prev, dt, system, solver, name, constraint_to
     q_in = np.array(state.pos, dtype=np.float64, copy=True)
     q_out, status, iters = system._project(state_prev, q_in, solver, constraint_tol, position_tol, divergence_tol,
                                            max_iters)
-    if state._call_counts is not None:  # :1382-1387
-        key = _cache_key_func(system, system.constr)
-        state._call_counts[key] = state._call_counts.get(key, 0) + iters
+    if state._call_counts is not None:
+        # quasi-Newton counts one constr call per iteration (:1382-1387); Newton also re-evaluates the Jacobian and
+        # the LU-factorised block products every iteration (:1451-1461)
+        methods = [system.constr] if solver == SOLVER_QUASI_NEWTON else [
+            system.constr, system.jacob_constr_blocks, "lu_jacob_product_blocks"]
+        for method in methods:
+            key = _cache_key_func(system, method)
+            state._call_counts[key] = state._call_counts.get(key, 0) + iters
     if status == 0:
         state.pos = q_out
         if state.mom is not None:

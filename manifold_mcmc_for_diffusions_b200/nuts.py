@@ -32,14 +32,13 @@ def _trailing_ones(x):
 
 class BatchedNUTS:
     def __init__(self, chains, max_tree_depth=10, max_delta_h=1000.0, do_extra_subtree_checks=True,
-                 error_accept_stat="zero"):
+                 error_accept_stat="partial"):
         """error_accept_stat: the `accept_stat` reported for a transition whose tree ended in an integrator error
-        (projection not converged / non-reversible step).  "zero" reports 0, "partial" the mean acceptance
-        probability over the steps taken before the error.  Mici is not available here and its source could not be
-        consulted; the statistics recorded in the reference's notebook (accept_stat 0.83, n_step 28.3,
-        convergence_error 0.15 after dual averaging to 0.8) are reproduced with "zero" and cannot be reproduced at any
-        step size with "partial" (DESIGN.md section 2), so "zero" is the default: it is what the step-size adapter
-        sees, and it keeps the adapted step size out of the regime where most trees end in an error."""
+        (projection not converged / non-reversible step).  "partial" (default) is Mici's rule as recorded in
+        SURVEY.md appendix A: sum_acc_prob / n_step over the steps taken before the error, 0 when there were none.
+        "zero" reports 0 for every such transition; it is an opt-in used by tools/notebook_nuts.py, which found that it
+        reproduces the sampler statistics recorded in the reference's notebook better -- Mici's
+        source is not available here, so the documented rule stays the default."""
         if error_accept_stat not in ("zero", "partial"):
             raise ValueError("error_accept_stat must be 'zero' or 'partial'")
         self.error_accept_stat = error_accept_stat
@@ -55,18 +54,28 @@ class BatchedNUTS:
         self.midp = [CK0 + 2 * D + i for i in range(D)]
         self.mids = [CK0 + 3 * D + i for i in range(D)]
         self.inop = [CK0 + 4 * D + i for i in range(D)]
-        chains.aux_reserve(CK0 + (5 if self.do_extra_subtree_checks else 2) * D)
+        # proposal stack of the sub-tree being built: Mici's _build_tree merges two sibling sub-trees by keeping the
+        # outer one's proposal with probability w_outer / (w_inner + w_outer); with leaves arriving in order the merges
+        # of the recursion are the carries of a binary counter, entry i of the stack = proposal of a finished sub-tree
+        self.prp = [CK0 + 5 * D + i for i in range(D + 1)]
+        chains.aux_reserve(CK0 + 5 * D + D + 1)
 
-    def transition(self, step_size, rng, seed, it, switch_partition=True):
+    def transition(self, step_size, rng, seed, it, switch_partition=True, trace=None):
         """One momentum refresh + dynamic integration transition (+ partition switch) for every chain.
         step_size: scalar or per-chain array; rng: NumPy Generator for the tree decisions (directions,
         multinomial / progressive sampling); (seed, it) key the on-device Philox momentum draw.
-        Returns the per-chain statistics Mici reports."""
+        Random numbers are drawn as one vector per decision in the order Mici's recursion draws them for a single
+        chain (direction; one per sub-tree merge, innermost first; top-level acceptance), so chain c driven by column c
+        of the draws reproduces the recursive transition (tests/test_gpu_nuts_parity.py).  `trace` (dict) receives the
+        state after the momentum refresh.  Returns the per-chain statistics Mici reports."""
         bc, n = self.bc, self.bc.n_chains
         Q, P = bc.VEC_Q, bc.VEC_P
         eps = np.broadcast_to(np.asarray(step_size, dtype=np.float64), (n,)).copy()
         bc.transition_begin(seed, it)
         h0 = bc.hamiltonian()
+        if trace is not None:
+            trace["state0"] = bc.get_state()
+            trace["partition"] = bc.partition
         for a in (EQ0, EQ1, PROP):
             bc.vec_axpby(a, Q)
         for a in (EP0, EP1, SUMP):
@@ -98,6 +107,7 @@ class BatchedNUTS:
             bc.set_step_sizes(dirs * eps)
             bc.vec_axpby(SUBSUM, SUBSUM, alpha=0.0, beta=0.0)
             sub_logw = np.full(n, -np.inf)
+            stack_lw = np.full((self.max_tree_depth + 1, n), -np.inf)
             in_sub = active.copy()
             for leaf in range(2 ** depth):
                 if not in_sub.any():
@@ -119,12 +129,11 @@ class BatchedNUTS:
                 ok &= ~div
                 bc.vec_axpby(SUBSUM, P, 1.0, 1.0, mask=ok)
                 lw = -h
-                new_logw = np.logaddexp(sub_logw, lw)
-                with np.errstate(divide="ignore"):
-                    take = ok & (np.log(rng.random(n)) < lw - new_logw)
-                sub_logw = np.where(ok, new_logw, sub_logw)
-                if take.any():
-                    bc.vec_axpby(SUBPROP, Q, mask=take)
+                sub_logw = np.where(ok, np.logaddexp(sub_logw, lw), sub_logw)
+                # push the leaf; the merges follow below, together with the no-U-turn checks of the same spans
+                pos = _popcount(leaf)
+                bc.vec_axpby(self.prp[pos], Q, mask=ok)
+                stack_lw[pos] = np.where(ok, lw, -np.inf)
                 turning = np.zeros(n, dtype=bool)
                 idx_max, t_ones = _popcount(leaf >> 1), _trailing_ones(leaf)
                 extra = self.do_extra_subtree_checks
@@ -137,6 +146,15 @@ class BatchedNUTS:
                 else:
                     # spans of 2, 4, ... leaves ending here (Mici _build_tree merges, innermost first)
                     for k, i in enumerate(range(idx_max, idx_max - t_ones, -1), start=1):
+                        # merge the two sibling sub-trees on top of the stack (inner = older, outer = newer)
+                        lw_i, lw_o = stack_lw[pos - 1], stack_lw[pos]
+                        lw_m = np.logaddexp(lw_i, lw_o)
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            take = ok & (np.log(rng.random(n)) < lw_o - lw_m)
+                        if take.any():
+                            bc.vec_axpby(self.prp[pos - 1], self.prp[pos], mask=take)
+                        stack_lw[pos - 1] = lw_m
+                        pos -= 1
                         d1, d2 = bc.vec_uturn(self.ckp[i], self.cks[i], SUBSUM, P)
                         turning |= ok & ((d1 < 0) | (d2 < 0))
                         if extra and k >= 2:
@@ -159,7 +177,7 @@ class BatchedNUTS:
             with np.errstate(divide="ignore"):
                 accept = done & (np.log(rng.random(n)) < sub_logw - logw)
             if accept.any():
-                bc.vec_axpby(PROP, SUBPROP, mask=accept)
+                bc.vec_axpby(PROP, self.prp[0], mask=accept)
             logw = np.where(done, np.logaddexp(logw, sub_logw), logw)
             bc.vec_axpby(SUMP, SUBSUM, 1.0, 1.0, mask=done)
             for sgn, eq, ep in ((1, EQ1, EP1), (-1, EQ0, EP0)):

@@ -53,3 +53,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_dlpack_consumer_rejects_host_memory():
+    """The DLPack path is device-only: CPU producers are refused (no hidden host fallback)."""
+    import numpy as np
+    import pytest
+    import torch
+
+    from manifold_mcmc_for_diffusions_b200._dlpack import DeviceArray
+
+    with pytest.raises(ValueError):
+        DeviceArray(torch.zeros(3, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        DeviceArray(np.zeros(3))
+    with pytest.raises(TypeError):
+        DeviceArray([0.0, 1.0])

@@ -4,6 +4,7 @@ leapfrog integrator and an artificial "projection failure" region.  The batched 
 object through the mmd_vec_* / transition_* surface, which a NumPy stand-in implements here."""
 
 import numpy as np
+import pytest
 
 from manifold_mcmc_for_diffusions_b200.mici_compat.errors import ConvergenceError
 from manifold_mcmc_for_diffusions_b200.mici_compat.transitions import MultinomialDynamicIntegrationTransition
@@ -206,3 +207,59 @@ def test_batched_init_step_size_search_matches_the_sequential_adapter():
         ref = ad._find_and_set_init_step_size(_State(q[c].copy(), p[c].copy()), _System(), integ)
         assert ref == eps[c], (c, ref, eps[c])
     assert len(set(eps)) > 1                      # not a trivial case: chains end at different step sizes
+
+
+class _RecordingRng:
+    """Generator whose vector draws are kept: column c is the uniform sequence chain c consumes."""
+
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+        self.draws = []
+
+    def random(self, n):
+        u = self.rng.random(n)
+        self.draws.append(u)
+        return u
+
+
+class _ReplayRng:
+    def __init__(self, seq):
+        self.seq, self.i = list(seq), 0
+
+    def uniform(self):
+        u = self.seq[self.i]
+        self.i += 1
+        return u
+
+
+@pytest.mark.parametrize("extra", [True, False])
+def test_batched_nuts_equals_recursive_transition_chain_by_chain(extra):
+    """Same start, same momenta, same uniforms (direction / sub-tree merges / acceptance in the recursion's draw
+    order): n_step, tree_depth, termination flags, accept_stat and the selected proposal must be IDENTICAL per chain.
+    An index slip in the check-point bookkeeping of nuts.py (popcount / trailing-ones levels, extra sub-tree checks,
+    proposal stack) cannot pass this."""
+    n, depth = 96, 6
+    rng0 = np.random.default_rng(77)
+    q0 = rng0.standard_normal((n, len(SCALES))) * SCALES * 0.9
+    bc = FakeChains(q0, 5)
+    nuts = BatchedNUTS(bc, max_tree_depth=depth, do_extra_subtree_checks=extra)
+    rec = _RecordingRng(123)
+    trace = {}
+    # FakeChains has no get_state: capture the refreshed momenta through the hook the transition calls
+    bc.get_state = lambda: (bc.q.copy(), bc.p.copy(), None)
+    stats = nuts.transition(0.23, rec, 0, 0, trace=trace)
+    qs, ps, _ = trace["state0"]
+    draws = np.array(rec.draws)                   # [n_draws, n]
+    tr = MultinomialDynamicIntegrationTransition(_System(), _Integrator(0.23), max_tree_depth=depth,
+                                                 do_extra_subtree_checks=extra)
+    seen_depths = set()
+    for c in range(n):
+        st, ref = tr.sample(_State(qs[c].copy(), ps[c].copy()), _ReplayRng(draws[:, c]))
+        assert ref["n_step"] == stats["n_step"][c], c
+        assert ref["tree_depth"] == stats["tree_depth"][c], c
+        assert ref["convergence_error"] == bool(stats["convergence_error"][c]), c
+        assert ref["diverging"] == bool(stats["diverging"][c]), c
+        assert abs(ref["accept_stat"] - stats["accept_stat"][c]) < 1e-14, c
+        assert np.array_equal(st.pos, bc.q[c]), c          # the same leaf was proposed and accepted
+        seen_depths.add(ref["tree_depth"])
+    assert len(seen_depths) >= 3 and stats["convergence_error"].any() and (stats["n_step"] >= 15).any()
