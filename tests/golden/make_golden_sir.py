@@ -19,7 +19,8 @@ from oracle import torch_oracle as O  # noqa: E402
 from oracle.models import sir  # noqa: E402
 
 T, S, N_CHAINS, DT = 14, 20, 2, 0.02
-# boarding-school influenza counts (the data set the reference's SIR script uses), 14 days
+# a synthetic 14-day epidemic curve of the boarding-school data's shape (NOT the bundled series 3, 8, 28, 75, 221,
+# 281, ...; that one is covered by make_golden_bundled.py / test_gpu_bundled_configs.py)
 y = np.array([3, 8, 26, 76, 225, 298, 258, 233, 189, 128, 68, 29, 14, 4], dtype=np.float64)[:, None]
 sysm = O.OracleSystem(1.0, S, T, y, 5, 3, 3, sir.forward_func, sir.generate_x_0, sir.generate_z, sir.obs_func,
                       sir.generate_σ_y, False, dim_v_0=1)

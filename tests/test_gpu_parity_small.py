@@ -126,3 +126,16 @@ def test_failed_step_keeps_state(prob):
     qb, pb, _ = bc.get_state()
     assert np.array_equal(qa, qb) and np.array_equal(pa, pb)
     bc.close()
+
+
+def test_linear_interpolation_initialiser_values(prob):
+    """k_init_interp against the oracle's find_initial_state_by_linear_interpolation (mici_extensions.py:1503-1526) on
+    the same u, v_0 and x_obs_seq: the noise sequence itself, not only the constraint residual."""
+    q_ref, xo = prob["q"], prob["xobs"]            # produced by the oracle's initialiser (tests/helpers.py)
+    bc = make_batched(prob)
+    bc.init_linear_interpolation(q_ref[:, :4], q_ref[:, 4:6], xo, 0)
+    q, _, x = bc.get_state()
+    assert np.array_equal(x, xo)
+    assert np.max(np.abs(q - q_ref)) <= 1e-9 * max(1.0, np.max(np.abs(q_ref)))
+    assert np.max(np.abs(bc.constr())) < 1e-8
+    bc.close()

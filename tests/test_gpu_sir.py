@@ -139,7 +139,7 @@ def test_leapfrog_steps(prob, solver):
 
 def test_sir_script_shape_golden():
     """The reference's SIR experiment shape (14 observations x 20 steps, one block, inferred noise scale,
-    dim_q = 860; boarding-school data) against committed oracle-frozen vectors (tests/golden/make_golden_sir.py)."""
+    dim_q = 860; a synthetic epidemic curve of the boarding-school shape) against committed oracle-frozen vectors (tests/golden/make_golden_sir.py)."""
     import os
 
     from manifold_mcmc_for_diffusions_b200 import BatchedChains
@@ -167,4 +167,35 @@ def test_sir_script_shape_golden():
         assert _rel(p, g[f"{solver}_p"]) < 1e-8
         h = bc.hamiltonian()
         assert np.max(np.abs(h - g[f"{solver}_h"]) / np.abs(h)) < 1e-9
+        bc.close()
+
+
+def test_clip_region_derivatives():
+    """sir.py:54-70: a log-state component at or below -500 is frozen at -500 and, as autodiff sees the clip and the
+    select, has no sensitivity and exerts none.  Blocks that start from a conditioned state with log S = -600 run
+    their whole interval inside the clip region; constraint, log-det, its gradient and the normal-space component
+    must agree with the autodiff oracle there too."""
+    prob = make_sir_problem(6, 4, 3, n_chains=2, seed=17)
+    sysm = prob["system"]
+    xo = prob["xobs"].copy()
+    xo[:, :, 0] = -600.0
+    rng = np.random.default_rng(5)
+    for part in _parts(prob):
+        q = prob["q"]
+        bc = make_bc(prob)
+        bc.set_state(q, xo, part)
+        c = bc.constr()
+        bc.linearize(True)
+        ld, g = bc.log_det_sqrt_gram(), bc.grad_log_det_sqrt_gram()
+        vct = rng.standard_normal(q.shape)
+        nsc = bc.normal_space_component(vct)
+        for i in range(q.shape[0]):
+            c_o = sysm._constr(torch.tensor(q[i]), torch.tensor(xo[i]), part).numpy()
+            assert np.max(np.abs(c[i] - c_o)) < 1e-11 * max(1.0, np.abs(c_o).max())
+            pt = sysm.point(q[i], xo[i], part)
+            assert np.isfinite(pt["grad_ld"].numpy()).all()
+            assert abs(ld[i] - pt["ld"]) < 1e-10 * max(1.0, abs(pt["ld"]))
+            assert _rel(g[i], pt["grad_ld"].numpy()) < 1e-9
+            nsc_o = sysm._normal_space_component(torch.tensor(vct[i]), pt["jac"], pt["chol"]).numpy()
+            assert _rel(nsc[i], nsc_o) < 1e-9
         bc.close()

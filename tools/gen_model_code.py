@@ -112,7 +112,7 @@ def _emit(name, args_sig, outputs, unpack, hoister):
     return "\n".join(lines)
 
 
-def gen_model(struct_name, fname, f, X, V, Z, sd, header, doc, extra_methods="", step_name="step"):
+def gen_model(struct_name, fname, f, X, V, Z, sd, header, doc, extra_methods="", step_name="step", deriv_suffix=""):
     """Emit one model header.  f: sympy column of the step map in terms of X, V, Z symbols and sd."""
     nx, nv, nz = len(X), len(V), len(Z)
     dyn = list(X) + list(V)
@@ -131,13 +131,13 @@ def gen_model(struct_name, fname, f, X, V, Z, sd, header, doc, extra_methods="",
     parts = []
     parts.append(_emit(step_name, sig + "double* xn", [(f"xn[{i}]", f[i]) for i in range(nx)], unpack, hs))
     Fx = f.jacobian(X)
-    parts.append(_emit("jac_x", sig + "double* F",
+    parts.append(_emit("jac_x" + deriv_suffix, sig + "double* F",
                        [(f"F[{i*nx+j}]", Fx[i, j]) for i in range(nx) for j in range(nx)], unpack, hd))
     Fv = f.jacobian(V)
-    parts.append(_emit("jac_v", sig + "double* B",
+    parts.append(_emit("jac_v" + deriv_suffix, sig + "double* B",
                        [(f"B[{i*nv+j}]", Fv[i, j]) for i in range(nx) for j in range(nv)], unpack, hd))
     Fz = f.jacobian(Z)
-    parts.append(_emit("jac_z", sig + "double* G",
+    parts.append(_emit("jac_z" + deriv_suffix, sig + "double* G",
                        [(f"G[{i*nz+j}]", Fz[i, j]) for i in range(nx) for j in range(nz)], unpack, hd))
     # second-order contraction: g[a] = sum_i sum_b d2 f_i / d y_a d y_b * Th[b*X + i]
     nj = len(joint)
@@ -152,7 +152,7 @@ def gen_model(struct_name, fname, f, X, V, Z, sd, header, doc, extra_methods="",
     th_unpack = unpack + "\n" + "\n".join(
         "    " + " ".join(f"const double Th{r}_{c} = Th[{r*nx+c}];" for c in range(nx)) for r in range(nj)
     )
-    parts.append(_emit("hess_contract", sig + "const double* Th, double* g",
+    parts.append(_emit("hess_contract" + deriv_suffix, sig + "const double* Th, double* g",
                        [(f"g[{a}]", gout[a]) for a in range(nj)], th_unpack, hd))
     jv_const = not (Fv.free_symbols & set(X) | Fv.free_symbols & set(V))
 
@@ -362,8 +362,56 @@ def gen_sir():
     xn[1] = xc[1] > -500.0 ? xr[1] : xc[1];
     xn[2] = xr[2];
   }
+
+  // Derivatives of the guarded step, as autodiff sees them (clip: zero slope below -500; select: the untouched
+  // clipped value): a component held at -500 neither moves nor influences the others -- its row and its column of
+  // d f / d x vanish, its rows of d f / d v and d f / d z vanish, and so does every second derivative that involves
+  // it.  Everything else is the raw derivative at the clipped state.
+  MMD_HD static void clip_state(const double* x, double* xc, bool* held) {
+    held[0] = !(x[0] > -500.0); held[1] = !(x[1] > -500.0); held[2] = false;
+    xc[0] = held[0] ? -500.0 : x[0]; xc[1] = held[1] ? -500.0 : x[1]; xc[2] = x[2];
+  }
+  MMD_HD static void jac_x(const Coef& c, const double* x, const double* v, double* F) {
+    if (x[0] > -500.0 && x[1] > -500.0) { jac_x_raw(c, x, v, F); return; }
+    double xc[3]; bool held[3];
+    clip_state(x, xc, held);
+    jac_x_raw(c, xc, v, F);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        if (held[i] || held[j]) F[i * 3 + j] = 0.0;
+  }
+  MMD_HD static void jac_v(const Coef& c, const double* x, const double* v, double* B) {
+    if (x[0] > -500.0 && x[1] > -500.0) { jac_v_raw(c, x, v, B); return; }
+    double xc[3]; bool held[3];
+    clip_state(x, xc, held);
+    jac_v_raw(c, xc, v, B);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < V; ++j)
+        if (held[i]) B[i * V + j] = 0.0;
+  }
+  MMD_HD static void jac_z(const Coef& c, const double* x, const double* v, double* G) {
+    if (x[0] > -500.0 && x[1] > -500.0) { jac_z_raw(c, x, v, G); return; }
+    double xc[3]; bool held[3];
+    clip_state(x, xc, held);
+    jac_z_raw(c, xc, v, G);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < Z; ++j)
+        if (held[i]) G[i * Z + j] = 0.0;
+  }
+  // g[a] = sum_i sum_b d2 f_i / d y_a d y_b Th[b * X + i],  y = (x, v, z)
+  MMD_HD static void hess_contract(const Coef& c, const double* x, const double* v, const double* Th, double* g) {
+    if (x[0] > -500.0 && x[1] > -500.0) { hess_contract_raw(c, x, v, Th, g); return; }
+    double xc[3]; bool held[3];
+    clip_state(x, xc, held);
+    double Tm[(X + V + Z) * X];
+    for (int b = 0; b < X + V + Z; ++b)
+      for (int i = 0; i < X; ++i) Tm[b * X + i] = (held[i] || (b < X && held[b])) ? 0.0 : Th[b * X + i];
+    hess_contract_raw(c, xc, v, Tm, g);
+    for (int a = 0; a < X; ++a)
+      if (held[a]) g[a] = 0.0;
+  }
 ''',
-        step_name="step_raw",
+        step_name="step_raw", deriv_suffix="_raw",
     )
 
 
