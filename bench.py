@@ -194,7 +194,10 @@ def run_ours(args):
 
     from manifold_mcmc_for_diffusions_b200 import diagnostics, example_models, parallel
 
-    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank"
+    # every rank (also a single one) runs next to its GPU: the page-locked buffers of the end-to-end leg are then
+    # allocated on that NUMA node; the original affinity comes back before the CPU baseline uses all the cores
+    orig_affinity = os.sched_getaffinity(0)
+    affinity = bind_to_gpu_numa_node(local_rank)
     strong = args.scaling == "strong"
     if strong:
         # BASELINE.json config 5: a fixed population sharded over the ranks (contiguous ranges, Philox streams and
@@ -493,6 +496,7 @@ def run_ours(args):
         }
         if diag is not None:
             out["diagnostics"] = diag
+        os.sched_setaffinity(0, orig_affinity)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds, dt=args.dt, L=L, burnin=args.burnin,
                                                burnin_dt=args.burnin_dt)

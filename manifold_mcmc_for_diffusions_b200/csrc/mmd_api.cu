@@ -149,6 +149,20 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   }
   if (cfg->device < 0 || cfg->device >= ndev) FAIL("bad device ordinal");
   DevGuard guard_(cfg->device);
+  {
+    // L2 set-aside for persisting lines: the evict_last hints on the per-iteration block factors (mmd_sweeps.cuh)
+    // only retain anything when a persisting carve-out exists (default size 0).  MMD_L2_PERSIST_MB overrides.
+    const char* e = getenv("MMD_L2_PERSIST_MB");
+    const long long mb = e ? atoll(e) : MMD_L2_PERSIST_MB_DEFAULT;
+    if (mb >= 0) {
+      int maxp = 0;
+      cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
+      size_t want = (size_t)mb << 20;
+      if (want > (size_t)maxp) want = (size_t)maxp;
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaGetLastError();
+    }
+  }
   const int NRMAX = ops->nrmax, RMAX = ops->rmax;
   const int T = cfg->num_obs, S = cfg->num_steps_per_obs;
   int R = cfg->num_obs_per_subseq;

@@ -40,6 +40,9 @@ constexpr int UMAX = 5;      // max dim_u
 #define MMD_NTMAX 192         // max threads per CTA (= chains per tile x observation blocks)
 #endif
 constexpr int NTMAX = MMD_NTMAX;
+#ifndef MMD_L2_PERSIST_MB_DEFAULT
+#define MMD_L2_PERSIST_MB_DEFAULT (-1)   // persisting-L2 carve-out set by mmd_create in MB (-1: leave the device limit alone)
+#endif
 #ifndef MMD_MINB
 #define MMD_MINB 3           // __launch_bounds__ min resident CTAs per SM for the phase kernels
 #endif

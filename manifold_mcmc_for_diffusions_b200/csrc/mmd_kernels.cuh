@@ -31,6 +31,12 @@
 #ifndef MMD_POINT_L2_PREFETCH
 #define MMD_POINT_L2_PREFETCH 0   // look-ahead (steps) of the HBM -> L2 prefetch in the linearisation sweeps (0 = off)
 #endif
+#ifndef MMD_POINT_L1_PREFETCH
+#define MMD_POINT_L1_PREFETCH 0   // look-ahead (steps) of the L1 prefetch in the linearisation sweeps (0 = off)
+#endif
+#ifndef MMD_POINTWISE_L1_PREFETCH
+#define MMD_POINTWISE_L1_PREFETCH 0   // look-ahead (steps) of the L1 prefetch in the pointwise passes (0 = off)
+#endif
 // compiler-only barrier: values read from shared memory are re-read after it instead of being kept in registers
 #ifndef MMD_SMEM_RELOAD
 #define MMD_SMEM_RELOAD asm volatile("" ::: "memory")

@@ -34,7 +34,7 @@ struct SmemPlan {
 // grad_log_det_sqrt_gram (:1143-1146, :1173-1184) by a hand-derived second-order adjoint.
 // ------------------------------------------------------------------------------------------
 template <class M, int NRMAX, int RMAX, int UMAX>
-MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ y, int part,
+MMD_PHASE void dev_point(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ y, int part,
                      int which, int with_grad) {
   const Tid t = thread_id(d);
   MMD_SMEM_SETUP
@@ -108,6 +108,9 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
 #if MMD_POINT_L2_PREFETCH > 0
         if (k * d.S + tt + MMD_POINT_L2_PREFETCH < B.n * d.S) prefetch_l2(vp + (tt + MMD_POINT_L2_PREFETCH) * V * nta);
 #endif
+#if MMD_POINT_L1_PREFETCH > 0
+        if (k * d.S + tt + MMD_POINT_L1_PREFETCH < B.n * d.S) prefetch_l1(vp + (tt + MMD_POINT_L1_PREFETCH) * V * nta);
+#endif
         strec<X>(xk + tt * X * nta, x);
         double v[V], xn[X];
         ldrec<V>(vp + tt * V * nta, v);
@@ -129,6 +132,12 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
         MMD_SMEM_RELOAD;
         // one Jacobian at a time (little live at once): K_t, then Z_k, then Psi
         double xt[X], v[V];
+#if MMD_POINT_L1_PREFETCH > 0
+        if (tt >= MMD_POINT_L1_PREFETCH) {
+          prefetch_l1(xk + (tt - MMD_POINT_L1_PREFETCH) * X * nta);
+          prefetch_l1(vp + (tt - MMD_POINT_L1_PREFETCH) * V * nta);
+        }
+#endif
         ldrec<X>(xk + tt * X * nta, xt);
         ldrec<V>(vp + tt * V * nta, v);
         {
@@ -574,6 +583,13 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
           prefetch_l2(Kk + (tt + MMD_POINT_L2_PREFETCH) * XV * nta);
         }
 #endif
+#if MMD_POINT_L1_PREFETCH > 0
+        if (tt + MMD_POINT_L1_PREFETCH < d.S) {
+          prefetch_l1(xk + (tt + MMD_POINT_L1_PREFETCH) * X * nta);
+          prefetch_l1(vp + (tt + MMD_POINT_L1_PREFETCH) * V * nta);
+          prefetch_l1(Kk + (tt + MMD_POINT_L1_PREFETCH) * XV * nta);
+        }
+#endif
         // Y <- F Y + B (K^T M) + G Lam, one Jacobian at a time
         double xt[X], v[V], Yn[X * X];
         ldrec<X>(xk + tt * X * nta, xt);
@@ -618,6 +634,13 @@ MMD_D void dev_point(const Dims& d, const Slots& S, const Work& W, const double*
           prefetch_l2(xk + sp * X * nta);
           prefetch_l2(vp + sp * V * nta);
           prefetch_l2(Kk + sp * XV * nta);
+        }
+#endif
+#if MMD_POINT_L1_PREFETCH > 0
+        if (tt >= MMD_POINT_L1_PREFETCH) {
+          prefetch_l1(xk + (tt - MMD_POINT_L1_PREFETCH) * X * nta);
+          prefetch_l1(vp + (tt - MMD_POINT_L1_PREFETCH) * V * nta);
+          prefetch_l1(Yk + (tt - MMD_POINT_L1_PREFETCH) * X * X * nta);
         }
 #endif
         ldrec<X>(xk + tt * X * nta, xt);
@@ -758,7 +781,7 @@ MMD_D void dev_constr(const Dims& d, const Slots& S, const Work& W, const double
 // ------------------------------------------------------------------------------------------
 
 template <class M, int NRMAX, int RMAXP, int UMAX>
-MMD_D void dev_project(const Dims& d, const Slots& S, const Work& W, int part, int lin_sel, int src_sel,
+MMD_PHASE void dev_project(const Dims& d, const Slots& S, const Work& W, int part, int lin_sel, int src_sel,
                        int dst_sel, double h, double qcoef, FlowCoef fl, int force = -1) {
   const Tid t = thread_id(d);
   MMD_SMEM_SETUP
@@ -1308,7 +1331,7 @@ MMD_D double qn_pass(const Dims& d, const Slots& S, const Work& W, const Blk& B,
 }
 
 template <class M, int NRMAX, int RMAXP, int UMAX, bool NEWTON>
-MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ y, int part, int mode,
+MMD_PHASE void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __restrict__ y, int part, int mode,
                   double mom_coef, double ctol, double ptol, double dtol, int max_iters) {
   const Tid t = thread_id(d);
   MMD_SMEM_SETUP
@@ -1366,6 +1389,11 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
   double final_norm = 0.0;
   ChainPar<M, UMAX> Pkeep;
   PH_T0
+#if defined(MMD_NO_FIRST_PASS_SKIP)
+  bool first_pass = false;
+#else
+  bool first_pass = true;
+#endif
   while (true) {
     const bool work = in_blk && !done;
     double sres[UMAX], err = 0.0;
@@ -1396,7 +1424,10 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
         a.xs_out = NEWTON ? tpr<X>(W.xs, d.rmax * d.S * X, t) : nullptr;
         if (NEWTON && !M::OBS_LINEAR) a.xend_out = tp(W.Yb, d.rmax * X * X, t);
         a.nta = nta; a.cpb = cpb; a.NT = NT; a.tid = t.tid;
-        constr_sweep<M, true, NEWTON>(d, B, a);
+        // first pass of the loop: lam_tot = 0, the iterate is q_w itself -- no need to stream K (the products with
+        // alpha = 0 leave v bit-for-bit unchanged)
+        if (first_pass) constr_sweep<M, false, NEWTON>(d, B, a);
+        else constr_sweep<M, true, NEWTON>(d, B, a);
       }
       if (NEWTON) Pkeep = P;
     }
@@ -1481,6 +1512,7 @@ MMD_D void dev_qn(const Dims& d, const Slots& S, const Work& W, const double* __
       }
       PH(11);
     }
+    first_pass = false;
     if (!done) {
       it += 1;
       const bool diverged = (err > dtol) || (err != err);
@@ -1541,23 +1573,23 @@ MMD_D void dev_commit(const Dims& d, const Slots& S, const Work& W, double rev_t
 #if defined(__CUDACC__)
 template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB>
 __global__ void __launch_bounds__(NTMAX, MINB)
-k_point(Dims d, Slots S, Work W, const double* __restrict__ y, int part, int which, int with_grad) {
+k_point(const __grid_constant__ Dims d, const __grid_constant__ Slots S, const __grid_constant__ Work W, const double* __restrict__ y, int part, int which, int with_grad) {
   dev_point<M, NRMAX, RMAX, UMAX>(d, S, W, y, part, which, with_grad);
 }
 template <class M, int NRMAX, int UMAX, int NTMAX, int MINB>
 __global__ void __launch_bounds__(NTMAX, MINB)
-k_constr(Dims d, Slots S, Work W, const double* __restrict__ y, int part, double* __restrict__ cout) {
+k_constr(const __grid_constant__ Dims d, const __grid_constant__ Slots S, const __grid_constant__ Work W, const double* __restrict__ y, int part, double* __restrict__ cout) {
   dev_constr<M, NRMAX, UMAX>(d, S, W, y, part, cout);
 }
 template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB>
 __global__ void __launch_bounds__(NTMAX, MINB)
-k_project(Dims d, Slots S, Work W, int part, int lin_sel, int src_sel, int dst_sel, double h, double qcoef,
+k_project(const __grid_constant__ Dims d, const __grid_constant__ Slots S, const __grid_constant__ Work W, int part, int lin_sel, int src_sel, int dst_sel, double h, double qcoef,
           FlowCoef fl) {
   dev_project<M, NRMAX, RMAX, UMAX>(d, S, W, part, lin_sel, src_sel, dst_sel, h, qcoef, fl);
 }
 template <class M, int NRMAX, int RMAX, int UMAX, int NTMAX, int MINB, bool NEWTON>
 __global__ void __launch_bounds__(NTMAX, MINB)
-k_qn(Dims d, Slots S, Work W, const double* __restrict__ y, int part, int mode, double mom_coef, double ctol,
+k_qn(const __grid_constant__ Dims d, const __grid_constant__ Slots S, const __grid_constant__ Work W, const double* __restrict__ y, int part, int mode, double mom_coef, double ctol,
      double ptol, double dtol, int max_iters) {
   dev_qn<M, NRMAX, RMAX, UMAX, NEWTON>(d, S, W, y, part, mode, mom_coef, ctol, ptol, dtol, max_iters);
 }
@@ -1578,7 +1610,7 @@ __global__ void __maxnreg__(MMD_LEAPFROG_MAXNREG)
 #else
 __global__ void __launch_bounds__(NTMAX, MINB)
 #endif
-k_leapfrog(Dims d, Slots S, Work W, const double* __restrict__ y, int part, double dt, double ctol, double ptol,
+k_leapfrog(const __grid_constant__ Dims d, const __grid_constant__ Slots S, const __grid_constant__ Work W, const double* __restrict__ y, int part, double dt, double ctol, double ptol,
            double dtol, int max_iters, double rev_tol, long long* __restrict__ n_ok, int n_steps,
            int reset_status) {
   const Tid t = thread_id(d);

@@ -73,16 +73,26 @@ MMD_D double ldg_keep(const double* g) {
   return *g;
 #endif
 }
+// The 16-byte copies allocate in L1 (.ca, not the L1-bypassing .cg): a thread's X*V-double record is fetched in
+// 16-byte pieces at a lane stride of X*V*8 bytes, so every copy instruction of a warp touches half of each 32-byte
+// sector and the next one the other half.  With .cg both requests go to L2 and the sweeps saturate the L2 request
+// path at 4.5 TB/s of useful bytes; with .ca the second one hits L1: 6.9 TB/s, next to the 7.2 TB/s of CTA-wide
+// cp.async.bulk copies (tools/stream_bench.cu, profiles/r2_stream_bench.json).
+#if defined(MMD_CP_ASYNC_CG)
+#define MMD_CP16 "cp.async.cg"
+#else
+#define MMD_CP16 "cp.async.ca"
+#endif
 template <int BYTES>
 MMD_D void cp_async(unsigned sdst, const void* gsrc) {
 #if defined(MMD_HINT_STREAM)
   if (BYTES == 16)
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sdst), "l"(gsrc), "l"(l2_policy_stream()) : "memory");
+    asm volatile(MMD_CP16 ".shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sdst), "l"(gsrc), "l"(l2_policy_stream()) : "memory");
   else
     asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;\n" ::"r"(sdst), "l"(gsrc), "l"(l2_policy_stream()) : "memory");
 #else
   if (BYTES == 16)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+    asm volatile(MMD_CP16 ".shared.global [%0], [%1], 16;\n" ::"r"(sdst), "l"(gsrc) : "memory");
   else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst), "l"(gsrc) : "memory");
 #endif
@@ -93,6 +103,7 @@ MMD_D void ldcol_keep(const double* g, int ld, double* r) {  // ldcol with the e
   for (int i = 0; i < N; ++i) r[i] = ldg_keep(g + i * ld);
 }
 MMD_D void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(g)); }
+MMD_D void prefetch_l1(const void* g) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(g)); }
 MMD_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 MMD_D void cp_async_wait() {
