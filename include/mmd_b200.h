@@ -224,6 +224,25 @@ int mmd_project_quasi_newton(mmd_handle h, const double* q_in, double dt, const 
 int mmd_init_linear_interpolation(mmd_handle h, const double* u, const double* v_0, const double* x_obs_seq,
                                   int partition);
 
+/* Standard-HMC target of the noisy-observation model: conditioned_diffusion_neg_log_dens_and_grad
+ * (sde/mici_extensions.py:82-205; the EuclideanMetricSystem baseline of scripts/*_hmc_experiment.py).
+ * q [n][mmd_hmc_dim] = [u | v_0 | v_seq] (no observation-noise variables), host.  val [n] receives
+ *   1/2 sum_k ((y_k - h(x_k)) / sigma)^2 + T dim_y log sigma  (+ 1/2 |q|^2 when add_prior != 0, i.e. without
+ * Gaussian splitting, :183-187); grad [n][mmd_hmc_dim] its gradient (the reference: jax.value_and_grad through
+ * lax.scan, :189) and resid [n][T] the scaled residuals (y - h(x)) / sigma; grad and resid may be NULL.  Needs a
+ * handle created with observation noise (fixed or inferred). */
+int mmd_hmc_dim(mmd_handle h);
+int mmd_hmc_target(mmd_handle h, const double* q, int add_prior, double* val, double* grad, double* resid);
+/* Batched Adam descent on that objective: find_initial_state_by_gradient_descent_noisy_system (:1679-1801; Adam as
+ * jax.experimental.optimizers.adam, :1733).  begin: (re)start the chains with mask != 0 (NULL: all) from
+ * u_v [n][mmd_hmc_dim] with cleared moments and iteration counter; eval: objective gradient and residuals at the
+ * current iterates, msr [n] = mean squared residual (:1759), val [n] (may be NULL) the objective; update: one Adam
+ * step (:1737-1741) for the chains with upd != 0; get: the iterates and the residuals of the last eval. */
+int mmd_adam_begin(mmd_handle h, const double* u_v, const int* mask);
+int mmd_adam_eval(mmd_handle h, double* msr, double* val);
+int mmd_adam_update(mmd_handle h, double step_size, const int* upd);
+int mmd_adam_get(mmd_handle h, double* u_v, double* resid);
+
 /* number of kernel launches issued since creation (bench.py's gpu_launches) and event timing on the
  * handle's stream */
 long long mmd_launch_count(mmd_handle h);

@@ -118,6 +118,12 @@ SIGNATURES = {
     "mmd_debug_phase_cycles": (C.c_int, [_H, C.POINTER(C.c_ulonglong), C.c_int]),
     "mmd_profile_enable": (C.c_int, [_H, C.c_int, C.c_int]),
     "mmd_profile_summary": (C.c_int, [_H, C.c_int, _ip, _dp]),
+    "mmd_hmc_dim": (C.c_int, [_H]),
+    "mmd_hmc_target": (C.c_int, [_H, _dp, C.c_int, _dp, _dp, _dp]),
+    "mmd_adam_begin": (C.c_int, [_H, _dp, _ip]),
+    "mmd_adam_eval": (C.c_int, [_H, _dp, _dp]),
+    "mmd_adam_update": (C.c_int, [_H, C.c_double, _ip]),
+    "mmd_adam_get": (C.c_int, [_H, _dp, _dp]),
     "mmd_launch_count": (C.c_longlong, [_H]),
     "mmd_timer_start": (C.c_int, [_H]),
     "mmd_timer_stop_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),

@@ -62,6 +62,7 @@ class BatchedChains:
         self._h = C.c_void_p()
         check(self._L.mmd_create(C.byref(cfg), C.byref(self._h)))
         self.n_chains = int(n_chains)
+        self._model = model
         self._dim_u = int(dim_u)
         self._dim_v_0 = {"fhn": 2, "fhn_notebook": 2, "sir": 1}[model]
         self._sigma_fixed = float(sigma_fixed)
@@ -202,6 +203,105 @@ class BatchedChains:
         u, v_0, x = _c(u), _c(v_0), _c(x_obs_seq)
         self._dim_x = x.shape[2]
         check(self._L.mmd_init_linear_interpolation(self._h, _dp(u), _dp(v_0), _dp(x), int(partition)))
+
+    # ---- standard-HMC target and the Adam initialiser (noisy-observation systems) --------------------
+    @property
+    def hmc_dim(self):
+        """dim_u + dim_v_0 + T S dim_v: the position of the standard-HMC target has no noise variables."""
+        return int(self._L.mmd_hmc_dim(self._h))
+
+    def neg_log_dens_and_grad(self, q, use_gaussian_splitting=False, with_grad=True, with_residuals=False):
+        """Batched ``conditioned_diffusion_neg_log_dens_and_grad`` (mici_extensions.py:82-205): q [n_chains, hmc_dim]
+        -> (value [n], gradient [n, hmc_dim] or None[, residuals [n, T]])."""
+        q = _c(q)
+        assert q.shape == (self.n_chains, self.hmc_dim), q.shape
+        val = np.empty(self.n_chains)
+        grad = np.empty_like(q) if with_grad else None
+        res = np.empty((self.n_chains, self.num_obs)) if with_residuals else None
+        check(self._L.mmd_hmc_target(self._h, _dp(q), int(not use_gaussian_splitting), _dp(val),
+                                     None if grad is None else _dp(grad), None if res is None else _dp(res)))
+        return (val, grad, res) if with_residuals else (val, grad)
+
+    def init_gradient_descent(self, rngs, adam_step_size=2e-2, max_iters=1000, max_init_tries=100, max_num_tries=10,
+                              threshold=1.0, slow_progress_ratio=0.8, check_iter=100, partition=0):
+        """Batched ``find_initial_state_by_gradient_descent_noisy_system`` (mici_extensions.py:1679-1801): every
+        chain runs the reference's procedure with its own generator ``rngs[c]`` -- draw u_v ~ N(0, I) until the
+        residuals are finite (:1745-1752), Adam on 1/2 |r|^2 + T log sigma + 1/2 |u_v|^2 (:1701-1731) until the mean
+        squared residual of the CURRENT iterate is below ``threshold`` (:1757-1763), restart on divergence (:1760-1762)
+        or slow progress (:1780-1788) -- with all gradient evaluations and Adam updates on the device.  On success
+        the resident position is [u_v | residuals] (:1767-1771) with x_obs_seq regenerated; returns (q, tries)."""
+        n, dim, T = self.n_chains, self.hmc_dim, self.num_obs
+        u_v = np.empty((n, dim))
+        tries = np.zeros(n, dtype=np.int32)         # Adam runs started per chain
+        done = np.zeros(n, dtype=bool)
+        it = np.zeros(n, dtype=np.int64)
+        prev = np.zeros(n)
+        q_out = np.empty((n, self.dim_q))
+
+        def fresh(idx):
+            # a finite starting point per chain (:1745-1755)
+            need = np.array(idx, dtype=np.int64)
+            init_tries = np.zeros(n, dtype=np.int64)
+            while need.size:
+                for c in need:
+                    u_v[c] = rngs[c].standard_normal(dim)
+                    init_tries[c] += 1
+                _, _, res = self.neg_log_dens_and_grad(u_v_safe(), with_grad=False, with_residuals=True)
+                ok = np.isfinite(res).all(axis=1)
+                need = np.array([c for c in need if not ok[c]], dtype=np.int64)
+                if need.size and init_tries[need].max() >= max_init_tries:
+                    raise RuntimeError(f"Did not find valid initial state in {max_init_tries} tries.")
+            mask = np.zeros(n, dtype=np.int32)
+            mask[idx] = 1
+            check(self._L.mmd_adam_begin(self._h, _dp(u_v), _ip(mask)))
+            it[idx] = 0
+            tries[idx] += 1
+            _, _, res = self.neg_log_dens_and_grad(u_v_safe(), with_grad=False, with_residuals=True)
+            prev[idx] = np.mean(res[idx] ** 2, axis=1)
+
+        def u_v_safe():
+            # chains that are finished keep their last (finite) row; rows never drawn yet are zero
+            return np.where(np.isfinite(u_v), u_v, 0.0)
+
+        u_v[:] = 0.0
+        fresh(list(range(n)))
+        msr = np.empty(n)
+        while not done.all():
+            check(self._L.mmd_adam_eval(self._h, _dp(msr), None))
+            active = ~done
+            diverged = active & ~np.isfinite(msr)
+            found = active & np.isfinite(msr) & (msr < threshold)
+            if found.any():
+                cur = np.empty((n, dim))
+                res = np.empty((n, T))
+                check(self._L.mmd_adam_get(self._h, _dp(cur), _dp(res)))
+                for c in np.nonzero(found)[0]:
+                    q_out[c] = np.concatenate([cur[c], res[c]])
+                    u_v[c] = cur[c]
+                done |= found
+            cont = active & ~diverged & ~found
+            # slow-progress test on the iterations the reference checks (:1777-1792)
+            chk = cont & (it % check_iter == 0)
+            slow = chk & (it > 0) & (it < max_iters // 2) & (msr / np.where(prev > 0, prev, 1.0) > slow_progress_ratio)
+            prev = np.where(chk & ~slow, msr, prev)
+            upd = cont & ~slow
+            exhausted = upd & (it + 1 >= max_iters)
+            if upd.any():
+                check(self._L.mmd_adam_update(self._h, float(adam_step_size), _ip(upd.astype(np.int32))))
+                it[upd] += 1
+            restart = diverged | slow | exhausted
+            if restart.any():
+                idx = [int(c) for c in np.nonzero(restart)[0]]
+                if (tries[idx] >= max_num_tries).any():
+                    raise RuntimeError(f"Did not find valid state in {max_num_tries} tries.")
+                fresh(idx)
+        xo = np.zeros((n, T, self._dim_x_model()))
+        self.set_state(q_out, xo, partition)
+        self.update_x_obs_seq()
+        return q_out, tries
+
+    def _dim_x_model(self):
+        return {"fhn": 2, "fhn_notebook": 2, "sir": 3}[self._model]
 
     def set_momentum(self, p):
         check(self._L.mmd_set_momentum(self._h, _dp(_c(p))))

@@ -3,6 +3,7 @@
 // every entry point fails with an error if CUDA is unavailable.
 #include "mmd_host.h"
 #include "mmd_kernels_main.cuh"
+#include "mmd_hmc_target.cuh"
 
 using namespace mmd;
 
@@ -111,6 +112,40 @@ int regroup_plan(mmd_handle h) {
   CK(cudaMemcpyAsync(h->slot_chain, sc.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));   // the host vectors go out of scope
   return 0;
+}
+
+// standard-HMC target / Adam initialiser scratch, allocated on first use
+int ht_reserve(mmd_handle h) {
+  if (h->ht_q) return 0;
+  if (h->d.noisy == MMD_NOISE_NONE) FAIL("the standard-HMC target needs observation noise (noise = 1 or 2)");
+  const size_t n = (size_t)h->d.n_chains;
+  h->ht_dim = h->d.off_n;
+  const size_t tot = (size_t)h->ht_dim * n;
+  if (dalloc(h, &h->ht_q, tot) || dalloc(h, &h->ht_g, tot) || dalloc(h, &h->ht_m, tot) || dalloc(h, &h->ht_v, tot) ||
+      dalloc(h, &h->ht_xs, ((size_t)h->d.T * h->d.S + 1) * h->X * n) || dalloc(h, &h->ht_val, n) ||
+      dalloc(h, &h->ht_res, (size_t)h->d.T * n) || dalloc(h, &h->ht_msr, n) || dalloc(h, &h->ht_it, n) ||
+      dalloc(h, &h->ht_mask, n) || dalloc(h, &h->ht_qin, tot) || dalloc(h, &h->ht_gout, tot) ||
+      dalloc(h, &h->ht_res2, (size_t)h->d.T * n))
+    return -2;
+  return 0;
+}
+int ht_upload(mmd_handle h, const double* q_host, int ld, const int* mask_dev, double* dstT) {
+  const int n = h->d.n_chains, dim = h->ht_dim;
+  // canonical rows go through the staging buffer (ld doubles per chain, ld <= dim_q)
+  if (h2d_stage(h, q_host, h->stage, (size_t)n * ld)) return -2;
+  dim3 grid((n + 31) / 32, (dim + 31) / 32), blk(32, 8);
+  k_transpose_in<<<grid, blk, 0, h->stream>>>(n, dim, ld, h->stage, dstT, mask_dev);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+int ht_download(mmd_handle h, const double* srcT, double* host, int ld) {
+  const int n = h->d.n_chains, dim = h->ht_dim;
+  dim3 grid((n + 31) / 32, (dim + 31) / 32), blk(32, 8);
+  k_transpose_out<<<grid, blk, 0, h->stream>>>(n, dim, ld, srcT, h->stage);
+  h->launches++;
+  CK(cudaGetLastError());
+  return d2h_sync(h, host, h->stage, (size_t)n * ld);
 }
 
 }  // namespace
@@ -1043,4 +1078,101 @@ int mmd_timer_stop_ms(mmd_handle h, float* ms) {
 }
 int mmd_synchronize(mmd_handle h) { MMD_GUARD(h); CK(cudaStreamSynchronize(h->stream)); return 0; }
 
+
+// ---- standard-HMC target (conditioned_diffusion_neg_log_dens_and_grad, mici_extensions.py:82-205) --------------
+int mmd_hmc_dim(mmd_handle h) { return h->d.off_n; }
+int mmd_hmc_target(mmd_handle h, const double* q, int add_prior, double* val, double* grad, double* resid) {
+  MMD_GUARD(h);
+  if (!q || !val) FAIL("null argument");
+  if (ht_reserve(h)) return -1;
+  const int n = h->d.n_chains, dim = h->ht_dim;
+  if (ht_upload(h, q, dim, nullptr, h->ht_qin)) return -2;
+  if (DISPATCH(h, hmc_target(h, h->ht_qin, h->ht_xs, h->ht_val, grad ? h->ht_gout : nullptr,
+                             resid ? h->ht_res2 : nullptr, n, add_prior, nullptr)))
+    return -2;
+  if (grad && ht_download(h, h->ht_gout, grad, dim)) return -2;
+  if (resid) {
+    // residuals come back as [chain][T]
+    dim3 grid((n + 31) / 32, (h->d.T + 31) / 32), blk(32, 8);
+    k_transpose_out<<<grid, blk, 0, h->stream>>>(n, h->d.T, h->d.T, h->ht_res2, h->stage);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (d2h_sync(h, resid, h->stage, (size_t)n * h->d.T)) return -2;
+  }
+  return d2h_sync(h, val, h->ht_val, (size_t)n);
+}
+
+// ---- Adam initialiser for noisy systems (find_initial_state_by_gradient_descent_noisy_system, :1679-1801) ------
+// begin: (re)start the chains with mask != 0 (NULL: all) from u_v [n][dim]; their Adam moments and iteration
+// counters are cleared.  eval: objective gradient and residuals at the current iterates, returns the mean squared
+// residual per chain.  update: one Adam step for the chains with upd != 0 (their iteration counter advances).
+int mmd_adam_begin(mmd_handle h, const double* u_v, const int* mask) {
+  MMD_GUARD(h);
+  if (!u_v) FAIL("null argument");
+  if (ht_reserve(h)) return -1;
+  const int n = h->d.n_chains;
+  const long long tot = (long long)h->ht_dim * n;
+  int* mdev = nullptr;
+  if (mask) {
+    CK(cudaMemcpyAsync(h->ht_mask, mask, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    mdev = h->ht_mask;
+  }
+  if (ht_upload(h, u_v, h->ht_dim, mdev, h->ht_q)) return -2;
+  k_zero_masked<<<1184, 256, 0, h->stream>>>(n, tot, h->ht_m, mdev);
+  k_zero_masked<<<1184, 256, 0, h->stream>>>(n, tot, h->ht_v, mdev);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  if (mask) {
+    std::vector<int> it(n);
+    CK(cudaMemcpyAsync(it.data(), h->ht_it, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < n; ++c)
+      if (mask[c]) it[c] = 0;
+    CK(cudaMemcpyAsync(h->ht_it, it.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  } else {
+    CK(cudaMemsetAsync(h->ht_it, 0, n * sizeof(int), h->stream));
+  }
+  return 0;
+}
+int mmd_adam_eval(mmd_handle h, double* msr_out, double* val_out) {
+  MMD_GUARD(h);
+  if (!h->ht_q) FAIL("mmd_adam_begin first");
+  const int n = h->d.n_chains;
+  if (DISPATCH(h, hmc_target(h, h->ht_q, h->ht_xs, h->ht_val, h->ht_g, h->ht_res, n, 1, nullptr))) return -2;
+  k_mean_sq_rows<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d.T, h->ht_res, h->ht_msr);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (val_out) CK(cudaMemcpyAsync(val_out, h->ht_val, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (msr_out) return d2h_sync(h, msr_out, h->ht_msr, (size_t)n);
+  return 0;
+}
+int mmd_adam_update(mmd_handle h, double step_size, const int* upd) {
+  MMD_GUARD(h);
+  if (!h->ht_q) FAIL("mmd_adam_begin first");
+  if (!upd) FAIL("null argument");
+  const int n = h->d.n_chains;
+  const long long tot = (long long)h->ht_dim * n;
+  CK(cudaMemcpyAsync(h->ht_mask, upd, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  k_adam_update<<<1184, 256, 0, h->stream>>>(n, tot, h->ht_q, h->ht_g, h->ht_m, h->ht_v, h->ht_it, h->ht_mask, step_size);
+  k_add_masked<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->ht_it, h->ht_mask);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));   // `upd` may be reused by the caller
+  return 0;
+}
+int mmd_adam_get(mmd_handle h, double* u_v, double* resid) {
+  MMD_GUARD(h);
+  if (!h->ht_q) FAIL("mmd_adam_begin first");
+  const int n = h->d.n_chains;
+  if (u_v && ht_download(h, h->ht_q, u_v, h->ht_dim)) return -2;
+  if (resid) {
+    dim3 grid((n + 31) / 32, (h->d.T + 31) / 32), blk(32, 8);
+    k_transpose_out<<<grid, blk, 0, h->stream>>>(n, h->d.T, h->d.T, h->ht_res, h->stage);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (d2h_sync(h, resid, h->stage, (size_t)n * h->d.T)) return -2;
+  }
+  return 0;
+}
 }  // extern "C"

@@ -98,6 +98,11 @@ struct mmd_handle_s {
   bool adapting;
   double ad_target, ad_reg_coef, ad_decay, ad_offset;
   double* ad_state;  // [4][chains]: iteration count, smoothed log step size, adapt-stat error, reg target
+  // standard-HMC target / Adam initialiser (allocated on first use): transposed [dim_uv][chains] arrays
+  int ht_dim;                 // dim_u + dim_v_0 + T S dim_v
+  double *ht_q, *ht_g, *ht_m, *ht_v, *ht_xs, *ht_val, *ht_res, *ht_msr;
+  double *ht_qin, *ht_gout, *ht_res2;   // mmd_hmc_target's own input / outputs (the Adam iterates stay untouched)
+  int *ht_it, *ht_mask;
   std::vector<double*> aux;   // auxiliary q-like arrays of the host-driven tree builder
   int* maskbuf;               // [chains] device copy of the caller's chain mask
 };
@@ -142,6 +147,8 @@ struct mmd_ops {
   int (*init_interp)(mmd_handle);
   int (*philox)(mmd_handle, uint64_t, uint64_t);
   void (*constr_rows)(mmd_handle, const std::vector<double>&, double*);
+  // standard-HMC target: value / gradient / residuals for n chains in transposed layout (mmd_hmc_target.cuh)
+  int (*hmc_target)(mmd_handle, const double*, double*, double*, double*, double*, int, int, const int*);
 };
 const mmd_ops* mmd_ops_fhn();
 const mmd_ops* mmd_ops_fhn_r5();   // blocks of <= 5 observations / 6 constraint rows

@@ -2,6 +2,7 @@
 #pragma once
 #include "mmd_host.h"
 #include "mmd_kernels_main.cuh"
+#include "mmd_hmc_target.cuh"
 
 using namespace mmd;
 
@@ -144,6 +145,14 @@ struct Ops {
     CK(cudaGetLastError());
     return 0;
   }
+  static int hmc_target(mmd_handle h, const double* qT, double* xs, double* val, double* gT, double* resid, int n,
+                        int add_prior, const int* active) {
+    k_hmc_target<Mdl, UMAX><<<(n + 127) / 128, 128, 0, h->stream>>>(h->d, h->y, qT, xs, val, gT, resid, n, add_prior,
+                                                                    active);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
   static void constr_rows(mmd_handle h, const std::vector<double>& buf, double* c_out) {
     // thread-private [tile][NRMAX][nta] -> [chain][n_c]: rows of block b start at its row0
     const Dims& d = h->d;
@@ -167,7 +176,7 @@ mmd_ops make_ops() {
   t.X = Mdl::X; t.V = Mdl::V; t.Z = Mdl::Z; t.V0 = Mdl::V0; t.Y = Mdl::Y; t.nrmax = NRMAX; t.rmax = RMAX;
   t.point = O::point; t.constr = O::constr; t.project = O::project; t.qn = O::qn; t.leapfrog = O::leapfrog;
   t.hamiltonian = O::hamiltonian; t.pack = O::pack; t.unpack = O::unpack; t.retile = O::retile;
-  t.vec_uturn = O::vec_uturn; t.gen_xobs = O::gen_xobs; t.init_interp = O::init_interp; t.philox = O::philox; t.constr_rows = O::constr_rows;
+  t.vec_uturn = O::vec_uturn; t.gen_xobs = O::gen_xobs; t.init_interp = O::init_interp; t.philox = O::philox; t.constr_rows = O::constr_rows; t.hmc_target = O::hmc_target;
   return t;
 }
 

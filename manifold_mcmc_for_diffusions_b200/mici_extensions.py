@@ -8,6 +8,9 @@ library through the C ABI (``include/mmd_b200.h``).  Mici samplers / integrators
     jitted_solve_projection_onto_manifold_quasi_newton   :1323-1402
     jitted_solve_projection_onto_manifold_newton         :1405-1476
     find_initial_state_by_linear_interpolation           :1479-1547
+    find_initial_state_by_gradient_descent_noisy_system  :1679-1801
+    conditioned_diffusion_neg_log_dens_and_grad          :82-205   (the standard-HMC baseline's target)
+    OnlineBlockDiagonalMetricAdapter                     :1804-1931
     split, split_and_reshape                :31-53
 
 This module is the *compatibility* path: one Mici chain = one resident chain on the device, one C
@@ -23,14 +26,18 @@ from numbers import Number
 import numpy as np
 
 try:  # prefer the real Mici when it is installed
-    from mici.errors import ConvergenceError
-    from mici.matrices import IdentityMatrix
+    from mici.adapters import Adapter
+    from mici.errors import AdaptationError, ConvergenceError, HamiltonianDivergenceError
+    from mici.matrices import (DensePositiveDefiniteMatrix, IdentityMatrix,
+                               PositiveDefiniteBlockDiagonalMatrix)
     from mici.states import ChainState, _cache_key_func
     from mici.systems import System, cache_in_state, cache_in_state_with_aux
     from mici.transitions import Transition
 except ImportError:  # pragma: no cover - exercised in this environment
-    from .mici_compat.errors import ConvergenceError
-    from .mici_compat.matrices import IdentityMatrix
+    from .mici_compat.adapters import Adapter
+    from .mici_compat.errors import AdaptationError, ConvergenceError, HamiltonianDivergenceError
+    from .mici_compat.matrices import (DensePositiveDefiniteMatrix, IdentityMatrix,
+                                       PositiveDefiniteBlockDiagonalMatrix)
     from .mici_compat.states import ChainState, _cache_key_func, cache_in_state, cache_in_state_with_aux
     from .mici_compat.systems import System
     from .mici_compat.transitions import Transition
@@ -457,6 +464,140 @@ def find_initial_state_by_linear_interpolation(system, rng, generate_x_obs_seq_i
     state = ConditionedDiffusionHamiltonianState(pos=q[0], x_obs_seq=x_obs_seq)
     state.mom = system.sample_momentum(state, rng)
     return state
+
+
+def conditioned_diffusion_neg_log_dens_and_grad(obs_interval, num_steps_per_obs, y_seq, dim_u, dim_v_0, dim_v,
+                                                forward_func, generate_x_0, generate_z, generate_σ, obs_func,
+                                                use_gaussian_splitting=False, return_jax_funcs=False, device=0):
+    """Negative log target density + gradient functions for the diffusion model (:82-205), the target of the
+    reference's standard-HMC baseline (``mici.systems.EuclideanMetricSystem``): forward simulation and the reverse
+    (adjoint) sweep run in one CUDA kernel (``k_hmc_target``).  Returns ``(neg_log_dens, grad_neg_log_dens)`` with
+    the reference's conventions: ``grad_neg_log_dens(q) -> (grad, value)``, non-finite values raise
+    ``HamiltonianDivergenceError`` (:193-204).  ``return_jax_funcs=True`` returns the unwrapped pair (arrays in,
+    arrays out, no exception), the role the raw JAX functions play in the reference."""
+    funcs = [forward_func, generate_x_0, generate_z, obs_func]
+    if isinstance(generate_σ, Number):
+        noise, sigma = 1, float(generate_σ)
+    else:
+        noise, sigma = 2, 0.0
+        funcs.append(generate_σ)
+    model = _model_tag(*funcs)
+    y_seq = np.asarray(y_seq, dtype=np.float64)
+    # (the handle's block structure is irrelevant to this target; any admissible blocking will do)
+    bc = BatchedChains(model, obs_interval, num_steps_per_obs, 5 if y_seq.shape[0] > 5 else None, y_seq, dim_u, 1,
+                       noise=noise, sigma_fixed=sigma,
+                       use_gaussian_splitting=use_gaussian_splitting, device=device)
+    if bc.hmc_dim != dim_u + dim_v_0 + dim_v * num_steps_per_obs * y_seq.shape[0]:
+        raise ValueError("dim_u / dim_v_0 / dim_v do not match the model")
+
+    def _neg_log_dens(q):
+        val, _ = bc.neg_log_dens_and_grad(np.asarray(q, dtype=np.float64)[None], use_gaussian_splitting, with_grad=False)
+        return val[0]
+
+    def _grad_neg_log_dens(q):
+        val, grad = bc.neg_log_dens_and_grad(np.asarray(q, dtype=np.float64)[None], use_gaussian_splitting)
+        return grad[0], val[0]
+
+    if return_jax_funcs:
+        return _neg_log_dens, _grad_neg_log_dens
+
+    def neg_log_dens(q):
+        val = float(_neg_log_dens(q))
+        if not np.isfinite(val):
+            raise HamiltonianDivergenceError("Hamiltonian non-finite")
+        return val
+
+    def grad_neg_log_dens(q):
+        grad, val = _grad_neg_log_dens(q)
+        if not np.isfinite(val):
+            raise HamiltonianDivergenceError("Hamiltonian non-finite")
+        return np.asarray(grad), float(val)
+
+    neg_log_dens._bc = grad_neg_log_dens._bc = bc      # keeps the device handle alive
+    return neg_log_dens, grad_neg_log_dens
+
+
+def find_initial_state_by_gradient_descent_noisy_system(system, rng, adam_step_size=2e-2, max_iters=1000,
+                                                        max_init_tries=100, max_num_tries=10, threshold=1.0,
+                                                        slow_progress_ratio=0.8, check_iter=100, **model_dict):
+    """Find an initial constraint satisfying state by a gradient descent based scheme (:1679-1801): Adam on the
+    negative log posterior density of the noisy-observation system until the mean squared residual is below
+    ``threshold``; the state on the manifold then takes the residuals as its observation-noise variables.  The
+    objective gradients and the Adam updates run on the device (``BatchedChains.init_gradient_descent``)."""
+    if not isinstance(system, ConditionedDiffusionConstrainedSystem):
+        raise NotImplementedError("device path: pass the ConditionedDiffusionConstrainedSystem of the noisy model")
+    bc = system._bc
+    q, _ = bc.init_gradient_descent([rng], adam_step_size, max_iters, max_init_tries, max_num_tries, threshold,
+                                    slow_progress_ratio, check_iter)
+    state = ConditionedDiffusionHamiltonianState(pos=q[0], x_obs_seq=None, _call_counts={})
+    system._resident = None
+    system.update_x_obs_seq(state)
+    state.mom = system.sample_momentum(state, rng)
+    return state
+
+
+class OnlineBlockDiagonalMetricAdapter(Adapter):
+    """Block diagonal metric adapter using online covariance estimates (:1804-1931): Welford accumulation of the
+    covariance of the first ``dim_param`` position components per chain, Schubert-Gertz / Chan combination across
+    chains, Stan-style regularisation towards a scaled identity; sets ``transition.system.metric`` to
+    blockdiag(inverse covariance estimate, identity).  Host-side bookkeeping of a few ``dim_param``-sized arrays per
+    chain, as in the reference (it belongs to the standard-HMC baseline, not to the constrained path)."""
+
+    is_fast = False
+
+    def __init__(self, dim_param, reg_iter_offset=5, reg_scale=1e-3):
+        self.dim_param = dim_param
+        self.reg_iter_offset = reg_iter_offset
+        self.reg_scale = reg_scale
+
+    def initialize(self, chain_state, transition):
+        dtype = chain_state.pos.dtype
+        return {
+            "iter": 0,
+            "mean": np.zeros(shape=(self.dim_param,), dtype=dtype),
+            "sum_diff_outer": np.zeros(shape=(self.dim_param, self.dim_param), dtype=dtype),
+            "dim_pos": chain_state.pos.shape[0],
+        }
+
+    def update(self, adapt_state, chain_state, trans_stats, transition):
+        adapt_state["iter"] += 1
+        par = chain_state.pos[: self.dim_param]
+        pos_minus_mean = par - adapt_state["mean"]
+        adapt_state["mean"] += pos_minus_mean / adapt_state["iter"]
+        adapt_state["sum_diff_outer"] += pos_minus_mean[None, :] * (par - adapt_state["mean"])[:, None]
+
+    def _regularize_covar_est(self, covar_est, n_iter):
+        covar_est *= n_iter / (self.reg_iter_offset + n_iter)
+        diag = np.einsum("ii->i", covar_est)
+        diag += self.reg_scale * (self.reg_iter_offset / (self.reg_iter_offset + n_iter))
+
+    def finalize(self, adapt_state, transition):
+        if isinstance(adapt_state, dict):
+            n_iter = adapt_state["iter"]
+            covar_est = adapt_state.pop("sum_diff_outer")
+            dim_pos = adapt_state["dim_pos"]
+        else:
+            for i, a in enumerate(adapt_state):
+                if i == 0:
+                    n_iter = a["iter"]
+                    mean_est = a.pop("mean")
+                    covar_est = a.pop("sum_diff_outer")
+                    dim_pos = a["dim_pos"]
+                else:
+                    n_iter_prev = n_iter
+                    n_iter += a["iter"]
+                    mean_diff = mean_est - a["mean"]
+                    mean_est *= n_iter_prev
+                    mean_est += a["iter"] * a["mean"]
+                    mean_est /= n_iter
+                    covar_est += a["sum_diff_outer"]
+                    covar_est += np.outer(mean_diff, mean_diff) * (a["iter"] * n_iter_prev) / n_iter
+        if n_iter < 2:
+            raise AdaptationError("At least two chain samples required to compute a variance estimates.")
+        covar_est /= n_iter - 1
+        self._regularize_covar_est(covar_est, n_iter)
+        transition.system.metric = PositiveDefiniteBlockDiagonalMatrix(
+            (DensePositiveDefiniteMatrix(covar_est).inv, IdentityMatrix(dim_pos - self.dim_param)))
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -836,3 +836,117 @@ def find_initial_state_by_linear_interpolation(system, rng, generate_x_obs_seq_i
     else:
         q = torch.cat([u, v_0, v_seq.flatten()])
     return q, x_obs_seq
+
+
+# ---------------------------------------------------------------------------------------------------
+# standard-HMC target and the Adam initialiser for noisy systems
+# ---------------------------------------------------------------------------------------------------
+def conditioned_diffusion_neg_log_dens_and_grad(
+    obs_interval, num_steps_per_obs, y_seq, dim_u, dim_v_0, dim_v, forward_func, generate_x_0, generate_z,
+    generate_σ, obs_func, use_gaussian_splitting=False,
+):
+    """mici_extensions.py:82-205 -- (neg_log_dens, value_and_grad) on torch tensors; the gradient is reverse-mode
+    automatic differentiation through the time loop, as jax.value_and_grad through lax.scan in the reference."""
+    y_seq = _t(y_seq)
+    num_obs, dim_y = y_seq.shape
+    δ = obs_interval / num_steps_per_obs
+    if isinstance(generate_σ, Number):
+        σ_fixed = generate_σ
+
+        def generate_σ(u):  # noqa: F811  (:146-150)
+            return torch.as_tensor(σ_fixed, dtype=torch.float64)
+
+    def _neg_log_dens(q):  # :152-171
+        num_step = num_steps_per_obs * num_obs
+        u, v_0, v_seq_flat = split(q, (dim_u, dim_v_0, dim_v * num_step))
+        z = generate_z(u)
+        σ = generate_σ(u)
+        x = generate_x_0(z, v_0)
+        v_seq = v_seq_flat.reshape((num_step, dim_v))
+        xs = []
+        for t in range(num_step):
+            x = forward_func(z, x, v_seq[t], δ)
+            xs.append(x)
+        x_seq = torch.stack(xs)
+        y_seq_mean = obs_func(x_seq[num_steps_per_obs - 1 :: num_steps_per_obs])
+        return (
+            0.5 * torch.sum(((y_seq - y_seq_mean) / σ) ** 2)
+            + num_obs * dim_y * torch.log(σ)
+            + (0 if use_gaussian_splitting else 0.5 * torch.sum(q ** 2))
+        )
+
+    def _value_and_grad(q):  # :173
+        q = _t(q).clone().requires_grad_(True)
+        val = _neg_log_dens(q)
+        (g,) = torch.autograd.grad(val, q)
+        return val.detach(), g
+
+    return (lambda q: _neg_log_dens(_t(q))), _value_and_grad
+
+
+def find_initial_state_by_gradient_descent_noisy_system(
+    model_dict, rng, adam_step_size=2e-2, max_iters=1000, max_init_tries=100, max_num_tries=10, threshold=1.0,
+    slow_progress_ratio=0.8, check_iter=100,
+):
+    """mici_extensions.py:1679-1801 restated: returns (u_v, residuals, tries, iterations) of the accepted point.
+    Adam follows jax.experimental.optimizers.adam (b1 = 0.9, b2 = 0.999, eps = 1e-8; :1733)."""
+    md = model_dict
+    num_step = md["num_steps_per_obs"] * md["num_obs"]
+    dim_u_v = md["dim_u"] + md["dim_v_0"] + num_step * md["dim_v"]
+    y_seq = _t(md["y_seq"])
+    gen_σ = md["generate_σ"]
+    if isinstance(gen_σ, Number):
+        σ_fixed = gen_σ
+        gen_σ = lambda u: torch.as_tensor(σ_fixed, dtype=torch.float64)  # noqa: E731
+
+    def init_objective(u_v):  # :1701-1731
+        u, v_0, v_flat = split(u_v, (md["dim_u"], md["dim_v_0"], num_step * md["dim_v"]))
+        v_seq = v_flat.reshape((num_step, md["dim_v"]))
+        z = md["generate_z"](u)
+        x = md["generate_x_0"](z, v_0)
+        σ = gen_σ(u)
+        xs = []
+        for t in range(num_step):
+            x = md["forward_func"](z, x, v_seq[t], md["δ"])
+            xs.append(x)
+        x_seq = torch.stack(xs)
+        obs_slc = slice(md["num_steps_per_obs"] - 1, None, md["num_steps_per_obs"])
+        residuals = (y_seq - md["obs_func"](x_seq[obs_slc])) / σ
+        return 0.5 * torch.sum(residuals ** 2) + md["num_obs"] * torch.log(σ) + 0.5 * torch.sum(u_v ** 2), residuals
+
+    def grad_init_objective(u_v):
+        u_v = u_v.clone().requires_grad_(True)
+        val, res = init_objective(u_v)
+        (g,) = torch.autograd.grad(val, u_v)
+        return g, res.detach()
+
+    b1, b2, eps = 0.9, 0.999, 1e-8
+    for t in range(max_num_tries):
+        found_valid_init_state, init_tries = False, 0
+        while not found_valid_init_state and init_tries < max_init_tries:
+            u_v = _t(rng.standard_normal(dim_u_v))
+            with torch.no_grad():
+                _, residuals = init_objective(u_v)
+            if bool(torch.isfinite(residuals).all()):
+                found_valid_init_state = True
+            init_tries += 1
+        if init_tries == max_init_tries:
+            raise RuntimeError(f"Did not find valid initial state in {init_tries} tries.")
+        m, v = torch.zeros_like(u_v), torch.zeros_like(u_v)
+        prev_mean_residual_sq = float(torch.mean(residuals ** 2))
+        for i in range(max_iters):
+            g, residuals = grad_init_objective(u_v)
+            m_n = (1 - b1) * g + b1 * m
+            v_n = (1 - b2) * g ** 2 + b2 * v
+            u_v_next = u_v - adam_step_size * (m_n / (1 - b1 ** (i + 1))) / (torch.sqrt(v_n / (1 - b2 ** (i + 1))) + eps)
+            mean_residuals_sq = float(torch.mean(residuals ** 2))
+            if not onp.isfinite(mean_residuals_sq):
+                break
+            if mean_residuals_sq < threshold:
+                return u_v.numpy(), residuals.numpy().flatten(), t + 1, i
+            u_v, m, v = u_v_next, m_n, v_n
+            if i % check_iter == 0:
+                if i > 0 and i < max_iters // 2 and (mean_residuals_sq / prev_mean_residual_sq) > slow_progress_ratio:
+                    break
+                prev_mean_residual_sq = mean_residuals_sq
+    raise RuntimeError(f"Did not find valid state in {max_num_tries} tries.")
