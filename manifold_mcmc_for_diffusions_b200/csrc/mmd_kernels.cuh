@@ -47,6 +47,9 @@
 #define MMD_HINT_KEEP 1
 #define MMD_HINT_STREAM 1
 #endif
+#ifndef MMD_FACTOR_PREFETCH
+#define MMD_FACTOR_PREFETCH 0   // 1: pull the per-iteration block factors into L2 before every solver sweep; 2: also before the momentum projections
+#endif
 #ifndef MMD_L2_PREFETCH_STEPS
 #define MMD_L2_PREFETCH_STEPS 8   // additional look-ahead of the HBM -> L2 prefetch (0 = off)
 #endif

@@ -857,6 +857,10 @@ MMD_PHASE void dev_project(const Dims& d, const Slots& S, const Work& W, int par
         if (j < U) s = fma(Ac[(rr * U + j) * nta], pu[j], s);
       sm_c[rr * NT] = s;
     }
+#if MMD_FACTOR_PREFETCH > 1
+    prefetch_col_l2(Dic, NTRI, nta);
+    prefetch_col_l2(DinvAc, NRMAX * U, nta);
+#endif
     // pass 1: r = J p'  (lmult_by_jacob_constr :822-877); p' written to dst when it differs from src
     for (int k = 0; k < B.n; ++k) {
       double sk[X];
@@ -1414,6 +1418,12 @@ MMD_PHASE void dev_qn(const Dims& d, const Slots& S, const Work& W, const double
         for (int j = 0; j < M::V0; ++j) v0[j] -= t0[j];
       }
       block_start<M>(d, B, P.z, v0, xoc, cpb, x);
+#if MMD_FACTOR_PREFETCH > 0
+      prefetch_col_l2(Dic, NTRI, nta);
+      prefetch_col_l2(DinvAc, NRMAX * U, nta);
+      prefetch_col_l2(Psibc, B.n * X * X, nta);
+      prefetch_col_l2(kapc, B.n * X, nta);
+#endif
       {
         SweepArgs<M> a;
         a.C = P.C; a.sigma_y = P.sigy; a.sigma_lin = sig_lin;

@@ -104,6 +104,11 @@ MMD_D void ldcol_keep(const double* g, int ld, double* r) {  // ldcol with the e
 }
 MMD_D void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(g)); }
 MMD_D void prefetch_l1(const void* g) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(g)); }
+// prefetch `rows` rows of a thread-private column into L2 (the demand loads of the block solve that follows the
+// sweep then hit L2 instead of queueing behind the sweeps' streams in DRAM)
+MMD_D void prefetch_col_l2(const double* g, int rows, int ld) {
+  for (int i = 0; i < rows; ++i) prefetch_l2(g + i * ld);
+}
 MMD_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 MMD_D void cp_async_wait() {
