@@ -120,13 +120,15 @@ class ClockSampler(threading.Thread):
 
 
 # work model (SURVEY.md 8d / DESIGN.md): bytes one quasi-Newton sweep must read per chain
-def leapfrog_bytes_per_chain_step(qn_iters, newton=False):
+def leapfrog_bytes_per_chain_step(qn_iters, newton=False, steps_per_launch=1):
     """Algorithmic HBM bytes of one constrained leapfrog step of one chain: doubles
     per SDE time step summed over the phases (X=V=2: a K_t record is 4 doubles, v_t / p_t / x_t records 2)."""
     # momentum projections (pass 1: J p, pass 2: p - J^T lambda), h1 kick and h2_flow fused in:
     project = (4 + 2 + 2 + 2 + 2) + (4 + 2 + 2 + 2 + 2)   # A(dt/2) at the old point + flow -> qw, pw
     project += (4 + 2) + (4 + 2 + 2 + 2 + 2)              # tangent projection at the new point + back flow
-    project += (4 + 2 + 2 + 2 + 2) + (4 + 2 + 2)          # A(dt/2) at the new point
+    # A(dt/2) at the new point: inside a multi-step launch it is fused with the opening kick of the next step (one
+    # projection with a full kick), so it is paid once per launch
+    project += ((4 + 2 + 2 + 2 + 2) + (4 + 2 + 2)) / max(steps_per_launch, 1)
     # quasi-Newton: one sweep per iteration (K_t + work position); Newton: forward sweep that also stores the
     # trajectory (4 + 2 + 2) and a backward sweep re-linearising at the iterate (trajectory, work position, K_t)
     qn = (16 if newton else 6) * qn_iters
@@ -414,7 +416,8 @@ def run_ours(args):
         steps_per_launch = ok / max(n_lf, 1)
         tflops = wm["flops"] * ok / lf_s / 1e12 if lf_s > 0 else 0.0
         floor_gbs = wm["bytes_min"] * ok / lf_s / 1e9 if lf_s > 0 else 0.0
-        alg_bytes_step = leapfrog_bytes_per_chain_step(iters_per_step, newton=args.solver == "newton")
+        alg_bytes_step = leapfrog_bytes_per_chain_step(iters_per_step, newton=args.solver == "newton",
+                                                       steps_per_launch=args.traj_len)
         impl_gbs = alg_bytes_step * ok / lf_s / 1e9 if lf_s > 0 else 0.0
         intensity = wm["flops"] / wm["bytes_min"]
         ridge = fp64_peak * 1e12 / (hbm_peak * 1e9)

@@ -252,7 +252,7 @@ long long mmd_successful_steps(mmd_handle h, int reset);
 long long mmd_total_qn_iterations(mmd_handle h, int reset);
 /* Development aid: per-phase cycle counters of the fused leapfrog kernel (thread 0 of every CTA), available only
  * in builds with -DMMD_PHASE_CLOCK (tools/phase_times.py); returns an error in product builds. */
-int mmd_debug_phase_cycles(mmd_handle h, unsigned long long* out32, int reset);
+int mmd_debug_phase_cycles(mmd_handle h, unsigned long long* out64, int reset);
 /* per-kernel CUDA-event timing on the handle's stream: kernel ids 0 linearise (k_point), 1 momentum
  * projection (k_project), 2 quasi-Newton projection (k_qn), 3 fused leapfrog step(s) (k_leapfrog) */
 int mmd_profile_enable(mmd_handle h, int on, int max_launches);

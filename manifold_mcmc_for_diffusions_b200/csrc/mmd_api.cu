@@ -179,7 +179,10 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
     const int nz_ = cfg->noise != MMD_NOISE_NONE;
     if (cfg->model == MMD_MODEL_FHN && R_ > 0 && R_ < T_ && !getenv("MMD_FHN_WIDE")) {
       const mmd_ops* small = mmd_ops_fhn_r5();
+      const mmd_ops* wide = mmd_ops_fhn_r16();
       if (R_ - 1 + nz_ + small->X <= small->nrmax && R_ <= small->rmax) ops = small;
+      else if ((R_ - 1 + nz_ + ops->X > ops->nrmax || R_ > ops->rmax) &&
+               R_ - 1 + nz_ + wide->X <= wide->nrmax && R_ <= wide->rmax) ops = wide;
     }
   }
   if (cfg->device < 0 || cfg->device >= ndev) FAIL("bad device ordinal");
@@ -333,7 +336,7 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   W.use_dt_chain = 0;
   W.phase = nullptr;
 #ifdef MMD_PHASE_CLOCK
-  rc |= dalloc(h, &W.phase, 32);
+  rc |= dalloc(h, &W.phase, 64);
 #endif
   rc |= dalloc(h, &h->ad_state, 4 * nc);
   rc |= dalloc(h, &h->maskbuf, nc);
@@ -993,12 +996,12 @@ static long long sum_counter(mmd_handle h, long long* dev, int reset) {
 long long mmd_successful_steps(mmd_handle h, int reset) { MMD_GUARD(h); return sum_counter(h, h->n_ok, reset); }
 long long mmd_total_qn_iterations(mmd_handle h, int reset) { MMD_GUARD(h); return sum_counter(h, h->W.itsum, reset); }
 
-int mmd_debug_phase_cycles(mmd_handle h, unsigned long long* out32, int reset) {
+int mmd_debug_phase_cycles(mmd_handle h, unsigned long long* out64, int reset) {
   MMD_GUARD(h);
   if (!h->W.phase) FAIL("phase clocks are compiled in only with -DMMD_PHASE_CLOCK (tools/phase_times.py)");
-  CK(cudaMemcpyAsync(out32, h->W.phase, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out64, h->W.phase, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (reset) CK(cudaMemsetAsync(h->W.phase, 0, 32 * sizeof(unsigned long long), h->stream));
+  if (reset) CK(cudaMemsetAsync(h->W.phase, 0, 64 * sizeof(unsigned long long), h->stream));
   return 0;
 }
 

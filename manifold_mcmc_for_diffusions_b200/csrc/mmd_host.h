@@ -152,5 +152,6 @@ struct mmd_ops {
 };
 const mmd_ops* mmd_ops_fhn();
 const mmd_ops* mmd_ops_fhn_r5();   // blocks of <= 5 observations / 6 constraint rows
+const mmd_ops* mmd_ops_fhn_r16();  // blocks of <= 14 observations / 16 constraint rows
 const mmd_ops* mmd_ops_sir();
 const mmd_ops* mmd_ops_fhn_notebook();

@@ -23,7 +23,7 @@
 #include <stdint.h>
 
 #ifndef MMD_PREFETCH_STEPS
-#define MMD_PREFETCH_STEPS 2      // cp.async ring depth of the recursion sweeps (steps in flight to shared memory)
+#define MMD_PREFETCH_STEPS 2      // cp.async ring of the recursion sweeps: MMD_PREFETCH_STEPS + 1 slots (= steps per group of the grouped / bulk sweeps)
 #endif
 #ifndef MMD_POINTWISE_L2_PREFETCH
 #define MMD_POINTWISE_L2_PREFETCH 8   // look-ahead (steps) of the HBM -> L2 prefetch in the pointwise passes (0 = off)
@@ -157,10 +157,24 @@ struct Work {
   do {                                                                            \
     if (threadIdx.x == 0 && W.phase) atomicAdd(&W.phase[i], (unsigned long long)(n)); \
   } while (0)
+// second, independent clock for finer marks inside a phase (slots 24..31)
+#define PHX_T0 long long _px = clock64();
+#define PHX_RESET _px = clock64();
+#define PHX(i)                                                                    \
+  do {                                                                            \
+    if (threadIdx.x == 0 && W.phase) {                                            \
+      const long long _n = clock64();                                             \
+      atomicAdd(&W.phase[i], (unsigned long long)(_n - _px));                     \
+      _px = _n;                                                                   \
+    }                                                                             \
+  } while (0)
 #else
 #define PH_T0
 #define PH(i)
 #define PH_ADD(i, n)
+#define PHX_T0
+#define PHX_RESET
+#define PHX(i)
 #endif
 
 struct FlowCoef {
@@ -417,20 +431,26 @@ MMD_D void block_reduce(double* vals, double* smem, const Tid& t) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) smem[i * NT + t.tid] = vals[i];
   __syncthreads();
+  // slot loop outside, value loop unrolled inside: the NV shared-memory reads of one slot are independent, so a
+  // slot costs one LDS latency instead of NV (the per-value order of the additions is unchanged: ascending slots)
+  double acc[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    double s = 0.0;
-    const double* col = smem + i * NT + t.cl;
-    for (int sl = 0; sl < t.nslot; ++sl) {
-      const double v = col[sl * t.cpb];
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  const double* col = smem + t.cl;
+#pragma unroll 3
+  for (int sl = 0; sl < t.nslot; ++sl) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const double v = col[i * NT + sl * t.cpb];
       if (i < NSUM) {
-        s += v;
+        acc[i] += v;
       } else {
-        s = (v > s || v != v) ? v : s;
+        acc[i] = (v > acc[i] || v != v) ? v : acc[i];
       }
     }
-    vals[i] = s;
   }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) vals[i] = acc[i];
   if (TAIL_SYNC) __syncthreads();
 }
 #endif
@@ -450,6 +470,34 @@ MMD_D double chol_packed_invdiag(double* Dm, int n) {
       double t = Dm[tri(i, j)];
       for (int k = 0; k < j; ++k) t -= Dm[tri(i, k)] * Dm[tri(j, k)];
       Dm[tri(i, j)] = t * inv;
+    }
+  }
+  return ld;
+}
+// the same factorisation with compile-time loop bounds (n <= N, rows beyond n untouched): every index is a constant
+// after unrolling, so the matrix stays in registers / fixed local slots; same operations in the same order
+template <int N>
+MMD_D double chol_packed_invdiag_fixed(double* Dm, int n) {
+  double ld = 0.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    if (j < n) {
+      double s = Dm[tri(j, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= Dm[tri(j, k)] * Dm[tri(j, k)];
+      const double ljj = sqrt(s);
+      ld += log(fabs(ljj));
+      const double inv = 1.0 / ljj;
+      Dm[tri(j, j)] = inv;
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) {
+        if (i < n) {
+          double t = Dm[tri(i, j)];
+#pragma unroll
+          for (int k = 0; k < j; ++k) t -= Dm[tri(i, k)] * Dm[tri(j, k)];
+          Dm[tri(i, j)] = t * inv;
+        }
+      }
     }
   }
   return ld;

@@ -26,7 +26,9 @@ struct SmemPlan {
   double* const sm_ring = smem;                                         \
   double* const sm_c = smem + SmemPlan<M, NRMAX, UMAX>::NSCR * NT + t.tid; \
   double* const sm_l = sm_c + NRMAX * NT;                               \
-  (void)sm_red; (void)sm_ring; (void)sm_c; (void)sm_l;
+  unsigned long long* const sm_bars = reinterpret_cast<unsigned long long*>(                     \
+      reinterpret_cast<char*>(smem + SmemPlan<M, NRMAX, UMAX>::PER_THREAD * NT) + t.cpb * sizeof(typename M::Coef)); \
+  (void)sm_red; (void)sm_ring; (void)sm_c; (void)sm_l; (void)sm_bars;
 
 // ------------------------------------------------------------------------------------------
 // dev_point: everything cached at a position.  Phase 1 = jacob_constr_blocks + chol_gram_blocks +
@@ -259,9 +261,58 @@ MMD_PHASE void dev_point(const Dims& d, const Slots& S, const Work& W, const dou
         nrow_done++;
       }
     }
+    double ldpart;
+    if (NRMAX <= 8) {
+      // small blocks: compile-time bounds, everything unrolled (constant indices into Dm / Am / red: no dependent
+      // local-memory addressing, independent solves interleave); identical operation order to the loops below
+      const int nr1 = B.nrows;
+#pragma unroll
+      for (int r = 0; r < NRMAX; ++r)
+#pragma unroll
+        for (int j = 0; j < UMAX; ++j)
+          if (r < nr1 && j < U) Ac[(r * U + j) * nta] = Am[r * UMAX + j];
+      ldpart = chol_packed_invdiag_fixed<NRMAX>(Dm, nr1);
+#pragma unroll
+      for (int i = 0; i < NTRI; ++i)
+        if (i < nr1 * (nr1 + 1) / 2) Lc[i * nta] = Dm[i];
+#pragma unroll
+      for (int c2 = 0; c2 < NRMAX; ++c2) {
+        if (c2 < nr1) {
+          double e[NRMAX];
+#pragma unroll
+          for (int r = 0; r < NRMAX; ++r) e[r] = (r == c2) ? 1.0 : 0.0;
+          chol_solve_invdiag_fixed<NRMAX>(Dm, nr1, e);
+#pragma unroll
+          for (int r = c2; r < NRMAX; ++r)
+            if (r < nr1) Dic[tri(r, c2) * nta] = e[r];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UMAX; ++j) {
+        if (j < U) {
+          double col[NRMAX];
+#pragma unroll
+          for (int r = 0; r < NRMAX; ++r) col[r] = (r < nr1) ? Am[r * UMAX + j] : 0.0;
+          chol_solve_invdiag_fixed<NRMAX>(Dm, nr1, col);
+#pragma unroll
+          for (int r = 0; r < NRMAX; ++r)
+            if (r < nr1) DinvAc[(r * U + j) * nta] = col[r];
+#pragma unroll
+          for (int i = j; i < UMAX; ++i) {
+            if (i < U) {
+              double s = 0.0;
+#pragma unroll
+              for (int r = 0; r < NRMAX; ++r)
+                if (r < nr1) s = fma(Am[r * UMAX + i], col[r], s);
+              red[tri(i, j)] = s;
+            }
+          }
+        }
+      }
+    } else {
     for (int r = 0; r < B.nrows; ++r)
       for (int j = 0; j < U; ++j) Ac[(r * U + j) * nta] = Am[r * UMAX + j];
-    const double ldpart = chol_packed_invdiag(Dm, B.nrows);
+    ldpart = chol_packed_invdiag(Dm, B.nrows);
     for (int i = 0; i < B.nrows * (B.nrows + 1) / 2; ++i) Lc[i * nta] = Dm[i];
     // explicit inverse of the block (lower triangle), column by column from the factor: what the Woodbury solves of
     // the projections use (inv_gram_block)
@@ -282,6 +333,7 @@ MMD_PHASE void dev_point(const Dims& d, const Slots& S, const Work& W, const dou
         for (int r = 0; r < B.nrows; ++r) s = fma(Am[r * UMAX + i], col[r], s);
         red[tri(i, j)] = s;
       }
+    }
     }
     red[UTRI] = ldpart;
     PH(17);
@@ -761,7 +813,7 @@ MMD_D void dev_constr(const Dims& d, const Slots& S, const Work& W, const double
     for (int i = 0; i < X; ++i) a.xstart[i] = x[i];
     a.vb = q.body; a.nzb = q.noise; a.xoc = xoc; a.y = y; a.Kb = nullptr; a.alph = nullptr; a.lamtot = nullptr;
     a.crow = sm_c; a.ring = sm_ring; a.xend_out = nullptr; a.xs_out = nullptr;
-    a.nta = t.nta; a.cpb = t.cpb; a.NT = NT; a.tid = t.tid;
+    a.nta = t.nta; a.cpb = t.cpb; a.NT = NT; a.tid = t.tid; a.phase = nullptr; a.mask = 0u; a.bars = nullptr;
     constr_sweep<M, false>(d, B, a);
   }
   double* co = tp(cout, NRMAX, t);
@@ -850,12 +902,37 @@ MMD_PHASE void dev_project(const Dims& d, const Slots& S, const Work& W, int par
 #pragma unroll
       for (int i = 0; i < X; ++i) m[i] = 0.0;
     }
-    for (int rr = 0; rr < B.nrows; ++rr) {
-      double s = 0.0;
+    // A_b p_u, three rows of A per batch of loads (see inv_gram_block)
+    if (NRMAX <= 8) {
 #pragma unroll
-      for (int j = 0; j < UMAX; ++j)
-        if (j < U) s = fma(Ac[(rr * U + j) * nta], pu[j], s);
-      sm_c[rr * NT] = s;
+      for (int r0 = 0; r0 < NRMAX; r0 += 3) {
+        if (r0 < B.nrows) {
+          double av[3][UMAX];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (r0 + c < NRMAX) {
+#pragma unroll
+              for (int j = 0; j < UMAX; ++j) av[c][j] = ldg_vol(Ac + ((r0 + c) * U + (j < U ? j : U - 1)) * nta);
+            }
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (r0 + c < NRMAX && r0 + c < B.nrows) {
+              double s = 0.0;
+#pragma unroll
+              for (int j = 0; j < UMAX; ++j)
+                if (j < U) s = fma(av[c][j], pu[j], s);
+              sm_c[(r0 + c) * NT] = s;
+            }
+        }
+      }
+    } else {
+      for (int rr = 0; rr < B.nrows; ++rr) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < UMAX; ++j)
+          if (j < U) s = fma(Ac[(rr * U + j) * nta], pu[j], s);
+        sm_c[rr * NT] = s;
+      }
     }
 #if MMD_FACTOR_PREFETCH > 1
     prefetch_col_l2(Dic, NTRI, nta);
@@ -1398,9 +1475,13 @@ MMD_PHASE void dev_qn(const Dims& d, const Slots& S, const Work& W, const double
 #else
   bool first_pass = true;
 #endif
+  PHX_T0
   while (true) {
     const bool work = in_blk && !done;
     double sres[UMAX], err = 0.0;
+    PHX_RESET
+    PH_ADD(30, work ? 1 : 0);
+    const unsigned wmask = __ballot_sync(0xffffffffu, work);   // (all threads of the CTA are converged here)
     if (work) {
       ChainPar<M, UMAX> P;
       {
@@ -1418,6 +1499,7 @@ MMD_PHASE void dev_qn(const Dims& d, const Slots& S, const Work& W, const double
         for (int j = 0; j < M::V0; ++j) v0[j] -= t0[j];
       }
       block_start<M>(d, B, P.z, v0, xoc, cpb, x);
+      PHX(24);
 #if MMD_FACTOR_PREFETCH > 0
       prefetch_col_l2(Dic, NTRI, nta);
       prefetch_col_l2(DinvAc, NRMAX * U, nta);
@@ -1433,13 +1515,14 @@ MMD_PHASE void dev_qn(const Dims& d, const Slots& S, const Work& W, const double
         a.crow = sm_c; a.ring = sm_ring; a.xend_out = nullptr;
         a.xs_out = NEWTON ? tpr<X>(W.xs, d.rmax * d.S * X, t) : nullptr;
         if (NEWTON && !M::OBS_LINEAR) a.xend_out = tp(W.Yb, d.rmax * X * X, t);
-        a.nta = nta; a.cpb = cpb; a.NT = NT; a.tid = t.tid;
+        a.nta = nta; a.cpb = cpb; a.NT = NT; a.tid = t.tid; a.phase = W.phase; a.mask = wmask; a.bars = sm_bars;
         // first pass of the loop: lam_tot = 0, the iterate is q_w itself -- no need to stream K (the products with
         // alpha = 0 leave v bit-for-bit unchanged)
         if (first_pass) constr_sweep<M, false, NEWTON>(d, B, a);
         else constr_sweep<M, true, NEWTON>(d, B, a);
       }
       if (NEWTON) Pkeep = P;
+      PHX(25);
     }
     double rr[NRMAX];
     {
@@ -1456,6 +1539,7 @@ MMD_PHASE void dev_qn(const Dims& d, const Slots& S, const Work& W, const double
     // left its sweep before any thread starts the cross-block reduction.  The same barrier ends the loop once
     // every chain of the tile is done (their threads skipped the sweep).
     if (__syncthreads_and(done ? 1 : 0)) break;
+    PHX(26);
     PH(9);
     PH_ADD(12, 1);
     if (NEWTON)
@@ -1463,7 +1547,8 @@ MMD_PHASE void dev_qn(const Dims& d, const Slots& S, const Work& W, const double
                                                 sm_l, W, rr, sres, &err, sm_red, t, NT);
     else
       // (no trailing barrier: the next write to the scratch comes after the __syncthreads_or below)
-      inv_gram_block<M, NRMAX, UMAX, false>(d, B, work, Dic, DinvAc, LCc, rr, sres, &err, sm_red, t);
+      inv_gram_block<M, NRMAX, UMAX, false>(d, B, work, Dic, DinvAc, LCc, rr, sres, &err, sm_red, t, W.phase);
+    PHX(27);
     // Convergence test of the reference (:1047-1055): |c| < constraint_tol AND |delta_q|_inf < position_tol for THIS
     // iteration's update delta_q = J_lin^T (increment of the multipliers).  The exact norm needs a pass over K; a
     // cheap upper bound (per-interval row maxima kap of K from the linearisation, exact for the head / noise
@@ -1485,7 +1570,9 @@ MMD_PHASE void dev_qn(const Dims& d, const Slots& S, const Work& W, const double
       for (int j = 0; j < UMAX; ++j) stot[j] += sres[j];
       alpha_block<M, NRMAX, RMAXP>(B, lt, Psibc, xendc, nta, alph, a0tot);
     }
+    PHX(28);
     const int any_check = __syncthreads_or(check ? 1 : 0);
+    PHX(29);
     PH(10);
     bool converged = false;
     if (any_check) {

@@ -14,7 +14,7 @@ struct Ops {
   // per-thread regions + one model-coefficient block per chain of the tile (used by the linearisation sweeps)
   static size_t smem(mmd_handle h, int nt) {
     return (size_t)SmemPlan<Mdl, NRMAX, UMAX>::PER_THREAD * nt * sizeof(double) +
-           (size_t)h->d.cpb * sizeof(typename Mdl::Coef);
+           (size_t)h->d.cpb * sizeof(typename Mdl::Coef) + 64;   // + one mbarrier per warp (bulk-copy sweeps)
   }
   static int nt(mmd_handle h) { return h->d.nb[h->partition] * h->d.cpb; }
   template <class Kern>

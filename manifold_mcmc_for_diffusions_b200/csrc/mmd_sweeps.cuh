@@ -97,6 +97,13 @@ MMD_D void cp_async(unsigned sdst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst), "l"(gsrc) : "memory");
 #endif
 }
+// plain volatile load: consecutive calls stay together and in order, so a batch of independent loads is in flight at
+// once instead of each one being scheduled next to its use
+MMD_D double ldg_vol(const double* g) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];\n" : "=d"(v) : "l"(g));
+  return v;
+}
 template <int N>
 MMD_D void ldcol_keep(const double* g, int ld, double* r) {  // ldcol with the evict_last hint
 #pragma unroll
@@ -114,6 +121,42 @@ template <int N>
 MMD_D void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// ------------------------------------------------------------------------------------------
+// Blackwell bulk copies: one elected lane per warp moves the warp's contiguous slab of a [step][nta][W] array
+// with cp.async.bulk (the TMA engine: no per-thread address arithmetic, no LDGSTS issue, no registers for data
+// in flight); completion is counted in bytes on an mbarrier the lanes of the warp wait on.
+// ------------------------------------------------------------------------------------------
+MMD_D void mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+MMD_D void mbar_inval(unsigned bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory"); }
+MMD_D void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+MMD_D void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MMD_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MMD_DONE_%=;\n"
+      "bra MMD_WAIT_%=;\n"
+      "MMD_DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+MMD_D void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+#if defined(MMD_HINT_STREAM)
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(l2_policy_stream()) : "memory");
+#else
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+#endif
+}
+MMD_D void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(bytes) : "memory");
+}
+MMD_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 // copy an N-double record (16-byte pieces when N is even)
 template <int N>
 MMD_D void cp_async_rec(unsigned sdst, const double* gsrc) {
@@ -173,7 +216,173 @@ struct SweepArgs {
   double* xend_out;      // thread-private [rmax*X] or null
   double* xs_out;        // thread-private trajectory records [rmax*S][X] (state BEFORE each step) or null
   int nta, cpb, NT, tid;
+  unsigned mask;         // lanes of this warp that run the sweep (0: caller did not form it -> per-thread cp.async path)
+  unsigned long long* bars;  // one mbarrier per warp (shared memory)
+  unsigned long long* phase;  // MMD_PHASE_CLOCK builds: cycle counters (slot 31: waits for the ring, slot 8: recursion)
 };
+
+// Warp-cooperative form of the quasi-Newton sweep on bulk copies.  The ring holds NSL steps: slot u =
+// [v slab: NT x V][K slab: NT x X*V] exactly as the arrays lie in global memory, so the records of one warp are one
+// contiguous piece per array and step.  Per group of NSL steps: wait on the warp's mbarrier, read the NSL records
+// and form v_t = qw_t - K_t^T alpha_k (independent of the recursion), __syncwarp, the elected lane re-arms the
+// barrier and issues the 2 * NSL bulk copies of the next group (plus an L2 prefetch of the one after), then the
+// NSL serial steps run while the copies are in flight.  Lanes whose block has fewer intervals stay in the loop
+// (predicated) so the warp keeps its barrier protocol; lanes outside `mask` never enter.  Same floating-point
+// operations in the same order as constr_sweep.
+template <class M, bool WITH_K>
+__device__ __noinline__ void constr_sweep_bulk(const Dims& d, const Blk& B, const SweepArgs<M>& a) {
+  constexpr int X = M::X, V = M::V, XV = M::X * M::V;
+  constexpr int NSL = MMD_PREFETCH_STEPS + 1;
+  const int nta = a.nta, NT = a.NT, S = d.S;
+  const unsigned mask = a.mask;
+  const int lane = a.tid & 31, warp = a.tid >> 5;
+  const bool leader = lane == (__ffs(mask) - 1);
+  const int nl = (NT - warp * 32) < 32 ? (NT - warp * 32) : 32;     // threads of this warp
+  const int nkw = __reduce_max_sync(mask, B.n);                      // intervals the warp walks through
+  const int nsw = nkw * S;
+  const typename M::Coef C = a.C;
+  double x[X];
+#pragma unroll
+  for (int i = 0; i < X; ++i) x[i] = a.xstart[i];
+  // shared-memory addresses: slot u at ring + u * slot_bytes; inside a slot the v slab, then the K slab
+  const unsigned slot_bytes = (unsigned)NT * (RingRec<M>::NWP * 8);
+  const unsigned ring = smem_u32(a.ring);
+  const unsigned my_v = ring + (unsigned)a.tid * (V * 8);
+  const unsigned my_K = ring + (unsigned)NT * (V * 8) + (unsigned)a.tid * (XV * 8);
+  const unsigned w_v = ring + (unsigned)(warp * 32) * (V * 8);
+  const unsigned w_K = ring + (unsigned)NT * (V * 8) + (unsigned)(warp * 32) * (XV * 8);
+  const unsigned bar = smem_u32(a.bars) + 8u * warp;
+  const double* vw = a.vb - lane * V;     // the warp's slab of step 0
+  const double* Kw = WITH_K ? a.Kb - lane * XV : nullptr;
+  const unsigned vbytes = (unsigned)nl * (V * 8), Kbytes = WITH_K ? (unsigned)nl * (XV * 8) : 0u;
+  const int vbump = V * nta, Kbump = XV * nta;
+  auto issue_group = [&](int s0) {   // leader only: steps s0 .. s0 + NSL - 1 into slots 0 .. NSL - 1
+    mbar_expect_tx(bar, NSL * (vbytes + Kbytes));
+#pragma unroll
+    for (int u = 0; u < NSL; ++u) {
+      bulk_g2s(w_v + u * slot_bytes, vw + (size_t)(s0 + u) * vbump, vbytes, bar);
+      if (WITH_K) bulk_g2s(w_K + u * slot_bytes, Kw + (size_t)(s0 + u) * Kbump, Kbytes, bar);
+    }
+#if MMD_L2_PREFETCH_STEPS > 0
+    if (s0 + 2 * NSL <= nsw - NSL) {   // the group after the next one: HBM -> L2
+#pragma unroll
+      for (int u = 0; u < NSL; ++u) {
+        bulk_prefetch_l2(vw + (size_t)(s0 + 2 * NSL + u) * vbump, vbytes);
+        if (WITH_K) bulk_prefetch_l2(Kw + (size_t)(s0 + 2 * NSL + u) * Kbump, Kbytes);
+      }
+    }
+#endif
+  };
+#ifdef MMD_BULK_DEBUG
+  if (blockIdx.x == 0) printf("enter tid %d warp %d lane %d mask %x leader %d nl %d nkw %d S %d vb %u Kb %u bar %u ring %u NT %d nta %d Bn %d\n", a.tid, warp, lane, mask, (int)leader, nl, nkw, S, vbytes, Kbytes, bar, ring, NT, nta, B.n);
+#endif
+  if (leader) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();   // the ring region was last touched through the generic proxy (reduction scratch)
+#if MMD_L2_PREFETCH_STEPS > 0
+    if (2 * NSL <= nsw) {
+#pragma unroll
+      for (int u = 0; u < NSL; ++u) {
+        bulk_prefetch_l2(vw + (size_t)(NSL + u) * vbump, vbytes);
+        if (WITH_K) bulk_prefetch_l2(Kw + (size_t)(NSL + u) * Kbump, Kbytes);
+      }
+    }
+#endif
+    issue_group(0);
+  }
+  __syncwarp(mask);
+  unsigned parity = 0;
+  const int gpi = S / NSL;
+  double al[X], aln[X];
+#pragma unroll
+  for (int i = 0; i < X; ++i) al[i] = aln[i] = 0.0;
+  if (WITH_K) ldcol<X>(a.alph, nta, al);
+  int s0 = 0;
+  for (int k = 0; k < nkw; ++k) {
+    const bool live = k < B.n;
+    double yk = 0.0, nk = 0.0;
+    if (live && k < B.ny) {
+      yk = a.y[B.o + k];
+      if (d.noisy) nk = a.nzb[k * nta];
+    }
+    if (WITH_K && k + 1 < B.n) ldcol<X>(a.alph + (k + 1) * X * nta, nta, aln);
+    for (int g = 0; g < gpi; ++g) {
+#ifdef MMD_PHASE_CLOCK
+      const long long tw0 = clock64();
+#endif
+#ifdef MMD_BULK_DEBUG
+      if (blockIdx.x == 0) printf("wait tid %d k %d g %d parity %u\n", a.tid, k, g, parity);
+#endif
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+#ifdef MMD_BULK_DEBUG
+      if (blockIdx.x == 0) printf("pass tid %d k %d g %d\n", a.tid, k, g);
+#endif
+#ifdef MMD_PHASE_CLOCK
+      const long long tw1 = clock64();
+      if (threadIdx.x == 0 && a.phase) atomicAdd(&a.phase[31], (unsigned long long)(tw1 - tw0));
+#endif
+      double v[NSL][V];
+#pragma unroll
+      for (int u = 0; u < NSL; ++u) {
+        lds_rec<V>(my_v + u * slot_bytes, v[u]);
+        if (WITH_K) {
+          double Kt[XV];
+          lds_rec<XV>(my_K + u * slot_bytes, Kt);
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+#pragma unroll
+            for (int i = 0; i < X; ++i) v[u][j] = fma(-Kt[i * V + j], al[i], v[u][j]);
+        }
+      }
+      s0 += NSL;
+      __syncwarp(mask);   // every lane has read its records: the slots may be overwritten
+      if (leader && s0 < nsw) issue_group(s0);
+#ifdef MMD_PHASE_CLOCK
+      const long long tc0 = clock64();
+#endif
+      if (live) {
+#pragma unroll
+        for (int u = 0; u < NSL; ++u) {
+          double xn[X];
+          M::step(C, x, v[u], xn);
+#pragma unroll
+          for (int i = 0; i < X; ++i) x[i] = xn[i];
+        }
+      }
+#ifdef MMD_PHASE_CLOCK
+      if (threadIdx.x == 0 && a.phase) {
+        const long long tc1 = clock64();
+        atomicAdd(&a.phase[8], (unsigned long long)(tc1 - tc0) + (unsigned long long)(x[0] == 1.2345e300 ? 1 : 0));
+      }
+#endif
+    }
+    if (live) {
+      if (k < B.ny) {
+        double cy = M::obs(x) - yk;
+        if (d.noisy) {
+          if (WITH_K) nk = fma(-a.sigma_lin, a.lamtot[k * NT], nk);
+          cy = fma(a.sigma_y, nk, cy);
+        }
+        a.crow[k * NT] = cy;
+      }
+      if (k == B.n - 1 && B.nx > 0) {
+        double xo[X];
+        ldcol<X>(a.xoc + (B.o + k) * X * a.cpb, a.cpb, xo);
+#pragma unroll
+        for (int i = 0; i < X; ++i) a.crow[(B.ny + i) * NT] = x[i] - xo[i];
+      }
+    }
+    if (WITH_K) {
+#pragma unroll
+      for (int i = 0; i < X; ++i) al[i] = aln[i];
+    }
+  }
+  // the barrier object must be invalidated before the next sweep initialises it again
+  __syncwarp(mask);
+  if (leader) mbar_inval(bar);
+}
 
 template <class M, bool WITH_K, bool WITH_XS = false>
 __device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const SweepArgs<M>& a) {
@@ -190,6 +399,132 @@ __device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const Swe
   const double* vp = a.vb;   // next record to fetch
   const double* Kp = a.Kb;
   const int vbump = V * nta, Kbump = XV * nta;
+#if defined(MMD_GROUPED_SWEEP) || defined(MMD_BULK_SWEEP)   // opt-in (build with -DMMD_PREFETCH_STEPS=4): measured slower under full load, see DESIGN.md
+  // Grouped form (quasi-Newton sweeps, S a multiple of the ring size): the recursion x_{t+1} = f(x_t, v_t) is a chain
+  // of ~9 dependent FP64 operations per step, and with one or two warps per scheduler nothing else hides their
+  // latency -- the step-at-a-time loop below runs at ~560 cycles per step on an otherwise idle SM although the chain
+  // itself is ~80.  Here NSL steps are handled together: their records are read from the ring and turned into
+  // v_t = qw_t - K_t^T alpha_k (independent of x: full instruction-level parallelism), the ring is refilled for the
+  // next group right away, and only then the NSL serial steps run, with nothing but arithmetic between them.  The
+  // observation row, noise variable and next alpha of an interval are fetched at its start.  Same operations in the
+  // same order as the loop below: bit-identical results.
+#if defined(MMD_BULK_SWEEP)
+  if (!WITH_XS && (S % NSL) == 0 && (V % 2) == 0 && (XV % 2) == 0 && a.mask != 0u) {
+    // bulk copies need 16-byte aligned slabs (warp-uniform test: the slab of the warp's first lane and the step strides)
+    unsigned long long al16 = reinterpret_cast<unsigned long long>(a.vb - (a.tid & 31) * V) | (unsigned long long)(V * nta * 8);
+    if (WITH_K) al16 |= reinterpret_cast<unsigned long long>(a.Kb - (a.tid & 31) * XV) | (unsigned long long)(XV * nta * 8);
+    if ((al16 & 15ull) == 0ull) {
+      constr_sweep_bulk<M, WITH_K>(d, B, a);
+      return;
+    }
+  }
+#endif
+  if (!WITH_XS && (S % NSL) == 0) {
+    auto fetch_group = [&](int s0) {   // records of steps s0 .. s0 + NSL - 1 into slots 0 .. NSL - 1
+#pragma unroll
+      for (int u = 0; u < NSL; ++u) {
+        cp_async_rec<V>(ring0 + u * sstride, vp + u * vbump);
+        if (WITH_K) cp_async_rec<XV>(ring0 + u * sstride + V * 8, Kp + u * Kbump);
+      }
+#if MMD_L2_PREFETCH_STEPS > 0
+      if (s0 + 3 * NSL <= ns) {   // pull the group after the next one from HBM into L2
+#pragma unroll
+        for (int u = 0; u < NSL; ++u) {
+          prefetch_l2(vp + (2 * NSL + u) * vbump);
+          if (WITH_K) prefetch_l2(Kp + (2 * NSL + u) * Kbump);
+        }
+      }
+#endif
+      vp += NSL * vbump;
+      Kp += NSL * Kbump;
+      cp_async_commit();
+    };
+#if MMD_L2_PREFETCH_STEPS > 0
+    if (2 * NSL <= ns) {
+#pragma unroll
+      for (int u = 0; u < NSL; ++u) {
+        prefetch_l2(vp + (NSL + u) * vbump);
+        if (WITH_K) prefetch_l2(Kp + (NSL + u) * Kbump);
+      }
+    }
+#endif
+    fetch_group(0);
+    const int gpi = S / NSL;
+    double al[X], aln[X];
+    if (WITH_K) ldcol<X>(a.alph, nta, al);
+    int s0 = 0;
+    for (int k = 0; k < B.n; ++k) {
+      // per-interval operands, in flight while the interval is integrated
+      double yk = 0.0, nk = 0.0;
+      if (k < B.ny) {
+        yk = a.y[B.o + k];
+        if (d.noisy) nk = a.nzb[k * nta];
+      }
+      if (WITH_K && k + 1 < B.n) ldcol<X>(a.alph + (k + 1) * X * nta, nta, aln);
+      for (int g = 0; g < gpi; ++g) {
+#ifdef MMD_PHASE_CLOCK
+        const long long tw0 = clock64();
+#endif
+        cp_async_wait<0>();
+#ifdef MMD_PHASE_CLOCK
+        const long long tw1 = clock64();
+        if (threadIdx.x == 0 && a.phase) atomicAdd(&a.phase[31], (unsigned long long)(tw1 - tw0));
+#endif
+        double v[NSL][V];
+#pragma unroll
+        for (int u = 0; u < NSL; ++u) {
+          lds_rec<V>(ring0 + u * sstride, v[u]);
+          if (WITH_K) {
+            double Kt[XV];
+            lds_rec<XV>(ring0 + u * sstride + V * 8, Kt);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+#pragma unroll
+              for (int i = 0; i < X; ++i) v[u][j] = fma(-Kt[i * V + j], al[i], v[u][j]);
+          }
+        }
+        s0 += NSL;
+        if (s0 < ns) fetch_group(s0);
+#ifdef MMD_PHASE_CLOCK
+        const long long tc0 = clock64();
+#endif
+#pragma unroll
+        for (int u = 0; u < NSL; ++u) {
+          double xn[X];
+          M::step(C, x, v[u], xn);
+#pragma unroll
+          for (int i = 0; i < X; ++i) x[i] = xn[i];
+        }
+#ifdef MMD_PHASE_CLOCK
+        if (threadIdx.x == 0 && a.phase) {
+          const long long tc1 = clock64();
+          atomicAdd(&a.phase[8], (unsigned long long)(tc1 - tc0) + (unsigned long long)(x[0] == 1.2345e300 ? 1 : 0));
+        }
+#endif
+      }
+      if (k < B.ny) {
+        double cy = M::obs(x) - yk;
+        if (d.noisy) {
+          if (WITH_K) nk = fma(-a.sigma_lin, a.lamtot[k * NT], nk);
+          cy = fma(a.sigma_y, nk, cy);
+        }
+        a.crow[k * NT] = cy;
+      }
+      if (k == B.n - 1 && B.nx > 0) {
+        double xo[X];
+        ldcol<X>(a.xoc + (B.o + k) * X * a.cpb, a.cpb, xo);
+#pragma unroll
+        for (int i = 0; i < X; ++i) a.crow[(B.ny + i) * NT] = x[i] - xo[i];
+      }
+      if (WITH_K) {
+#pragma unroll
+        for (int i = 0; i < X; ++i) al[i] = aln[i];
+      }
+    }
+    cp_async_wait<0>();
+    return;
+  }
+#endif
   unsigned wr = ring0;
 #pragma unroll
   for (int i = 0; i < PF; ++i) {
@@ -203,62 +538,74 @@ __device__ __noinline__ void constr_sweep(const Dims& d, const Blk& B, const Swe
     wr += sstride;
   }
   unsigned rd = ring0;
-  double al[X];
+  double al[X], aln[X];
+#pragma unroll
+  for (int i = 0; i < X; ++i) aln[i] = 0.0;
   if (WITH_K) ldcol<X>(a.alph, nta, al);
-  int k = 0, t = 0;
-  for (int s = 0; s < ns; ++s) {
-    cp_async_wait<PF - 1>();
-    double v[V], xn[X];
-    if (WITH_XS && a.xs_out) strec<X>(a.xs_out + s * X * nta, x);   // (Newton only: keeps the test out of the loop)
-    lds_rec<V>(rd, v);
-    if (WITH_K) {
-      double Kt[XV];
-      lds_rec<XV>(rd + V * 8, Kt);
+  int s = 0;
+  for (int k = 0; k < B.n; ++k) {
+    // operands of the interval's end (observation, noise variable, conditioned state, next alpha): requested now, so
+    // the loads are in flight while the interval is integrated instead of stalling the recursion at its last step
+    double yk = 0.0, nk = 0.0, xo[X];
 #pragma unroll
-      for (int j = 0; j < V; ++j)
-#pragma unroll
-        for (int i = 0; i < X; ++i) v[j] = fma(-Kt[i * V + j], al[i], v[j]);
+    for (int i = 0; i < X; ++i) xo[i] = 0.0;
+    if (k < B.ny) {
+      yk = a.y[B.o + k];
+      if (d.noisy) nk = a.nzb[k * nta];
     }
-    if (s + PF < ns) {  // refill the slot consumed one step ago
-      cp_async_rec<V>(wr, vp);
-      if (WITH_K) cp_async_rec<XV>(wr + V * 8, Kp);
+    if (k == B.n - 1 && B.nx > 0) ldcol<X>(a.xoc + (B.o + k) * X * a.cpb, a.cpb, xo);
+    if (WITH_K && k + 1 < B.n) ldcol<X>(a.alph + (k + 1) * X * nta, nta, aln);
+    for (int t = 0; t < S; ++t, ++s) {
+      cp_async_wait<PF - 1>();
+      double v[V], xn[X];
+      if (WITH_XS && a.xs_out) strec<X>(a.xs_out + s * X * nta, x);   // (Newton only: keeps the test out of the loop)
+      lds_rec<V>(rd, v);
+      if (WITH_K) {
+        double Kt[XV];
+        lds_rec<XV>(rd + V * 8, Kt);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+#pragma unroll
+          for (int i = 0; i < X; ++i) v[j] = fma(-Kt[i * V + j], al[i], v[j]);
+      }
+      if (s + PF < ns) {  // refill the slot consumed one step ago
+        cp_async_rec<V>(wr, vp);
+        if (WITH_K) cp_async_rec<XV>(wr + V * 8, Kp);
 #if MMD_L2_PREFETCH_STEPS > 0
-      if (s + PF + MMD_L2_PREFETCH_STEPS < ns) {  // pull the records of a later step from HBM into L2
-        prefetch_l2(vp + MMD_L2_PREFETCH_STEPS * vbump);
-        if (WITH_K) prefetch_l2(Kp + MMD_L2_PREFETCH_STEPS * Kbump);
-      }
-#endif
-      vp += vbump;
-      Kp += Kbump;
-    }
-    cp_async_commit();
-    rd += sstride;
-    if (rd == ring_end) rd = ring0;
-    wr += sstride;
-    if (wr == ring_end) wr = ring0;
-    M::step(C, x, v, xn);
-#pragma unroll
-    for (int i = 0; i < X; ++i) x[i] = xn[i];
-    if (++t == S) {  // end of observation interval k
-      t = 0;
-      if (WITH_XS && a.xend_out) stcol<X>(a.xend_out + k * X * nta, nta, x);
-      if (k < B.ny) {
-        double cy = M::obs(x) - a.y[B.o + k];
-        if (d.noisy) {
-          double nk = a.nzb[k * nta];
-          if (WITH_K) nk = fma(-a.sigma_lin, a.lamtot[k * NT], nk);
-          cy = fma(a.sigma_y, nk, cy);
+        if (s + PF + MMD_L2_PREFETCH_STEPS < ns) {  // pull the records of a later step from HBM into L2
+          prefetch_l2(vp + MMD_L2_PREFETCH_STEPS * vbump);
+          if (WITH_K) prefetch_l2(Kp + MMD_L2_PREFETCH_STEPS * Kbump);
         }
-        a.crow[k * NT] = cy;
+#endif
+        vp += vbump;
+        Kp += Kbump;
       }
-      if (k == B.n - 1 && B.nx > 0) {
-        double xo[X];
-        ldcol<X>(a.xoc + (B.o + k) * X * a.cpb, a.cpb, xo);
+      cp_async_commit();
+      rd += sstride;
+      if (rd == ring_end) rd = ring0;
+      wr += sstride;
+      if (wr == ring_end) wr = ring0;
+      M::step(C, x, v, xn);
 #pragma unroll
-        for (int i = 0; i < X; ++i) a.crow[(B.ny + i) * NT] = x[i] - xo[i];
+      for (int i = 0; i < X; ++i) x[i] = xn[i];
+    }
+    // end of observation interval k
+    if (WITH_XS && a.xend_out) stcol<X>(a.xend_out + k * X * nta, nta, x);
+    if (k < B.ny) {
+      double cy = M::obs(x) - yk;
+      if (d.noisy) {
+        if (WITH_K) nk = fma(-a.sigma_lin, a.lamtot[k * NT], nk);
+        cy = fma(a.sigma_y, nk, cy);
       }
-      ++k;
-      if (WITH_K && k < B.n) ldcol<X>(a.alph + k * X * nta, nta, al);
+      a.crow[k * NT] = cy;
+    }
+    if (k == B.n - 1 && B.nx > 0) {
+#pragma unroll
+      for (int i = 0; i < X; ++i) a.crow[(B.ny + i) * NT] = x[i] - xo[i];
+    }
+    if (WITH_K) {
+#pragma unroll
+      for (int i = 0; i < X; ++i) al[i] = aln[i];
     }
   }
   cp_async_wait<0>();
@@ -314,6 +661,18 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
                        const double* __restrict__ xendc, int nta, double* alph_out, double* alpha_start,
                        const double* __restrict__ kapc = nullptr, double* body_bound = nullptr) {
   constexpr int X = M::X;
+  // small blocks: every Psib_k of the block is fetched up front in one batch of volatile loads (one L2 round trip for
+  // the whole recursion instead of one per interval; intervals beyond the block re-read its last one)
+  constexpr bool PRELOAD = RMAX * X * X <= 24;
+  double Pall[PRELOAD ? RMAX : 1][X * X];
+  if (PRELOAD) {
+#pragma unroll
+    for (int k = 0; k < RMAX; ++k) {
+      const int kk = k < B.n ? k : B.n - 1;
+#pragma unroll
+      for (int i = 0; i < X * X; ++i) Pall[PRELOAD ? k : 0][i] = ldg_vol(Psibc + (kk * X * X + i) * nta);
+    }
+  }
   double al[X], bnd = 0.0;
 #pragma unroll
   for (int i = 0; i < X; ++i) al[i] = 0.0;
@@ -322,7 +681,12 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
     if (k < B.n) {
       if (k < B.n - 1) {
         double Ps[X * X], t[X];
-        ldcol_keep<X * X>(Psibc + (k + 1) * X * X * nta, nta, Ps);
+        if (PRELOAD) {
+#pragma unroll
+          for (int i = 0; i < X * X; ++i) Ps[i] = Pall[(PRELOAD && k + 1 < RMAX) ? k + 1 : 0][i];
+        } else {
+          ldcol_keep<X * X>(Psibc + (k + 1) * X * X * nta, nta, Ps);
+        }
         mtv<X, X>(Ps, al, t);
 #pragma unroll
         for (int i = 0; i < X; ++i) al[i] = t[i];
@@ -356,7 +720,12 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
   }
   {
     double Ps[X * X];
-    ldcol_keep<X * X>(Psibc, nta, Ps);
+    if (PRELOAD) {
+#pragma unroll
+      for (int i = 0; i < X * X; ++i) Ps[i] = Pall[0][i];
+    } else {
+      ldcol_keep<X * X>(Psibc, nta, Ps);
+    }
     mtv<X, X>(Ps, al, alpha_start);
   }
   if (body_bound) *body_bound = bnd;
@@ -371,10 +740,31 @@ MMD_D void alpha_block(const Blk& B, const double* lam, const double* __restrict
 // iteration.  `r` (registers, NRMAX entries, entries >= nrows ignored) is overwritten by lam_b; s (= u-part of
 // J^T G^{-1} r) is returned in `s_out`.  `extra_max` rides along the same cross-block reduction as a maximum (the
 // solver's |c|_inf).
+// Loads: the factors are thread-private columns in global memory (L2 / L1 hits).  Left to the compiler, each load
+// ends up next to the multiply-add that consumes it (the register cap leaves no room to hoist 57 loads), i.e. a chain
+// of ~25 exposed L2 round trips per call -- 41 k cycles measured on an otherwise idle SM, once per solver iteration.
+// Here they are issued in a few batches of volatile loads (kept together, in order, by the compiler), two columns of
+// D^-1 plus two rows of D^-1 A per batch, and the capacitance factor is fetched before the reduction barrier: three
+// round trips for the first product, two for the second.  The order of the floating-point operations is unchanged.
 template <class M, int NRMAX, int UMAX, bool TAIL_SYNC = true>
 MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const double* __restrict__ Dic,
                           const double* __restrict__ DinvAc, const double* __restrict__ LCc, double* r, double* s_out,
-                          double* extra_max, double* smem_red, const Tid& t) {
+                          double* extra_max, double* smem_red, const Tid& t, unsigned long long* ph = nullptr) {
+#ifdef MMD_PHASE_CLOCK
+  long long _pg = clock64();
+#define PHG(i)                                                                                     \
+  do {                                                                                             \
+    if (threadIdx.x == 0 && ph) {                                                                  \
+      const long long _n = clock64();                                                              \
+      atomicAdd(&ph[i], (unsigned long long)(_n - _pg));                                           \
+      _pg = _n;                                                                                    \
+    }                                                                                              \
+  } while (0)
+#else
+#define PHG(i)
+#endif
+  constexpr int UTRI = UMAX * (UMAX + 1) / 2;
+  constexpr int CG = (NRMAX <= 8) ? 2 : 1;   // columns of D^-1 (and rows of D^-1 A) per load batch
   const int U = d.U, nta = t.nta;
   const int n = has_blk ? B.nrows : 0;
   double g[UMAX + 1], tb[NRMAX];
@@ -385,43 +775,85 @@ MMD_D void inv_gram_block(const Dims& d, const Blk& B, bool has_blk, const doubl
   for (int i = 0; i < NRMAX; ++i) tb[i] = 0.0;
   if (has_blk) {
     MMD_SOLVE_UNROLL
-    for (int i = 0; i < NRMAX; ++i) {
-      if (i < n) {
-        const double ri = r[i];
-        // column i of the packed symmetric inverse: entries (k, i), k >= i, and by symmetry (i, k)
-        MMD_SOLVE_UNROLL
-        for (int k = i; k < NRMAX; ++k)
-          if (k < n) {
-            const double dv = Dic[tri(k, i) * nta];
-            tb[k] = fma(dv, ri, tb[k]);
-            if (k != i) tb[i] = fma(dv, r[k], tb[i]);
-          }
+    for (int i0 = 0; i0 < NRMAX; i0 += CG) {
+      if (i0 < n) {
+        double dv[CG][NRMAX], av[CG][UMAX];
 #pragma unroll
-        for (int j = 0; j < UMAX; ++j)
-          if (j < U) g[j] = fma(DinvAc[(i * U + j) * nta], ri, g[j]);
+        for (int c = 0; c < CG; ++c) {
+          const int i = i0 + c;
+          if (i < NRMAX) {
+            // column i of the packed symmetric inverse: entries (k, i), k >= i  (rows >= n: allocated, ignored below)
+#pragma unroll
+            for (int k = i; k < NRMAX; ++k) dv[c][k] = ldg_vol(Dic + tri(k, i) * nta);
+#pragma unroll
+            for (int j = 0; j < UMAX; ++j) av[c][j] = ldg_vol(DinvAc + (i * U + (j < U ? j : U - 1)) * nta);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+          const int i = i0 + c;
+          if (i < NRMAX && i < n) {
+            const double ri = r[i];
+#pragma unroll
+            for (int k = i; k < NRMAX; ++k)
+              if (k < n) {
+                tb[k] = fma(dv[c][k], ri, tb[k]);
+                if (k != i) tb[i] = fma(dv[c][k], r[k], tb[i]);
+              }
+#pragma unroll
+            for (int j = 0; j < UMAX; ++j)
+              if (j < U) g[j] = fma(av[c][j], ri, g[j]);
+          }
+        }
       }
     }
   }
-  block_reduce<UMAX, 1, TAIL_SYNC>(g, smem_red, t);
-  if (extra_max) *extra_max = g[UMAX];
-  double LCm[UMAX * (UMAX + 1) / 2];
+  // factor of the capacitance matrix: fetched before the barrier of the reduction, used after it
+  double LCm[UTRI];
+  {
+    const int utri = U * (U + 1) / 2;
 #pragma unroll
-  for (int i = 0; i < UMAX * (UMAX + 1) / 2; ++i) LCm[i] = (i < U * (U + 1) / 2) ? LCc[i * t.cpb] : 0.0;
+    for (int i = 0; i < UTRI; ++i) {
+      const double v = ldg_vol(LCc + (i < utri ? i : 0) * t.cpb);
+      LCm[i] = (i < utri) ? v : 0.0;
+    }
+  }
+  PHG(32);
+  block_reduce<UMAX, 1, TAIL_SYNC>(g, smem_red, t);
+  PHG(33);
+  if (extra_max) *extra_max = g[UMAX];
   chol_solve_invdiag_fixed<UMAX>(LCm, U, g);
 #pragma unroll
   for (int j = 0; j < UMAX; ++j) s_out[j] = g[j];
+  PHG(34);
   if (has_blk) {
+    constexpr int RG = (NRMAX <= 8) ? 3 : 1;   // rows of D^-1 A per load batch
     MMD_SOLVE_UNROLL
-    for (int i = 0; i < NRMAX; ++i) {
-      if (i < n) {
-        double ti = tb[i];
+    for (int i0 = 0; i0 < NRMAX; i0 += RG) {
+      if (i0 < n) {
+        double av[RG][UMAX];
 #pragma unroll
-        for (int j = 0; j < UMAX; ++j)
-          if (j < U) ti = fma(-DinvAc[(i * U + j) * nta], g[j], ti);
-        r[i] = ti;
+        for (int c = 0; c < RG; ++c)
+          if (i0 + c < NRMAX) {
+#pragma unroll
+            for (int j = 0; j < UMAX; ++j) av[c][j] = ldg_vol(DinvAc + ((i0 + c) * U + (j < U ? j : U - 1)) * nta);
+          }
+#pragma unroll
+        for (int c = 0; c < RG; ++c) {
+          const int i = i0 + c;
+          if (i < NRMAX && i < n) {
+            double ti = tb[i];
+#pragma unroll
+            for (int j = 0; j < UMAX; ++j)
+              if (j < U) ti = fma(-av[c][j], g[j], ti);
+            r[i] = ti;
+          }
+        }
       }
     }
   }
+  PHG(35);
+#undef PHG
 }
 
 }  // namespace mmd

@@ -13,7 +13,9 @@ from tests.helpers import make_batched, make_fhn_problem
 
 pytestmark = pytest.mark.gpu
 
-CASES = [(10, 5, 5), (12, 4, 5), (7, 6, 3)]
+# the last case has blocks of 10 observations (11 constraint rows): the 16-row FHN instantiation (mmd_ops_fhn_r16.cu),
+# the R = 10 point of the reference's operation-time sweep (run_fhn_model_noiseless_obs_experiments.sh:16-22)
+CASES = [(10, 5, 5), (12, 4, 5), (7, 6, 3), (20, 5, 10)]
 
 
 @pytest.fixture(scope="module", params=CASES, ids=lambda c: "T%d_S%d_R%d" % c)

@@ -79,4 +79,28 @@ if os.environ.get("CPU", "1") == "1":
     pp = sysm.project_onto_cotangent_space(torch.tensor(rng.standard_normal(pr["q"].shape[1])), pt)
     t0 = time.perf_counter(); O.leapfrog_step(sysm, pr["q"][0], pp, pr["xobs"][0], 0, 0.02, pt=pt); cpu["constrained_leapfrog_step_quasi_newton"] = time.perf_counter() - t0
     res["cpu_oracle_seconds_per_state_one_core"] = {k: round(v, 4) for k, v in cpu.items()}
+    # compiled CPU column (numba restatement of the same path, oracle/numba_chmc.py), one core, median of repeats,
+    # the state of one chain on the manifold after the burn-in above
+    os.environ["NUMBA_NUM_THREADS"] = "1"
+    from oracle import numba_chmc as N
+    ch = N.NumbaChain(T, S, R, y, 0.2)
+    ch.set_state(q[0], x[0], 0)
+    nrng = np.random.default_rng(1)
+
+    def med(fn, reps=7):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+    bo, bn = ch.parts[0]
+    ch.refresh_momentum(nrng); ch.step(0.05); ch._relinearize()          # compile
+    cn = {"jacob_constr_blocks+chol_gram_blocks+log_det_sqrt_gram": med(lambda: N.linearize(ch.q, ch.xobs, ch.y, bo, bn, S, ch.dl)),
+          "grad_log_det_sqrt_gram (incl. the above)": med(ch._relinearize),
+          "project_onto_cotangent_space": med(lambda: ch.refresh_momentum(nrng))}
+
+    def one_step():
+        ch.refresh_momentum(nrng)
+        ch.step(0.05)
+    cn["constrained_leapfrog_step_quasi_newton (incl. one momentum projection)"] = med(one_step)
+    res["cpu_numba_microseconds_per_state_one_core"] = {k: round(v * 1e6, 1) for k, v in cn.items()}
 print(json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in res.items()}))

@@ -24,7 +24,7 @@ xo = np.concatenate((np.broadcast_to(y, (n, T, 1)), 0.5 * rng.standard_normal((n
 bc.init_linear_interpolation(u, v0, xo, 0)
 for it in range(burn):
     bc.hmc_transition(0.05, 8, 1, it)
-out = (C.c_ulonglong * 32)()
+out = (C.c_ulonglong * 64)()
 from manifold_mcmc_for_diffusions_b200._lib import check  # noqa: E402
 check(bc._L.mmd_debug_phase_cycles(bc._h, out, 1))
 bc.successful_steps(reset=True)
@@ -57,4 +57,20 @@ res = {"chains": n, "ms_per_step": ms / (L * ntr), "chain_steps_per_s": bc.succe
                                           "grad: forward tangent sweep": round(c[20] / step_cycles, 4),
                                           "grad: reverse adjoint sweep": round(c[21] / step_cycles, 4),
                                           "grad: tail + reduce": round(c[23] / step_cycles, 4)}}
+# absolute CTA-resident cycles per tile and step (meaningful as latencies when one CTA is resident per SM: NCH <= 148 * cpb)
+keys = {0: "project_fwd", 1: "solve_fwd", 2: "linearise", 3: "project_rev", 4: "solve_rev", 5: "project_kick2", 6: "commit", 9: "solve_sweeps",
+        10: "solve_block_algebra", 11: "solve_checks", 15: "solve_final_pass", 16: "lin_sweeps12", 17: "lin_obs_algebra", 18: "lin_cap_reduce",
+        19: "grad_block_algebra", 22: "grad_setup", 20: "grad_fwd_sweep", 21: "grad_rev_sweep", 23: "grad_tail"}
+res["cycles_per_cta_step"] = {v: round(c[k] / c[7]) for k, v in keys.items()}
+res["solver_iteration_detail_cycles_per_iteration"] = {
+    "thread0_working_fraction": round(c[30] / max(c[12], 1), 3),
+    "loop top: parameters, coefficients, block start": round(c[24] / max(c[12], 1)),
+    "sweep call": round(c[25] / max(c[12], 1)), "  of which waits for the ring (cp.async)": round(c[31] / max(c[12], 1)),
+    "  of which the serial recursion": round(c[8] / max(c[12], 1)), "barrier after sweep": round(c[26] / max(c[12], 1)),
+    "Woodbury block solve incl. cross-block reduction": round(c[27] / max(c[12], 1)),
+    "  first product (factor loads, D^-1 r, (D^-1 A)^T r, capacitance factor loads)": round(c[32] / max(c[12], 1)),
+    "  cross-block reduction (barrier + sums)": round(c[33] / max(c[12], 1)),
+    "  capacitance solve": round(c[34] / max(c[12], 1)), "  second product": round(c[35] / max(c[12], 1)),
+    "multiplier update + alpha recursion": round(c[28] / max(c[12], 1)), "barrier (any check)": round(c[29] / max(c[12], 1))}
+res["step_cycles"] = round(step_cycles / c[7])
 print(json.dumps(res))
