@@ -1,21 +1,14 @@
-// GENERATED by tools/gen_model_code.py -- do not edit by hand.
 // FitzHugh-Nagumo model with the prior parametrisation of the reference's notebook
-// (FitzHugh-Nagumo_example.ipynb cells 7-18): same strong-order-1.5 step as fhn.py, different
-// generate_z / generate_x_0.  Used for the distributional known-answer test against the
-// posterior table recorded in the notebook.
+// (FitzHugh-Nagumo_example.ipynb cells 7-18): the strong-order-1.5 step, its derivatives and the observation
+// function are those of FhnModel (mmd_model_fhn.cuh, inherited); only generate_z / generate_x_0 differ.  Used for the
+// distributional known-answer test against the posterior table recorded in the notebook.
 #pragma once
-#include "mmd_common.cuh"
+#include "mmd_model_fhn.cuh"
 
-struct FhnNotebookModel {
-  static constexpr int X = 2;   // dim_x   (fhn.py:10)
-  static constexpr int V = 2;   // dim_v   (fhn.py:14)
-  static constexpr int Z = 4;   // dim_z   (fhn.py:12)  z = [sigma, epsilon, gamma, beta]
-  static constexpr int V0 = 2;  // dim_v_0 (fhn.py:13)
-  static constexpr int Y = 1;   // dim_y: obs_func(x) = x[0]  (fhn.py:37-38)
+struct FhnNotebookModel : FhnModel {
   static constexpr int MODEL_ID = 2;
 
-  // z = generate_z(u) of FitzHugh-Nagumo_example.ipynb (cell 18):
-  //   [exp(.5 u0 - 1), exp(.5 u1 - 2), .5 u2 + 1, .5 u3 + 1]
+  // z = generate_z(u) (notebook cell 18): [exp(.5 u0 - 1), exp(.5 u1 - 2), .5 u2 + 1, .5 u3 + 1]
   MMD_HD static void gen_z(const double* u, double* z, double* dzdu /* Z x Z */) {
     z[0] = exp(0.5 * u[0] - 1.0); z[1] = exp(0.5 * u[1] - 2.0); z[2] = 0.5 * u[2] + 1.0; z[3] = 0.5 * u[3] + 1.0;
     for (int i = 0; i < 16; ++i) dzdu[i] = 0.0;
@@ -33,193 +26,4 @@ struct FhnNotebookModel {
     dx0_dv0[0] = 1.0; dx0_dv0[1] = 0.0; dx0_dv0[2] = 0.0; dx0_dv0[3] = 1.0;
     for (int i = 0; i < 8; ++i) dx0_dz[i] = 0.0;
   }
-  // observation y = h(x) = x[0]; gradient e0; zero second derivative
-  MMD_HD static double obs(const double* x) { return x[0]; }
-  MMD_HD static void obs_grad(const double* x, double* dh) { dh[0] = 1.0; dh[1] = 0.0; }
-  MMD_HD static void obs_hess_vec(const double* x, const double* d, double* out) { out[0] = 0.0; out[1] = 0.0; }
-  static constexpr bool OBS_LINEAR = true;
-
-  static constexpr bool JV_CONST = true;  // d f / d v independent of the state
-
-  // per-thread constants of the step map: every parameter-only sub-expression of the generated code,
-  // so no division / power / parameter product is left inside the time-stepping loops
-  struct Coef {
-    double z[Z];
-    double sd;
-    double ks[13];   // step
-    double kd[4];   // derivatives (jac_x, jac_v, jac_z, hess_contract)
-  };
-  MMD_HD static void make_coef_step(const double* z, double sd, Coef& c) {
-    for (int i = 0; i < Z; ++i) c.z[i] = z[i];
-    c.sd = sd;
-    const double sigma = z[0]; const double epsilon = z[1]; const double gamma = z[2]; const double beta = z[3]; (void)sigma; (void)epsilon; (void)gamma; (void)beta;
-    c.ks[0] = gamma;
-    c.ks[1] = beta;
-    c.ks[2] = -1/epsilon;
-    c.ks[3] = (1.0/(epsilon*epsilon));
-    c.ks[4] = (1.0/2.0)*(sd*sd*sd*sd);
-    c.ks[5] = (sd*sd)/epsilon;
-    c.ks[6] = -1.0/2.0*(sd*sd*sd)*sigma/epsilon;
-    c.ks[7] = (sd*sd);
-    c.ks[8] = -gamma;
-    c.ks[9] = gamma/epsilon;
-    c.ks[10] = -beta;
-    c.ks[11] = sd*sigma;
-    c.ks[12] = -1.0/2.0*(sd*sd*sd)*sigma;
-  }
-  MMD_HD static void make_coef(const double* z, double sd, Coef& c) {
-    make_coef_step(z, sd, c);
-    const double sigma = z[0]; const double epsilon = z[1]; const double gamma = z[2]; const double beta = z[3]; (void)sigma; (void)epsilon; (void)gamma; (void)beta;
-    c.kd[0] = (1.0/(epsilon*epsilon));
-    c.kd[1] = (1.0/(epsilon));
-    c.kd[2] = (1.0/2.0)*(sd*sd*sd*sd)*(1 - gamma/epsilon);
-    c.kd[3] = (1.0/(epsilon*epsilon*epsilon));
-  }
-
-  MMD_HD static void step(const Coef& c, const double* x, const double* v, double* xn) {
-    const double x0 = x[0]; const double x1 = x[1];
-    const double v0 = v[0]; const double v1 = v[1];
-    (void)x0; (void)x1; (void)v0; (void)v1;
-    const double sigma = c.z[0]; const double epsilon = c.z[1]; const double gamma = c.z[2]; const double beta = c.z[3]; const double sd = c.sd;
-    (void)sigma; (void)epsilon; (void)gamma; (void)beta; (void)sd;
-    const double ks0 = c.ks[0];
-    const double ks1 = c.ks[1];
-    const double ks2 = c.ks[2];
-    const double ks3 = c.ks[3];
-    const double ks4 = c.ks[4];
-    const double ks5 = c.ks[5];
-    const double ks6 = c.ks[6];
-    const double ks7 = c.ks[7];
-    const double ks8 = c.ks[8];
-    const double ks9 = c.ks[9];
-    const double ks10 = c.ks[10];
-    const double ks11 = c.ks[11];
-    const double ks12 = c.ks[12];
-    const double t0 = (x0*x0*x0) - x0 + x1;
-    const double t1 = v0 + (1.0/3.0)*1.7320508075688772*v1;
-    const double t2 = ks0*x0 + ks1 - x1;
-    xn[0] = ks4*(ks2*t2 + ks3*t0*(3*(x0*x0) - 1)) - ks5*t0 + ks6*t1 + x0;
-    xn[1] = ks11*v0 + ks12*t1 + ks4*(ks10 + ks8*x0 - ks9*t0 + x1) + ks7*t2 + x1;
-  }
-
-  MMD_HD static void jac_x(const Coef& c, const double* x, const double* v, double* F) {
-    const double x0 = x[0]; const double x1 = x[1];
-    const double v0 = v[0]; const double v1 = v[1];
-    (void)x0; (void)x1; (void)v0; (void)v1;
-    const double sigma = c.z[0]; const double epsilon = c.z[1]; const double gamma = c.z[2]; const double beta = c.z[3]; const double sd = c.sd;
-    (void)sigma; (void)epsilon; (void)gamma; (void)beta; (void)sd;
-    const double kd0 = c.kd[0];
-    const double kd1 = c.kd[1];
-    const double kd2 = c.kd[2];
-    const double t0 = (sd*sd);
-    const double t1 = 3*(x0*x0) - 1;
-    const double t2 = kd1*t1;
-    const double t3 = -t1;
-    const double t4 = (1.0/2.0)*t0;
-    F[0] = -1.0/2.0*(sd*sd*sd*sd)*(gamma*kd1 - kd0*(t3*t3) + 6*kd0*x0*(-(x0*x0*x0) + x0 - x1)) - t0*t2 + 1;
-    F[1] = -t0*(kd1 + t4*(kd0*t3 - kd1));
-    F[2] = gamma*t0*(-t4*(t2 + 1) + 1);
-    F[3] = kd2 - t0 + 1;
-  }
-
-  MMD_HD static void jac_v(const Coef& c, const double* x, const double* v, double* B) {
-    const double x0 = x[0]; const double x1 = x[1];
-    const double v0 = v[0]; const double v1 = v[1];
-    (void)x0; (void)x1; (void)v0; (void)v1;
-    const double sigma = c.z[0]; const double epsilon = c.z[1]; const double gamma = c.z[2]; const double beta = c.z[3]; const double sd = c.sd;
-    (void)sigma; (void)epsilon; (void)gamma; (void)beta; (void)sd;
-    const double kd1 = c.kd[1];
-    const double t0 = (sd*sd*sd)*sigma;
-    const double t1 = kd1*t0;
-    const double t2 = (1.0/6.0)*1.7320508075688772;
-    B[0] = -1.0/2.0*t1;
-    B[1] = -t1*t2;
-    B[2] = sd*sigma*(1 - 1.0/2.0*(sd*sd));
-    B[3] = -t0*t2;
-  }
-
-  MMD_HD static void jac_z(const Coef& c, const double* x, const double* v, double* G) {
-    const double x0 = x[0]; const double x1 = x[1];
-    const double v0 = v[0]; const double v1 = v[1];
-    (void)x0; (void)x1; (void)v0; (void)v1;
-    const double sigma = c.z[0]; const double epsilon = c.z[1]; const double gamma = c.z[2]; const double beta = c.z[3]; const double sd = c.sd;
-    (void)sigma; (void)epsilon; (void)gamma; (void)beta; (void)sd;
-    const double kd0 = c.kd[0];
-    const double kd1 = c.kd[1];
-    const double kd3 = c.kd[3];
-    const double t0 = 1.7320508075688772*v1;
-    const double t1 = (1.0/2.0)*kd1;
-    const double t2 = (sd*sd);
-    const double t3 = -x0;
-    const double t4 = t3 + (x0*x0*x0) + x1;
-    const double t5 = kd0*t4;
-    const double t6 = (1.0/6.0)*t0 + (1.0/2.0)*v0;
-    const double t7 = (1.0/2.0)*t2;
-    const double t8 = (sd*sd*sd*sd);
-    const double t9 = t1*t8;
-    G[0] = -(sd*sd*sd)*t1*((1.0/3.0)*t0 + v0);
-    G[1] = t2*(kd0*sd*sigma*t6 + t5 + t7*(kd0*(beta + gamma*x0 - x1) - 2*kd3*t4*(3*(x0*x0) - 1)));
-    G[2] = -t9*x0;
-    G[3] = -t9;
-    G[4] = sd*(-t2*t6 + v0);
-    G[5] = (1.0/2.0)*gamma*t5*t8;
-    G[6] = t2*(-t3 - t7*(kd1*t4 + x0));
-    G[7] = t2*(1 - t7);
-  }
-
-  MMD_HD static void hess_contract(const Coef& c, const double* x, const double* v, const double* Th, double* g) {
-    const double x0 = x[0]; const double x1 = x[1];
-    const double v0 = v[0]; const double v1 = v[1];
-    (void)x0; (void)x1; (void)v0; (void)v1;
-    const double sigma = c.z[0]; const double epsilon = c.z[1]; const double gamma = c.z[2]; const double beta = c.z[3]; const double sd = c.sd;
-    (void)sigma; (void)epsilon; (void)gamma; (void)beta; (void)sd;
-    const double Th0_0 = Th[0]; const double Th0_1 = Th[1];
-    const double Th1_0 = Th[2]; const double Th1_1 = Th[3];
-    const double Th2_0 = Th[4]; const double Th2_1 = Th[5];
-    const double Th3_0 = Th[6]; const double Th3_1 = Th[7];
-    const double Th4_0 = Th[8]; const double Th4_1 = Th[9];
-    const double Th5_0 = Th[10]; const double Th5_1 = Th[11];
-    const double Th6_0 = Th[12]; const double Th6_1 = Th[13];
-    const double Th7_0 = Th[14]; const double Th7_1 = Th[15];
-    const double kd0 = c.kd[0];
-    const double kd1 = c.kd[1];
-    const double kd3 = c.kd[3];
-    const double t0 = (sd*sd);
-    const double t1 = kd1*t0;
-    const double t2 = gamma*x0;
-    const double t3 = 3*t1;
-    const double t4 = (x0*x0);
-    const double t5 = 3*t4 - 1;
-    const double t6 = kd1*t5;
-    const double t7 = t0*(t6 + 1) - 2;
-    const double t8 = (1.0/2.0)*Th6_1;
-    const double t9 = 3*x0;
-    const double t10 = (x0*x0*x0);
-    const double t11 = t10 - x0 + x1;
-    const double t12 = t0*(-gamma + 12*kd1*t11*x0 + 2*kd1*(t5*t5)) - 6*t4 + 2;
-    const double t13 = (1.0/2.0)*Th5_0*kd0;
-    const double t14 = kd0*t0;
-    const double t15 = (1.0/2.0)*t0;
-    const double t16 = kd0*t15;
-    const double t17 = gamma*t16;
-    const double t18 = t0*(2*t6 + 1) - 2;
-    const double t19 = Th4_0*kd1;
-    const double t20 = t0 - 2;
-    const double t21 = (1.0/2.0)*sd;
-    const double t22 = 1.7320508075688772;
-    const double t23 = Th3_0*t22;
-    const double t24 = t22*v1 + 3*v0;
-    const double t25 = (1.0/6.0)*sd;
-    const double t26 = kd0*sigma;
-    const double t27 = (1.0/2.0)*kd0;
-    g[0] = t0*(3*Th0_0*kd1*(t1*(t11 + t5*t9) - 2*x0) - Th0_1*t2*t3 + 3*Th1_0*kd0*t0*x0 + (1.0/2.0)*Th5_1*gamma*kd0*t0*t5 - 1.0/2.0*Th6_0*t1 - t12*t13 - t7*t8);
-    g[1] = t0*(Th0_0*t14*t9 + Th5_1*t17 - t1*t8 - t13*t18);
-    g[2] = t21*(-Th4_1*t20 + Th5_0*kd0*sigma*t0 - t0*t19);
-    g[3] = (1.0/6.0)*(sd*sd*sd)*t22*(-Th4_1 + Th5_0*kd0*sigma - t19);
-    g[4] = t25*(-Th2_0*t3 - 3*Th2_1*t20 - Th3_1*t0*t22 + Th5_0*kd0*t0*t24 - t1*t23);
-    g[5] = t0*(-Th0_0*t12*t27 + Th0_1*t17*t5 - Th1_0*t18*t27 + Th1_1*t17 + Th2_0*t21*t26 + Th4_0*kd0*t24*t25 - 1.0/3.0*Th5_0*kd3*(sd*sigma*t24 + 3*t0*(beta - 3*t11*t6 + t2 - x1) + 6*t10 - 6*x0 + 6*x1) - Th5_1*gamma*kd3*t0*t11 + Th6_0*t16*x0 + Th7_0*t16 + t11*t14*t8 + t23*t25*t26);
-    g[6] = t15*(-Th0_0*t1 - Th0_1*t7 - Th1_1*t1 + Th5_0*kd0*t0*x0 + Th5_1*kd0*t0*t11);
-    g[7] = (sd*sd*sd*sd)*t13;
-  }
-
 };

@@ -240,55 +240,16 @@ FHN_HEADER = """  static constexpr int X = 2;   // dim_x   (fhn.py:10)
 """
 
 
-FHN_NB_HEADER = FHN_HEADER.replace(
-    "static constexpr int MODEL_ID = 0;", "static constexpr int MODEL_ID = 2;"
-).replace(
-    """  // z = generate_z(u) and dz/du (fhn.py:41-43): z = [exp u0, exp u1, exp u2, u3]
-  MMD_HD static void gen_z(const double* u, double* z, double* dzdu /* Z x Z */) {
-    z[0] = exp(u[0]); z[1] = exp(u[1]); z[2] = exp(u[2]); z[3] = u[3];
-    for (int i = 0; i < 16; ++i) dzdu[i] = 0.0;
-    dzdu[0] = z[0]; dzdu[5] = z[1]; dzdu[10] = z[2]; dzdu[15] = 1.0;
-  }""",
-    """  // z = generate_z(u) of FitzHugh-Nagumo_example.ipynb (cell 18):
-  //   [exp(.5 u0 - 1), exp(.5 u1 - 2), .5 u2 + 1, .5 u3 + 1]
-  MMD_HD static void gen_z(const double* u, double* z, double* dzdu /* Z x Z */) {
-    z[0] = exp(0.5 * u[0] - 1.0); z[1] = exp(0.5 * u[1] - 2.0); z[2] = 0.5 * u[2] + 1.0; z[3] = 0.5 * u[3] + 1.0;
-    for (int i = 0; i < 16; ++i) dzdu[i] = 0.0;
-    dzdu[0] = 0.5 * z[0]; dzdu[5] = 0.5 * z[1]; dzdu[10] = 0.5; dzdu[15] = 0.5;
-  }""",
-).replace(
-    "extra[0] = Gam[0] * z[0]; extra[1] = Gam[5] * z[1]; extra[2] = Gam[10] * z[2]; extra[3] = 0.0;",
-    "extra[0] = 0.25 * Gam[0] * z[0]; extra[1] = 0.25 * Gam[5] * z[1]; extra[2] = 0.0; extra[3] = 0.0;",
-).replace(
-    """  // x_0 = generate_x_0(z, v_0) = v_0 - [0, z3] (fhn.py:50-51); linear: d/dv_0 = I, d/dz = -e1 e3^T
-  MMD_HD static void gen_x0(const double* z, const double* v0, double* x0) {
-    x0[0] = v0[0]; x0[1] = v0[1] - z[3];
-  }""",
-    """  // x_0 = generate_x_0(z, v_0) = [-.5, -.5] + v_0 (notebook cell 18); d/dv_0 = I, d/dz = 0
-  MMD_HD static void gen_x0(const double* z, const double* v0, double* x0) {
-    x0[0] = v0[0] - 0.5; x0[1] = v0[1] - 0.5;
-  }""",
-).replace("    dx0_dz[7] = -1.0;\n", "")
-assert "dx0_dz[7]" not in FHN_NB_HEADER and "0.25 * Gam[0]" in FHN_NB_HEADER and "v0[0] - 0.5" in FHN_NB_HEADER
+# (the notebook prior parametrisation is a hand-written struct derived from FhnModel: csrc/mmd_model_fhn_notebook.cuh)
 
 
-def gen_fhn(notebook=False):
+def gen_fhn():
     from oracle.models import derive_fhn_step
 
     f, sy = derive_fhn_step(simplify=False)
     d = sy["delta"]
     sd = sp.symbols("sd", positive=True)  # sqrt(delta): keeps pow() out of the generated code
     f = f.subs(d, sd ** 2)
-    if notebook:
-        gen_model(
-            "FhnNotebookModel", "mmd_model_fhn_notebook.cuh", f, list(sy["x"]), list(sy["v"]), list(sy["z"]), "sd",
-            FHN_NB_HEADER,
-            "// FitzHugh-Nagumo model with the prior parametrisation of the reference's notebook\n"
-            "// (FitzHugh-Nagumo_example.ipynb cells 7-18): same strong-order-1.5 step as fhn.py, different\n"
-            "// generate_z / generate_x_0.  Used for the distributional known-answer test against the\n"
-            "// posterior table recorded in the notebook.",
-        )
-        return
     gen_model(
         "FhnModel", "mmd_model_fhn.cuh", f, list(sy["x"]), list(sy["v"]), list(sy["z"]), "sd", FHN_HEADER,
         "// FitzHugh-Nagumo hypoelliptic diffusion, strong-order-1.5 Taylor step (additive noise).\n"
@@ -417,5 +378,4 @@ def gen_sir():
 
 if __name__ == "__main__":
     gen_fhn()
-    gen_fhn(notebook=True)
     gen_sir()
