@@ -101,7 +101,12 @@ MMD_D void cp_async(unsigned sdst, const void* gsrc) {
 // once instead of each one being scheduled next to its use
 MMD_D double ldg_vol(const double* g) {
   double v;
+#if defined(MMD_KEEP_FACTORS)
+  // evict_last: the factors are re-read by every solver iteration while ~350 MB of streams pass through L2 in between
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;\n" : "=d"(v) : "l"(g), "l"(l2_policy_keep()));
+#else
   asm volatile("ld.global.f64 %0, [%1];\n" : "=d"(v) : "l"(g));
+#endif
   return v;
 }
 template <int N>
