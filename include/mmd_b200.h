@@ -160,6 +160,11 @@ void mmd_default_integrator_opts(mmd_integrator_opts* o);
 /* One ConstrainedLeapfrogIntegrator.step (n_inner_step = 1) of size `dt` (signed = dir * step_size)
  * for every chain.  Chains whose step fails keep their state; their status bits say why. */
 int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts);
+/* The same step with the B part split into `n_inner_step` inner steps of size dt / n_inner_step, each with its own
+ * projection and reverse check (Mici ConstrainedLeapfrogIntegrator(n_inner_step=...); the reference's
+ * --num-inner-h2-step, scripts/utils.py:132, 286).  A chain that fails in any inner step is left exactly where it
+ * was before the call.  n_inner_step = 1 is mmd_leapfrog_step. */
+int mmd_leapfrog_step_inner(mmd_handle h, double dt, int n_inner_step, const mmd_integrator_opts* opts);
 /* One full Markov transition for every chain, entirely on device: IndependentMomentumTransition
  * (Philox draw keyed by (seed, iter) + cotangent projection), `n_leapfrog` constrained leapfrog
  * steps of size dt, Metropolis accept on the Hamiltonian error (integrator errors reject), then

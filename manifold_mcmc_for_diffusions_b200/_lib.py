@@ -88,6 +88,7 @@ SIGNATURES = {
     "mmd_get_factor": (C.c_int, [_H, C.c_char_p, _dp, _ip]),
     "mmd_default_integrator_opts": (None, [C.POINTER(MmdIntegratorOpts)]),
     "mmd_leapfrog_step": (C.c_int, [_H, C.c_double, C.POINTER(MmdIntegratorOpts)]),
+    "mmd_leapfrog_step_inner": (C.c_int, [_H, C.c_double, C.c_int, C.POINTER(MmdIntegratorOpts)]),
     "mmd_get_step_info": (C.c_int, [_H, _ip, _ip, _ip, _dp]),
     "mmd_project_quasi_newton": (
         C.c_int,

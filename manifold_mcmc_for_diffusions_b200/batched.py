@@ -377,8 +377,13 @@ class BatchedChains:
         return out
 
     # ---- integrator --------------------------------------------------------------------
-    def leapfrog_step(self, dt):
-        check(self._L.mmd_leapfrog_step(self._h, float(dt), C.byref(self.opts)))
+    def leapfrog_step(self, dt, n_inner_step=1):
+        """One ConstrainedLeapfrogIntegrator.step of every chain; n_inner_step > 1 splits the h2 flow + projection
+        into inner steps of size dt / n_inner_step (Mici's n_inner_step, scripts/utils.py:132)."""
+        if n_inner_step == 1:
+            check(self._L.mmd_leapfrog_step(self._h, float(dt), C.byref(self.opts)))
+        else:
+            check(self._L.mmd_leapfrog_step_inner(self._h, float(dt), int(n_inner_step), C.byref(self.opts)))
 
     def hmc_transition(self, dt, n_leapfrog, seed, it, switch_partition=True):
         """Momentum refresh + static constrained trajectory + Metropolis accept (+ partition switch)."""

@@ -750,6 +750,68 @@ int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts) 
   return leapfrog_impl(h, dt, opts, true);
 }
 
+// ConstrainedLeapfrogIntegrator.step with n_inner_step > 1 (Mici 0.1.10 _step_b; exposed by the
+// reference as --num-inner-h2-step, scripts/utils.py:132, 286):
+//   A(dt/2);  n times [ h2_flow(dt/n) + projection onto the manifold from the previous inner point, cotangent
+//   projection at the new point, reverse check over dt/n ];  A(dt/2)
+// driven from the host over the per-phase kernels.  Every inner step commits into the other state slot, so the
+// start-of-step q, p are snapshotted first; chains that fail in any inner step are rolled back to the snapshot and
+// re-linearised there -- like Mici, whose step works on a copy of the state and raises.
+int mmd_leapfrog_step_inner(mmd_handle h, double dt, int n_inner_step, const mmd_integrator_opts* opts) {
+  MMD_GUARD(h);
+  if (n_inner_step < 1) FAIL("n_inner_step must be >= 1");
+  if (n_inner_step == 1) return leapfrog_impl(h, dt, opts, true);
+  if (h->W.use_dt_chain) FAIL("n_inner_step > 1 is not available with per-chain step sizes");
+  mmd_integrator_opts o;
+  if (opts) o = *opts; else mmd_default_integrator_opts(&o);
+  if (o.solver != MMD_SOLVER_QUASI_NEWTON && o.solver != MMD_SOLVER_NEWTON) FAIL("unknown projection solver");
+  if (!h->lin_valid) {
+    int rc0 = mmd_linearize(h, 1);
+    if (rc0) return rc0;
+  }
+  const size_t nc = (size_t)h->d.n_tiles * h->d.cpb;
+  if (!h->inner_q) {
+    int rc0 = dalloc(h, &h->inner_q, (size_t)h->d.qsize);
+    rc0 |= dalloc(h, &h->inner_p, (size_t)h->d.qsize);
+    rc0 |= dalloc(h, &h->inner_cnt, nc);
+    rc0 |= dalloc(h, &h->inner_status, nc);
+    if (rc0) return -2;
+  }
+  CK(cudaMemsetAsync(h->W.status, 0, nc * sizeof(int), h->stream));
+  k_snapshot_qp<<<1184, 256, 0, h->stream>>>(h->d, h->S, h->inner_q, h->inner_p);
+  h->launches++;
+  const StepCoef sc = step_coef(h->d, dt);                       // half kicks over the whole step
+  const StepCoef si = step_coef(h->d, dt / n_inner_step);        // flows / momentum coefficient of one inner step
+  const int grid = (h->d.n_chains + 127) / 128;
+  int rc = DISPATCH(h, project(h, 0, PSEL_CUR, PSEL_WORK, sc.half_dt, sc.qcoef, si.fwd)); if (rc) return rc;
+  for (int i = 0; i < n_inner_step; ++i) {
+    const bool last = i == n_inner_step - 1;
+    rc = DISPATCH(h, qn(h, 0, si.mom_coef, &o)); if (rc) return rc;
+    rc = DISPATCH(h, point(h, 1, last ? 1 : 0)); if (rc) return rc;           // dh1_dpos only where it is needed
+    rc = DISPATCH(h, project(h, 1, PSEL_OTHER, PSEL_OTHER, 0.0, 0.0, si.back)); if (rc) return rc;
+    rc = DISPATCH(h, qn(h, 1, 0.0, &o)); if (rc) return rc;
+    if (last) {
+      rc = DISPATCH(h, project(h, 1, PSEL_OTHER, PSEL_OTHER, sc.half_dt, sc.qcoef, NOFLOW)); if (rc) return rc;
+    }
+    k_commit<<<grid, 128, 0, h->stream>>>(h->d, h->S, h->W, o.reverse_check_tol, last ? h->n_ok : h->inner_cnt);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (!last) {
+      // the committed point is the new "previous" point: flow on from it (its momentum is already tangent)
+      rc = DISPATCH(h, project(h, 0, PSEL_CUR, PSEL_WORK, 0.0, 0.0, si.fwd)); if (rc) return rc;
+    }
+  }
+  // roll back the chains that failed, and give them back the linearisation of the point they are left at
+  k_restore_qp<<<1184, 256, 0, h->stream>>>(h->d, h->S, h->W, h->inner_q, h->inner_p);
+  k_status_swap<<<grid, 128, 0, h->stream>>>(h->d, h->W, h->inner_status, 1);
+  h->launches += 2;
+  rc = DISPATCH(h, point(h, 0, 1)); if (rc) return rc;
+  k_status_swap<<<grid, 128, 0, h->stream>>>(h->d, h->W, h->inner_status, 0);
+  h->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int mmd_transition_begin(mmd_handle h, uint64_t seed, uint64_t iter) {
   MMD_GUARD(h);
   int rc = mmd_linearize(h, 1); if (rc) return rc;               // also clears status

@@ -105,6 +105,10 @@ struct mmd_handle_s {
   int *ht_it, *ht_mask;
   std::vector<double*> aux;   // auxiliary q-like arrays of the host-driven tree builder
   int* maskbuf;               // [chains] device copy of the caller's chain mask
+  // steps with n_inner_step > 1 (allocated on first use): snapshot of q, p; scratch counter; saved status words
+  double *inner_q, *inner_p;
+  long long* inner_cnt;
+  int* inner_status;
 };
 
 

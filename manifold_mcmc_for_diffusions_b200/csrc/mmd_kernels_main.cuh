@@ -2212,6 +2212,42 @@ static __global__ void k_restore(Dims d, Slots S, const int* __restrict__ accept
   }
 }
 // snapshot of the current position (tile layout) at the start of a transition
+// Snapshot / roll-back of position AND momentum of the live slot (steps with n_inner_step > 1: a chain that fails in a
+// later inner step must be left exactly where it was before the whole step, mici ConstrainedLeapfrogIntegrator.step
+// works on a copy).  restore: chains with a non-zero status only.
+static __global__ void k_snapshot_qp(Dims d, Slots S, double* __restrict__ qs, double* __restrict__ ps) {
+  const long long n = d.qsize;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int chain = chain_of_qlike_index(d, e);
+    const long long o = (long long)S.cur[chain < d.n_tiles * d.cpb ? chain : 0] * S.s_q + e;
+    qs[e] = S.q[o];
+    ps[e] = S.p[o];
+  }
+}
+static __global__ void k_restore_qp(Dims d, Slots S, Work W, const double* __restrict__ qs, const double* __restrict__ ps) {
+  const long long n = d.qsize;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int chain = chain_of_qlike_index(d, e);
+    if (chain < d.n_chains && W.status[chain] != 0) {
+      const long long o = (long long)S.cur[chain] * S.s_q + e;
+      S.q[o] = qs[e];
+      S.p[o] = ps[e];
+    }
+  }
+}
+// park the chains without an error and clear the error of the others (so that the next k_point re-linearises exactly
+// the rolled-back chains), and undo it afterwards
+static __global__ void k_status_swap(Dims d, Work W, int* __restrict__ saved, int begin) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.n_chains) return;
+  if (begin) {
+    const int st = W.status[c];
+    saved[c] = st;
+    W.status[c] = st != 0 ? 0 : ST_INACTIVE;
+  } else {
+    W.status[c] = saved[c];
+  }
+}
 static __global__ void k_snapshot(Dims d, Slots S, double* __restrict__ qsave) {
   const long long n = d.qsize;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;

@@ -743,9 +743,10 @@ def leapfrog_step(
     divergence_tol=1e10,
     max_iters=50,
     reverse_check_tol=2e-8,
+    n_inner_step=1,
 ):
-    """One ConstrainedLeapfrogIntegrator.step with n_inner_step=1 (Mici 0.1.10) using
-    the reference's projection solvers (mici_extensions.py:1323-1476).
+    """One ConstrainedLeapfrogIntegrator.step (Mici 0.1.10, SURVEY.md 3.3: _step_a, n_inner_step x _step_b, _step_a)
+    using the reference's projection solvers (mici_extensions.py:1323-1476).
 
     Returns (q, p, pt_new, info).  Raises ConvergenceError / NonReversibleStepError like Mici."""
     q, p, x_obs_seq = _t(q), _t(p), _t(x_obs_seq)
@@ -774,20 +775,26 @@ def leapfrog_step(
     # A(dt/2)
     p = p - 0.5 * dt * system.dh1_dpos(q, pt)
     p = system.project_onto_cotangent_space(p, pt)
-    # B(dt)
-    q_prev, pt_prev = q, pt
-    q_, p_ = system.h2_flow(q, p, dt)
-    q_new, mu, n_fwd = project(q_, q_prev, pt_prev, dt)
-    cos_or_one = onp.cos(dt) if system.use_gaussian_splitting else 1.0
-    p = p_ - cos_or_one * mu  # state.mom -= dh2_flow_mom_dmom @ mu  (:1391, :1233-1238)
-    pt_new = system.point(q_new, x_obs_seq, partition)
-    p = system.project_onto_cotangent_space(p, pt_new)
-    q_b, _ = system.h2_flow(q_new, p, -dt)
-    q_back, _, n_back = project(q_b, q_new, pt_new, -dt)
-    rev = float(torch.max(torch.abs(q_back - q_prev)))
-    info.update(n_fwd=n_fwd, n_back=n_back, rev_diff=rev)
-    if rev > reverse_check_tol:
-        raise NonReversibleStepError(f"reverse error {rev:.2e}")
+    # B(dt): n_inner_step inner steps, each with its own projection and reverse check
+    dt_i = dt / n_inner_step
+    n_fwd_all, n_back_all, rev = [], [], 0.0
+    for _ in range(n_inner_step):
+        q_prev, pt_prev = q, pt
+        q_, p_ = system.h2_flow(q, p, dt_i)
+        q_new, mu, n_fwd = project(q_, q_prev, pt_prev, dt_i)
+        cos_or_one = onp.cos(dt_i) if system.use_gaussian_splitting else 1.0
+        p = p_ - cos_or_one * mu  # state.mom -= dh2_flow_mom_dmom @ mu  (:1391, :1233-1238)
+        pt_new = system.point(q_new, x_obs_seq, partition)
+        p = system.project_onto_cotangent_space(p, pt_new)
+        q_b, _ = system.h2_flow(q_new, p, -dt_i)
+        q_back, _, n_back = project(q_b, q_new, pt_new, -dt_i)
+        rev = float(torch.max(torch.abs(q_back - q_prev)))
+        n_fwd_all.append(n_fwd)
+        n_back_all.append(n_back)
+        info.update(n_fwd=n_fwd, n_back=n_back, rev_diff=rev, n_fwd_inner=n_fwd_all, n_back_inner=n_back_all)
+        if rev > reverse_check_tol:
+            raise NonReversibleStepError(f"reverse error {rev:.2e}")
+        q, pt = q_new, pt_new
     # A(dt/2)
     p = p - 0.5 * dt * system.dh1_dpos(q_new, pt_new)
     p = system.project_onto_cotangent_space(p, pt_new)
