@@ -157,6 +157,16 @@ typedef struct {
 } mmd_integrator_opts;
 void mmd_default_integrator_opts(mmd_integrator_opts* o);
 
+/* Run-time parameters of the model's generators (the reference passes generate_z / generate_x_0 as Python callables,
+ * mici_extensions.py:211-240; here a parametrised family per model, so priors change without recompiling).
+ * FHN (22 values): z_i = a_i u_i + b_i, exponentiated where m_i != 0, x_0 = v_0 + c + E z, laid out
+ * [a (4) | b (4) | m (4) | c (2) | E (2 x 4 row-major)]; default = sde/example_models/fhn.py:41-51; the model id
+ * MMD_MODEL_FHN_NOTEBOOK is the same model created with the notebook's values.  SIR has none (0 values).
+ * Set them right after mmd_create, before the first state is loaded. */
+int mmd_num_generator_params(mmd_handle h);
+int mmd_get_generator_params(mmd_handle h, double* params);
+int mmd_set_generator_params(mmd_handle h, const double* params, int n);
+
 /* One ConstrainedLeapfrogIntegrator.step (n_inner_step = 1) of size `dt` (signed = dir * step_size)
  * for every chain.  Chains whose step fails keep their state; their status bits say why. */
 int mmd_leapfrog_step(mmd_handle h, double dt, const mmd_integrator_opts* opts);

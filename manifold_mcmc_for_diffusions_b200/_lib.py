@@ -87,6 +87,9 @@ SIGNATURES = {
     "mmd_sample_momentum": (C.c_int, [_H, C.c_uint64, C.c_uint64]),
     "mmd_get_factor": (C.c_int, [_H, C.c_char_p, _dp, _ip]),
     "mmd_default_integrator_opts": (None, [C.POINTER(MmdIntegratorOpts)]),
+    "mmd_num_generator_params": (C.c_int, [_H]),
+    "mmd_get_generator_params": (C.c_int, [_H, _dp]),
+    "mmd_set_generator_params": (C.c_int, [_H, _dp, C.c_int]),
     "mmd_leapfrog_step": (C.c_int, [_H, C.c_double, C.POINTER(MmdIntegratorOpts)]),
     "mmd_leapfrog_step_inner": (C.c_int, [_H, C.c_double, C.c_int, C.POINTER(MmdIntegratorOpts)]),
     "mmd_get_step_info": (C.c_int, [_H, _ip, _ip, _ip, _dp]),

@@ -42,7 +42,10 @@ class BatchedChains:
         sigma_fixed=0.0,
         use_gaussian_splitting=False,
         device=0,
+        generator_params=None,
     ):
+        """generator_params: run-time parameters of the model's generate_z / generate_x_0 (FHN: the 22 values of
+        `example_models.fhn.generator_params(...)`; None keeps the reference's generators)."""
         self._L = lib()
         self._y = _c(np.asarray(y_seq).reshape(-1))
         cfg = MmdConfig(
@@ -71,6 +74,19 @@ class BatchedChains:
         self.num_obs = cfg.num_obs
         self.opts = MmdIntegratorOpts()
         self._L.mmd_default_integrator_opts(C.byref(self.opts))
+        if generator_params is not None:
+            self.set_generator_params(generator_params)
+
+    # ---- run-time generator parameters (priors) ---------------------------------------------
+    def set_generator_params(self, params):
+        params = _c(np.asarray(params).reshape(-1))
+        check(self._L.mmd_set_generator_params(self._h, _dp(params), int(params.size)))
+
+    def get_generator_params(self):
+        out = np.empty(max(self._L.mmd_num_generator_params(self._h), 0))
+        if out.size:
+            check(self._L.mmd_get_generator_params(self._h, _dp(out)))
+        return out
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:

@@ -2,6 +2,7 @@
 // on a machine without a GPU (tests/test_model_functor_host.py).  Not part of the product path.
 #include "mmd_model_fhn.cuh"
 #include "mmd_philox.cuh"
+#define MMD_GEN_MAX_HOST 24
 
 namespace {
 FhnModel::Coef coef(const double* z, double sd) {
@@ -19,7 +20,18 @@ void fhn_jac_z(const double* z, double sd, const double* x, const double* v, dou
 void fhn_hess_contract(const double* z, double sd, const double* x, const double* v, const double* Th, double* g) {
   FhnModel::hess_contract(coef(z, sd), x, v, Th, g);
 }
-void fhn_gen_z(const double* u, double* z, double* dzdu) { FhnModel::gen_z(u, z, dzdu); }
+void fhn_gen_z(const double* u, double* z, double* dzdu) {
+  double gp[MMD_GEN_MAX_HOST];
+  FhnModel::default_gen(gp);
+  FhnModel::gen_z(gp, u, z, dzdu);
+}
+void fhn_gen_all(const double* gp, const double* u, const double* v0, const double* Gam, double* z, double* dzdu, double* extra, double* x0,
+                 double* dx0_dv0, double* dx0_dz) {
+  FhnModel::gen_z(gp, u, z, dzdu);
+  FhnModel::gen_z_second(gp, u, z, Gam, extra);
+  FhnModel::gen_x0(gp, z, v0, x0);
+  FhnModel::gen_x0_jac(gp, z, dx0_dv0, dx0_dz);
+}
 void philox_normal_pair(unsigned long long seed, unsigned long long offset, unsigned long long idx, double* a, double* b) {
   mmd::philox_normal_pair(seed, offset, idx, a, b);
 }
@@ -41,6 +53,6 @@ void sir_jac_z(const double* z, double sd, const double* x, const double* v, dou
 void sir_hess_contract(const double* z, double sd, const double* x, const double* v, const double* Th, double* g) {
   SirModel::hess_contract(scoef(z, sd), x, v, Th, g);
 }
-void sir_gen_z(const double* u, double* z, double* dzdu) { SirModel::gen_z(u, z, dzdu); }
-void sir_gen_z_second(const double* u, const double* z, const double* Gam, double* extra) { SirModel::gen_z_second(u, z, Gam, extra); }
+void sir_gen_z(const double* u, double* z, double* dzdu) { SirModel::gen_z(nullptr, u, z, dzdu); }
+void sir_gen_z_second(const double* u, const double* z, const double* Gam, double* extra) { SirModel::gen_z_second(nullptr, u, z, Gam, extra); }
 }

@@ -169,15 +169,15 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     FAIL("no CUDA device: this library has no CPU path");
-  const mmd_ops* ops = cfg->model == MMD_MODEL_FHN ? mmd_ops_fhn()
-                       : cfg->model == MMD_MODEL_SIR ? mmd_ops_sir()
-                       : cfg->model == MMD_MODEL_FHN_NOTEBOOK ? mmd_ops_fhn_notebook() : nullptr;
+  // MMD_MODEL_FHN_NOTEBOOK is the FHN model with the notebook's generator parameters (set below)
+  const bool is_fhn = cfg->model == MMD_MODEL_FHN || cfg->model == MMD_MODEL_FHN_NOTEBOOK;
+  const mmd_ops* ops = is_fhn ? mmd_ops_fhn() : cfg->model == MMD_MODEL_SIR ? mmd_ops_sir() : nullptr;
   if (!ops) FAIL("unknown model id");
   {
     // the smallest instantiation that holds the problem's blocks (fewer rows = less per-thread state)
     const int T_ = cfg->num_obs, R_ = cfg->num_obs_per_subseq;
     const int nz_ = cfg->noise != MMD_NOISE_NONE;
-    if (cfg->model == MMD_MODEL_FHN && R_ > 0 && R_ < T_ && !getenv("MMD_FHN_WIDE")) {
+    if (is_fhn && R_ > 0 && R_ < T_ && !getenv("MMD_FHN_WIDE")) {
       const mmd_ops* small = mmd_ops_fhn_r5();
       const mmd_ops* wide = mmd_ops_fhn_r16();
       if (R_ - 1 + nz_ + small->X <= small->nrmax && R_ <= small->rmax) ops = small;
@@ -214,6 +214,14 @@ int mmd_create(const mmd_config* cfg, mmd_handle* out) {
 
   mmd_handle h = new mmd_handle_s();
   memset(&h->d, 0, sizeof(Dims));
+  static_assert(MMD_GEN_MAX >= 22, "generator parameter block too small");
+  ops->default_gen(h->d.gen);
+  if (cfg->model == MMD_MODEL_FHN_NOTEBOOK) {
+    // FitzHugh-Nagumo_example.ipynb cell 18: z = [exp(.5 u0 - 1), exp(.5 u1 - 2), .5 u2 + 1, .5 u3 + 1], x_0 = v_0 - .5
+    const double nb[22] = {0.5, 0.5, 0.5, 0.5, -1.0, -2.0, 1.0, 1.0, 1.0, 1.0, 0.0, 0.0, -0.5, -0.5,
+                           0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 22; ++i) h->d.gen[i] = nb[i];
+  }
   h->model = cfg->model;
   h->device = cfg->device;
   h->ops = ops;
@@ -976,6 +984,26 @@ int mmd_set_inactive(mmd_handle h, const int* mask, int clear_errors) {
   k_set_inactive<<<(h->d.n_chains + 127) / 128, 128, 0, h->stream>>>(h->d, h->W, m, clear_errors);
   h->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+
+int mmd_num_generator_params(mmd_handle h) { return h ? h->ops->ngen : -1; }
+
+int mmd_get_generator_params(mmd_handle h, double* params) {
+  MMD_GUARD(h);
+  if (!params) FAIL("null argument");
+  for (int i = 0; i < h->ops->ngen; ++i) params[i] = h->d.gen[i];
+  return 0;
+}
+
+int mmd_set_generator_params(mmd_handle h, const double* params, int n) {
+  MMD_GUARD(h);
+  if (!params) FAIL("null argument");
+  if (n != h->ops->ngen) FAIL("wrong number of generator parameters for this model");
+  for (int i = 0; i < n; ++i)
+    if (!(params[i] == params[i])) FAIL("generator parameter is NaN");
+  for (int i = 0; i < n; ++i) h->d.gen[i] = params[i];
+  h->lin_valid = false;   // everything cached at the position depends on the generators
   return 0;
 }
 

@@ -76,7 +76,7 @@ k_hmc_target(Dims d, const double* __restrict__ y, const double* __restrict__ qT
     v0[j] = qc[(long long)(U + j) * n];
     sq = fma(v0[j], v0[j], sq);
   }
-  M::gen_x0(P.z, v0, x);
+  M::gen_x0(d.gen, P.z, v0, x);
   const double* vq = qc + (long long)d.off_v * n;
   double* xc = xs + c;
   double acc = 0.0;
@@ -147,7 +147,7 @@ k_hmc_target(Dims d, const double* __restrict__ y, const double* __restrict__ qT
   }
   {
     double dx0_dv0[X * V0], dx0_dz[X * Z], t0[V0], tz[Z];
-    M::gen_x0_jac(P.z, dx0_dv0, dx0_dz);
+    M::gen_x0_jac(d.gen, P.z, dx0_dv0, dx0_dz);
     mtv<X, V0>(dx0_dv0, lam, t0);
     mtv<X, Z>(dx0_dz, lam, tz);
 #pragma unroll

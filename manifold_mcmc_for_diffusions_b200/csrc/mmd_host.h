@@ -137,6 +137,8 @@ inline mmd::StepCoef step_coef(const mmd::Dims& d, double dt) { return mmd::make
 // model dimensions and the launcher table the C ABI dispatches through
 struct mmd_ops {
   int X, V, Z, V0, Y, nrmax, rmax;
+  int ngen;                        // number of run-time generator parameters of the model (0: none)
+  void (*default_gen)(double*);    // the reference's generators (fills ngen values)
   int (*point)(mmd_handle, int, int);
   int (*constr)(mmd_handle);
   int (*project)(mmd_handle, int, int, int, double, double, mmd::FlowCoef);
@@ -158,4 +160,3 @@ const mmd_ops* mmd_ops_fhn();
 const mmd_ops* mmd_ops_fhn_r5();   // blocks of <= 5 observations / 6 constraint rows
 const mmd_ops* mmd_ops_fhn_r16();  // blocks of <= 14 observations / 16 constraint rows
 const mmd_ops* mmd_ops_sir();
-const mmd_ops* mmd_ops_fhn_notebook();

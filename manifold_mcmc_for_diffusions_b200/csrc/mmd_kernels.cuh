@@ -59,7 +59,10 @@ namespace mmd {
 // ------------------------------------------------------------------------------------------
 // problem description (host fills, passed by value to kernels)
 // ------------------------------------------------------------------------------------------
+// run-time parameters of the model's generators (generate_z, generate_x_0): see the model functor for their meaning
+#define MMD_GEN_MAX 24
 struct Dims {
+  double gen[MMD_GEN_MAX];
   int T, S, R;        // num_obs, num_steps_per_obs, num_obs_per_subseq  (mici_extensions.py:317-351)
   int U;              // dim_u
   int X, V;           // dim_x, dim_v of the model

@@ -94,7 +94,7 @@ MMD_PHASE void dev_point(const Dims& d, const Slots& S, const Work& W, const dou
 
   if (has_blk && !skip) {
     double dx0_dv0[X * M::V0], dx0_dz[X * Z];
-    M::gen_x0_jac(P.z, dx0_dv0, dx0_dz);
+    M::gen_x0_jac(d.gen, P.z, dx0_dv0, dx0_dz);
     // ---------------- interval sweeps: trajectory, compressed Jacobian, interval summaries
     double x[X];
     {
@@ -357,7 +357,7 @@ MMD_PHASE void dev_point(const Dims& d, const Slots& S, const Work& W, const dou
   for (int j = 0; j < UMAX; ++j) gu[j] = 0.0;
   if (has_blk && !skip) {
     double dx0_dv0[X * M::V0], dx0_dz[X * Z];
-    M::gen_x0_jac(P.z, dx0_dv0, dx0_dz);
+    M::gen_x0_jac(d.gen, P.z, dx0_dv0, dx0_dz);
     const int nr = B.nrows;
     // rows: compile-time bound and full unrolling for the small blocks (FHN), run-time bound for the large (SIR)
     constexpr bool STATIC_ROWS = NRMAX <= 8;
@@ -762,7 +762,7 @@ MMD_PHASE void dev_point(const Dims& d, const Slots& S, const Work& W, const dou
     for (int m = 0; m < Z; ++m)
 #pragma unroll
       for (int j = 0; j < Z; ++j) GamZ[m * Z + j] = Gam[m * UMAX + j];
-    M::gen_z_second(P.u, P.z, GamZ, extra);
+    M::gen_z_second(d.gen, P.u, P.z, GamZ, extra);
 #pragma unroll
     for (int j = 0; j < Z; ++j) {
       double s = extra[j];
@@ -878,8 +878,8 @@ MMD_PHASE void dev_project(const Dims& d, const Slots& S, const Work& W, int par
     double u[UMAX], z[Z], dzdu[Z * Z];
 #pragma unroll
     for (int j = 0; j < UMAX; ++j) u[j] = (j < U) ? q.head[j * cpb] : 0.0;
-    M::gen_z(u, z, dzdu);
-    M::gen_x0_jac(z, dx0_dv0, dx0_dz);
+    M::gen_z(d.gen, u, z, dzdu);
+    M::gen_x0_jac(d.gen, z, dx0_dv0, dx0_dz);
     sig = sigma_of<M>(d, u);
     // head of the kicked momentum (u and v_0 components), kept in registers
 #pragma unroll
@@ -1111,7 +1111,7 @@ MMD_D void newton_solve_block(const Dims& d, const Blk& B, bool work, const Chai
     double* Qc = tp(W.Qk, d.rmax * X * X, t);    // cross sums  sum_t K_t(q) K_t(q_lin)^T
     double* Ztc = tp(W.Zt, d.rmax * X * Z, t);
     double dx0_dv0[X * M::V0], dx0_dz[X * Z];
-    M::gen_x0_jac(P.z, dx0_dv0, dx0_dz);
+    M::gen_x0_jac(d.gen, P.z, dx0_dv0, dx0_dz);
     // ---- backward sweeps per interval at the current iterate
     for (int k = 0; k < B.n; ++k) {
       double al[X];
@@ -1453,8 +1453,8 @@ MMD_PHASE void dev_qn(const Dims& d, const Slots& S, const Work& W, const double
     double u[UMAX], z[Z], dzdu[Z * Z], dx0_dz[X * Z];
 #pragma unroll
     for (int j = 0; j < UMAX; ++j) u[j] = (j < U) ? qlin.head[j * cpb] : 0.0;
-    M::gen_z(u, z, dzdu);
-    M::gen_x0_jac(z, dx0_dv0, dx0_dz);
+    M::gen_z(d.gen, u, z, dzdu);
+    M::gen_x0_jac(d.gen, z, dx0_dv0, dx0_dz);
     sig_lin = sigma_of<M>(d, u);
   }
   double a0tot[X];
@@ -2004,11 +2004,11 @@ __global__ void k_gen_xobs(Dims d, Slots S, Work W, int part) {
   double u[UMAX], z[M::Z], dzdu[M::Z * M::Z], v0[M::V0], x[X];
 #pragma unroll
   for (int j = 0; j < UMAX; ++j) u[j] = (j < d.U) ? head[j * d.cpb] : 0.0;
-  M::gen_z(u, z, dzdu);
+  M::gen_z(d.gen, u, z, dzdu);
   typename M::Coef C;
   M::make_coef(z, d.sd, C);
   ldcol<M::V0>(head + d.U * d.cpb, d.cpb, v0);
-  M::gen_x0(z, v0, x);
+  M::gen_x0(d.gen, z, v0, x);
   double* xo = W.xobs + ((long long)tile * d.T * X) * d.cpb + cl;
   for (int b = 0; b < d.nb[part]; ++b) {
     const Blk B = get_block<M>(d, part, b);
@@ -2041,7 +2041,7 @@ __global__ void k_init_interp(Dims d, Slots S, Work W, int part) {
   double u[UMAX], z[Z], dzdu[Z * Z];
 #pragma unroll
   for (int j = 0; j < UMAX; ++j) u[j] = (j < d.U) ? q.head[j * t.cpb] : 0.0;
-  M::gen_z(u, z, dzdu);
+  M::gen_z(d.gen, u, z, dzdu);
   typename M::Coef C;
   M::make_coef(z, d.sd, C);
   const Blk B = get_block<M>(d, part, t.slot);
@@ -2051,7 +2051,7 @@ __global__ void k_init_interp(Dims d, Slots S, Work W, int part) {
     if (o == 0) {
       double v0[M::V0];
       ldcol<M::V0>(q.head + d.U * t.cpb, t.cpb, v0);
-      M::gen_x0(z, v0, xa);
+      M::gen_x0(d.gen, z, v0, xa);
     } else {
       ldcol<X>(xoc + (o - 1) * X * t.cpb, t.cpb, xa);
     }

@@ -174,6 +174,7 @@ mmd_ops make_ops() {
   using O = Ops<Mdl, NRMAX, RMAX>;
   mmd_ops t;
   t.X = Mdl::X; t.V = Mdl::V; t.Z = Mdl::Z; t.V0 = Mdl::V0; t.Y = Mdl::Y; t.nrmax = NRMAX; t.rmax = RMAX;
+  t.ngen = Mdl::NGEN; t.default_gen = Mdl::default_gen;
   t.point = O::point; t.constr = O::constr; t.project = O::project; t.qn = O::qn; t.leapfrog = O::leapfrog;
   t.hamiltonian = O::hamiltonian; t.pack = O::pack; t.unpack = O::unpack; t.retile = O::retile;
   t.vec_uturn = O::vec_uturn; t.gen_xobs = O::gen_xobs; t.init_interp = O::init_interp; t.philox = O::philox; t.constr_rows = O::constr_rows; t.hmc_target = O::hmc_target;

@@ -26,7 +26,7 @@ template <class M, int UMAX>
 MMD_D void make_par(const Dims& d, const double* u, ChainPar<M, UMAX>& P) {
 #pragma unroll
   for (int j = 0; j < UMAX; ++j) P.u[j] = u[j];
-  M::gen_z(P.u, P.z, P.dzdu);
+  M::gen_z(d.gen, P.u, P.z, P.dzdu);
   M::make_coef(P.z, d.sd, P.C);
   P.sigy = sigma_of<M>(d, P.u);
 }
@@ -37,7 +37,7 @@ template <class M>
 MMD_D void block_start(const Dims& d, const Blk& B, const double* z, const double* v0, const double* xoc, int cpb,
                        double* x) {
   if (B.ini) {
-    M::gen_x0(z, v0, x);
+    M::gen_x0(d.gen, z, v0, x);
   } else {
     ldcol<M::X>(xoc + (B.o - 1) * M::X * cpb, cpb, x);
   }

@@ -68,3 +68,39 @@ def generate_x_seq(z, x_0, v_seq, δ):
 def generate_y_seq(z, x_0, v_seq, δ, num_steps_per_obs):
     x_seq = generate_x_seq(z, x_0, v_seq, δ)
     return obs_func(x_seq[num_steps_per_obs - 1:: num_steps_per_obs])
+
+
+# ---- run-time generator parameters (priors without recompiling) -------------------------------------------------
+# The device functor evaluates   z_i = a_i u_i + b_i  (exponentiated where exp_mask_i),   x_0 = v_0 + c + E z
+# from 22 run-time values (include/mmd_b200.h: mmd_set_generator_params).  The functions above are the default
+# (a = 1, b = 0, exp_mask = [1, 1, 1, 0], c = 0, E[1, 3] = -1); the notebook's priors are another set.
+def generator_params(scale=(1.0, 1.0, 1.0, 1.0), shift=(0.0, 0.0, 0.0, 0.0), exp_mask=(1, 1, 1, 0), x0_shift=(0.0, 0.0),
+                     x0_z=((0.0, 0.0, 0.0, 0.0), (0.0, 0.0, 0.0, -1.0))):
+    """Flat parameter vector for ``BatchedChains(..., generator_params=...)`` / ``mmd_set_generator_params``."""
+    p = np.concatenate([np.asarray(scale, float).reshape(4), np.asarray(shift, float).reshape(4),
+                        np.asarray(exp_mask, float).reshape(4) != 0, np.asarray(x0_shift, float).reshape(2),
+                        np.asarray(x0_z, float).reshape(8)]).astype(np.float64)
+    return p
+
+
+NOTEBOOK_GENERATOR_PARAMS = generator_params(scale=(0.5,) * 4, shift=(-1.0, -2.0, 1.0, 1.0), exp_mask=(1, 1, 0, 0),
+                                             x0_shift=(-0.5, -0.5), x0_z=np.zeros((2, 4)))
+
+
+def make_generators(params):
+    """NumPy ``generate_z`` / ``generate_x_0`` for a parameter vector (tagged like the default ones, carrying the
+    parameters so that the drop-in system forwards them to the device)."""
+    params = np.asarray(params, dtype=np.float64).reshape(22)
+    a, b, m, c, E = params[0:4], params[4:8], params[8:12] != 0, params[12:14], params[14:22].reshape(2, 4)
+
+    def generate_z(u):
+        lin = a * np.asarray(u)[..., :4] + b
+        return np.where(m, np.exp(lin), lin)
+
+    def generate_x_0(z, v_0):
+        return np.asarray(v_0) + c + np.asarray(z) @ E.T
+
+    for f in (generate_z, generate_x_0):
+        f._mmd_model = "fhn"
+        f._mmd_generator_params = params
+    return generate_z, generate_x_0

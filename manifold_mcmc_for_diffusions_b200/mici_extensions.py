@@ -128,12 +128,18 @@ class ConditionedDiffusionConstrainedSystem(System):
             funcs.append(generate_σ)
         model = _model_tag(*funcs)
         self._model = model
+        # generators built by example_models.fhn.make_generators carry run-time parameters (priors): both must carry
+        # the same ones
+        gps = [getattr(f, "_mmd_generator_params", None) for f in (generate_x_0, generate_z)]
+        if (gps[0] is None) != (gps[1] is None) or (gps[0] is not None and not np.array_equal(gps[0], gps[1])):
+            raise ValueError("generate_x_0 and generate_z must come from the same make_generators(...) call")
+        self._gen_params = gps[0]
         y_seq = np.asarray(y_seq, dtype=np.float64)
         num_obs, dim_y = y_seq.shape
         dim_v_0 = dim_x if dim_v_0 is None else dim_v_0
         self._bc = BatchedChains(model, obs_interval, num_steps_per_obs, num_obs_per_subseq, y_seq, dim_u, 1,
                                  noise=noise, sigma_fixed=sigma, use_gaussian_splitting=use_gaussian_splitting,
-                                 device=device)
+                                 device=device, generator_params=self._gen_params)
         self.num_partition = self._bc.num_partition
         self.dim_q = self._bc.dim_q
         self.model_dict = {
@@ -224,7 +230,8 @@ class ConditionedDiffusionConstrainedSystem(System):
         if bc is None:
             c = self._ctor
             bc = BatchedChains(c["model"], c["obs_interval"], c["S"], c["R"], c["y"], c["dim_u"], n, noise=c["noise"],
-                               sigma_fixed=c["sigma"], use_gaussian_splitting=c["gaussian"], device=c["device"])
+                               sigma_fixed=c["sigma"], use_gaussian_splitting=c["gaussian"], device=c["device"],
+                               generator_params=self._gen_params)
             bc._ticket = 0
             self._batch[n] = bc
         return bc

@@ -137,3 +137,39 @@ def test_sir_functor_matches_autodiff(shim):
         Gc = np.ascontiguousarray(Gam)
         shim.sir_gen_z_second(_p(u), _p(zz), _p(Gc), _p(ex))
         assert np.max(np.abs(ex - ref2)) < 1e-13 * max(1.0, np.abs(ref2).max())
+
+
+def test_fhn_generators_with_runtime_parameters(shim):
+    """generate_z / generate_x_0 of the FHN functor with run-time parameters (mmd_set_generator_params): values against
+    the NumPy mirror example_models.fhn.make_generators, first and second derivatives against autodiff, for the
+    reference's parametrisation, the notebook's and a random one."""
+    from manifold_mcmc_for_diffusions_b200.example_models import fhn as M
+
+    rng = np.random.default_rng(5)
+    rnd = M.generator_params(scale=rng.uniform(0.3, 1.5, 4), shift=rng.standard_normal(4), exp_mask=(0, 1, 1, 0),
+                             x0_shift=rng.standard_normal(2), x0_z=rng.standard_normal((2, 4)))
+    for gp in (M.generator_params(), M.NOTEBOOK_GENERATOR_PARAMS, rnd):
+        gen_z, gen_x0 = M.make_generators(gp)
+        a, b, m = torch.tensor(gp[0:4]), torch.tensor(gp[4:8]), torch.tensor(gp[8:12] != 0)
+        c, E = torch.tensor(gp[12:14]), torch.tensor(gp[14:22].reshape(2, 4))
+
+        def tz(u_):
+            lin = a * u_ + b
+            return torch.where(m, torch.exp(lin), lin)
+
+        for _ in range(5):
+            u, v0, Gam = rng.standard_normal(4), rng.standard_normal(2), rng.standard_normal(16)
+            z, dzdu, extra, x0, dv0, dz = (np.zeros(n) for n in (4, 16, 4, 2, 4, 8))
+            shim.fhn_gen_all(_p(gp), _p(u), _p(v0), _p(Gam), _p(z), _p(dzdu), _p(extra), _p(x0), _p(dv0), _p(dz))
+            assert np.max(np.abs(z - gen_z(u))) < 1e-14 * max(1, np.abs(z).max())
+            assert np.max(np.abs(x0 - gen_x0(z, v0))) < 1e-13 * max(1, np.abs(x0).max())
+            J = torch.func.jacrev(tz)(torch.tensor(u)).numpy()
+            assert np.max(np.abs(dzdu.reshape(4, 4) - J)) < 1e-13 * max(1, np.abs(J).max())
+            H = torch.func.jacfwd(torch.func.jacrev(tz))(torch.tensor(u)).numpy()          # [m, j, j']
+            ex = np.einsum("mj,mjk->k", Gam.reshape(4, 4), H)
+            assert np.max(np.abs(extra - ex)) < 1e-12 * max(1, np.abs(ex).max())
+            assert np.array_equal(dv0.reshape(2, 2), np.eye(2)) and np.array_equal(dz.reshape(2, 4), E.numpy())
+    # the default parameters reproduce the reference's generators exactly
+    gz, gx = M.make_generators(M.generator_params())
+    u, v0 = rng.standard_normal(4), rng.standard_normal(2)
+    assert np.array_equal(gz(u), M.generate_z(u)) and np.array_equal(gx(gz(u), v0), M.generate_x_0(gz(u), v0))

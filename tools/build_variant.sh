@@ -12,5 +12,5 @@ nvcc $F "$@" -c -o $out/mmd_api.o $C/mmd_api.cu &
 nvcc $F "$@" -c -o $out/mmd_ops_fhn_r5.o $C/mmd_ops_fhn_r5.cu &
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build_variants/libmmd_$name.so $out/mmd_api.o $out/mmd_ops_fhn_r5.o \
-  build/mmd_ops_fhn.o build/mmd_ops_fhn_r16.o build/mmd_ops_sir.o build/mmd_ops_fhn_notebook.o
+  build/mmd_ops_fhn.o build/mmd_ops_fhn_r16.o build/mmd_ops_sir.o
 ls -la build_variants/libmmd_$name.so

@@ -213,24 +213,42 @@ FHN_HEADER = """  static constexpr int X = 2;   // dim_x   (fhn.py:10)
   static constexpr int Y = 1;   // dim_y: obs_func(x) = x[0]  (fhn.py:37-38)
   static constexpr int MODEL_ID = 0;
 
-  // z = generate_z(u) and dz/du (fhn.py:41-43): z = [exp u0, exp u1, exp u2, u3]
-  MMD_HD static void gen_z(const double* u, double* z, double* dzdu /* Z x Z */) {
-    z[0] = exp(u[0]); z[1] = exp(u[1]); z[2] = exp(u[2]); z[3] = u[3];
+  // Generators with run-time parameters gp[22] (Dims::gen; mmd_set_generator_params):
+  //   z_i = a_i u_i + b_i, exponentiated where m_i != 0        gp = [a (4) | b (4) | m (4) | c (2) | E (2 x 4, row-major)]
+  //   x_0 = v_0 + c + E z
+  // The reference's fhn.py:41-51 (z = [exp u0, exp u1, exp u2, u3], x_0 = v_0 - [0, z3]) is a = 1, b = 0,
+  // m = [1, 1, 1, 0], c = 0, E[1][3] = -1 (the default); the notebook's priors are another parameter set.
+  static constexpr int NGEN = 22;
+  MMD_HD static void default_gen(double* gp) {
+    for (int i = 0; i < NGEN; ++i) gp[i] = 0.0;
+    gp[0] = gp[1] = gp[2] = gp[3] = 1.0;
+    gp[8] = gp[9] = gp[10] = 1.0;
+    gp[14 + 1 * 4 + 3] = -1.0;
+  }
+  MMD_HD static void gen_z(const double* gp, const double* u, double* z, double* dzdu /* Z x Z */) {
     for (int i = 0; i < 16; ++i) dzdu[i] = 0.0;
-    dzdu[0] = z[0]; dzdu[5] = z[1]; dzdu[10] = z[2]; dzdu[15] = 1.0;
+    for (int i = 0; i < 4; ++i) {
+      const double lin = gp[i] * u[i] + gp[4 + i];
+      const bool ex = gp[8 + i] != 0.0;
+      z[i] = ex ? exp(lin) : lin;
+      dzdu[5 * i] = ex ? gp[i] * z[i] : gp[i];
+    }
   }
   // extra[j'] = sum_{m,j} Gam[m*Z+j] * d2 z_m / du_j du_j'   (second derivative of generate_z)
-  MMD_HD static void gen_z_second(const double* u, const double* z, const double* Gam, double* extra) {
-    extra[0] = Gam[0] * z[0]; extra[1] = Gam[5] * z[1]; extra[2] = Gam[10] * z[2]; extra[3] = 0.0;
+  MMD_HD static void gen_z_second(const double* gp, const double* u, const double* z, const double* Gam, double* extra) {
+    for (int i = 0; i < 4; ++i) extra[i] = gp[8 + i] != 0.0 ? Gam[5 * i] * gp[i] * gp[i] * z[i] : 0.0;
   }
-  // x_0 = generate_x_0(z, v_0) = v_0 - [0, z3] (fhn.py:50-51); linear: d/dv_0 = I, d/dz = -e1 e3^T
-  MMD_HD static void gen_x0(const double* z, const double* v0, double* x0) {
-    x0[0] = v0[0]; x0[1] = v0[1] - z[3];
+  MMD_HD static void gen_x0(const double* gp, const double* z, const double* v0, double* x0) {
+    for (int i = 0; i < 2; ++i) {
+      double s = v0[i] + gp[12 + i];
+      for (int j = 0; j < 4; ++j)
+        if (gp[14 + 4 * i + j] != 0.0) s += gp[14 + 4 * i + j] * z[j];
+      x0[i] = s;
+    }
   }
-  MMD_HD static void gen_x0_jac(const double* z, double* dx0_dv0 /* X x V0 */, double* dx0_dz /* X x Z */) {
+  MMD_HD static void gen_x0_jac(const double* gp, const double* z, double* dx0_dv0 /* X x V0 */, double* dx0_dz /* X x Z */) {
     dx0_dv0[0] = 1.0; dx0_dv0[1] = 0.0; dx0_dv0[2] = 0.0; dx0_dv0[3] = 1.0;
-    for (int i = 0; i < 8; ++i) dx0_dz[i] = 0.0;
-    dx0_dz[7] = -1.0;
+    for (int i = 0; i < 8; ++i) dx0_dz[i] = gp[14 + i];
   }
   // observation y = h(x) = x[0]; gradient e0; zero second derivative
   MMD_HD static double obs(const double* x) { return x[0]; }
@@ -266,7 +284,7 @@ SIR_HEADER = """  static constexpr int X = 3;   // dim_x   (sir.py:9)   state [l
   static constexpr int MODEL_ID = 1;
 
   // z = generate_z(u) (sir.py:77-85): [exp u0, exp u1, u2, exp(sqrt(.75) u3 + .5 u1 - 3)] and dz/du
-  MMD_HD static void gen_z(const double* u, double* z, double* dzdu /* Z x Z */) {
+  MMD_HD static void gen_z(const double* /*gp: no run-time generator parameters*/, const double* u, double* z, double* dzdu /* Z x Z */) {
     z[0] = exp(u[0]); z[1] = exp(u[1]); z[2] = u[2];
     z[3] = exp(0.8660254037844386 * u[3] + 0.5 * u[1] - 3.0);
     for (int i = 0; i < 16; ++i) dzdu[i] = 0.0;
@@ -274,7 +292,9 @@ SIR_HEADER = """  static constexpr int X = 3;   // dim_x   (sir.py:9)   state [l
     dzdu[13] = 0.5 * z[3]; dzdu[15] = 0.8660254037844386 * z[3];
   }
   // extra[j'] = sum_{m,j} Gam[m*Z+j] * d2 z_m / du_j du_j'
-  MMD_HD static void gen_z_second(const double* u, const double* z, const double* Gam, double* extra) {
+  static constexpr int NGEN = 0;
+  MMD_HD static void default_gen(double*) {}
+  MMD_HD static void gen_z_second(const double*, const double* u, const double* z, const double* Gam, double* extra) {
     const double a = 0.5, b = 0.8660254037844386;
     extra[0] = Gam[0] * z[0];
     extra[1] = Gam[5] * z[1] + z[3] * (Gam[13] * a * a + Gam[15] * a * b);
@@ -282,10 +302,10 @@ SIR_HEADER = """  static constexpr int X = 3;   // dim_x   (sir.py:9)   state [l
     extra[3] = z[3] * (Gam[13] * a * b + Gam[15] * b * b);
   }
   // x_0 = generate_x_0(z, v_0) = [log 762, log 1, v_0[0]] (sir.py:88-89)
-  MMD_HD static void gen_x0(const double* z, const double* v0, double* x0) {
+  MMD_HD static void gen_x0(const double*, const double* z, const double* v0, double* x0) {
     x0[0] = 6.635946555686647; x0[1] = 0.0; x0[2] = v0[0];
   }
-  MMD_HD static void gen_x0_jac(const double* z, double* dx0_dv0 /* X x V0 */, double* dx0_dz /* X x Z */) {
+  MMD_HD static void gen_x0_jac(const double*, const double* z, double* dx0_dv0 /* X x V0 */, double* dx0_dz /* X x Z */) {
     dx0_dv0[0] = 0.0; dx0_dv0[1] = 0.0; dx0_dv0[2] = 1.0;
     for (int i = 0; i < 12; ++i) dx0_dz[i] = 0.0;
   }
