@@ -594,12 +594,13 @@ def run_reference(args):
         "warmup": args.warmup,
         "ms_per_step": (1e3 / cb["value"]) if cb["value"] > 0 else None,   # one chain-step on the host cores
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step_size": args.dt, "traj_len": args.traj_len,
-                   "burnin_transitions": args.burnin},
+        "config": {"workload": WORKLOAD, "total_chains": args.total_chains if args.scaling == "strong" else None,
+                   "step_size": args.dt, "traj_len": args.traj_len, "burnin_transitions": args.burnin,
+                   "note": "host cores only: every step is a bounded sample of the workload (cpu_baseline.sample)"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -649,7 +650,7 @@ def main():
                          "chain are bit-identical, tests/test_gpu_regrouping.py; measured: no gain, the iteration "
                          "count of a chain is not persistent across transitions)")
     ap.add_argument("--e2e-steps", type=int, default=6)
-    ap.add_argument("--e2e-pipeline", type=int, default=2,
+    ap.add_argument("--e2e-pipeline", type=int, default=4,
                     help="number of BatchedChains objects the end-to-end loop alternates between (1 = no overlap)")
     ap.add_argument("--scaling", choices=("weak", "strong"), default="strong",
                     help="strong (default): BASELINE.json config 5, --total-chains sharded over the ranks; weak: --chains "
