@@ -1,8 +1,11 @@
 #!/usr/bin/env python
 """Throughput of the other configurations BASELINE.json names (they are parity-test cases, not bench.py lines):
-  * FHN noisy observations, inferred noise scale: T=100, S=40, R=5, dim_u=5 (fhn_model_noisy_obs_chmc_experiment.py)
-  * SIR, boarding-school shape: T=14, S=20, one block of 14 observations, dim_u=5 (sir_model_chmc_experiment.py)
-Synthetic data of those shapes; static-trajectory transitions (8 leapfrog steps, momentum refresh, accept, partition
+  * FHN noisy observations (noise scale 0.1): T=100, S=40, R=5 (fhn_model_noisy_obs_chmc_experiment.py)
+  * SIR, boarding-school data: T=14, S=20, one block of 14 observations, noise scale 1 (sir_model_chmc_experiment.py)
+Observation series: the reference's own bundled data sets (scripts/fhn_model_noisy_obs_data.npz,
+scripts/sir_model_boarding_school_data.npz) as stored in tests/golden/bundled_configs_golden.npz by
+tests/golden/make_golden_bundled.py; chains start from prior draws (FHN) / replicas of the golden initial state with
+fresh momenta (SIR).  Static-trajectory transitions (8 leapfrog steps, momentum refresh, accept, partition
 switch) timed on the device after a short burn-in; successful chain leapfrog steps per second."""
 import json
 import os
@@ -36,29 +39,31 @@ def run(bc, dt, burn_dt, burn, L=8, ntr=4, tag=""):
 def fhn_noisy(n, solver):
     T, S, R = 100, 40, 5
     rng = np.random.default_rng(7)
-    y = np.load(os.path.join(ROOT, "tests/golden/fhn_yseq_T100.npy")) + 0.1 * rng.standard_normal((T, 1))
-    bc = BatchedChains("fhn", 0.2, S, R, y, 5, n, noise=2)
+    g = np.load(os.path.join(ROOT, "tests/golden/bundled_configs_golden.npz"))
+    y = np.asarray(g["fhn_noisy_y"], dtype=np.float64)
+    assert (int(g["fhn_noisy_T"]), int(g["fhn_noisy_S"]), int(g["fhn_noisy_R"])) == (T, S, R)
+    bc = BatchedChains("fhn", float(g["fhn_noisy_obs_interval"]), S, R, y, 4, n, noise=1,
+                       sigma_fixed=float(g["fhn_noisy_sigma"]))
     bc.opts.solver = solver
-    u = rng.standard_normal((n, 5))
-    u[:, 4] = np.log(0.1) + 0.3 * u[:, 4]
+    u = rng.standard_normal((n, 4))
     v0 = rng.standard_normal((n, 2))
     xo = np.concatenate((np.broadcast_to(y, (n, T, 1)), 0.5 * rng.standard_normal((n, T, 1))), -1)
     bc.init_linear_interpolation(u, v0, xo, 0)
-    out = run(bc, 0.1, 0.05, 30, tag="FHN noisy obs, inferred sigma, T=100 S=40 R=5")
+    out = run(bc, 0.1, 0.05, 30, tag="FHN noisy obs (bundled data), observation noise 0.1, T=100 S=40 R=5")
     bc.close()
     return out
 
 
 def sir(n, solver):
-    g = np.load(os.path.join(ROOT, "tests/golden/sir_T14_S20_golden.npz"))
-    k = g["q0"].shape[0]
-    reps = (n + k - 1) // k
-    q = np.tile(g["q0"], (reps, 1))[:n]
-    x = np.tile(g["xobs"], (reps, 1, 1))[:n]
-    bc = BatchedChains("sir", 1.0, int(g["S"]), int(g["T"]), g["y"], 5, n, noise=2)
+    g = np.load(os.path.join(ROOT, "tests/golden/bundled_configs_golden.npz"))
+    q = np.tile(g["sir_q0"][None], (n, 1))
+    x = np.tile(g["sir_xobs"][None], (n, 1, 1))
+    bc = BatchedChains("sir", float(g["sir_obs_interval"]), int(g["sir_S"]), int(g["sir_T"]), g["sir_y"], 4, n, noise=1,
+                       sigma_fixed=float(g["sir_sigma"]))
     bc.opts.solver = solver
     bc.set_state(q, x, 0)
-    out = run(bc, float(g["dt"]), float(g["dt"]), 20, tag="SIR T=14 S=20 one block of 14 observations")
+    out = run(bc, float(g["sir_dt"]), float(g["sir_dt"]), 20,
+              tag="SIR (bundled boarding-school data) T=14 S=20 one block of 14 observations")
     bc.close()
     return out
 
