@@ -20,6 +20,10 @@ struct Ops {
   template <class Kern>
   static int prep(Kern kern, size_t bytes) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // tuning aid: MMD_SMEM_CARVEOUT = preferred shared-memory carve-out in percent of the unified L1 / shared array
+    // (the driver otherwise picks the smallest configuration that holds the resident CTAs)
+    static const int carve = [] { const char* e = getenv("MMD_SMEM_CARVEOUT"); return e ? atoi(e) : -1; }();
+    if (carve >= 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     return 0;
   }
   static int point(mmd_handle h, int which, int with_grad) {
