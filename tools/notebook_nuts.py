@@ -48,7 +48,9 @@ def main():
             src = rng.choice(np.flatnonzero(moved > 0), size=len(stuck))
             q[stuck], x[stuck] = q[src], x[src]
             bc.set_state(q, x, bc.partition)
-    nuts = BatchedNUTS(bc, max_tree_depth=depth)
+    # ERR_STAT: accept_stat reported for transitions that end in an integrator error: "partial" (Mici's
+    # sum_acc_prob / n_step, the default) or "zero" (the reading of the round-1 runs)
+    nuts = BatchedNUTS(bc, max_tree_depth=depth, error_accept_stat=os.environ.get("ERR_STAT", "partial"))
     t0 = time.time()
     # Mici: every chain's adapter starts from its own coarse step-size search (no step size is given in cell 33/43)
     from manifold_mcmc_for_diffusions_b200.adaptation import find_init_step_sizes
@@ -94,6 +96,7 @@ def main():
            "adapted_step_size": eps, "init_step_size_search_quantiles": np.quantile(eps0, [0.05, 0.5, 0.95]).tolist(), "accept_stat": float(np.mean(acc)), "n_step": float(np.mean(nst)),
            "convergence_error": float(np.mean(cerr)), "non_reversible_step": float(np.mean(nrv)),
            "tree_depth": float(np.mean(dep)), "wall_s": round(time.time() - t0, 1),
+           "error_accept_stat": nuts.error_accept_stat,
            "warm_up_accept_stat_last20": float(np.mean(warm["accept_stat"][-20:])),
            "notebook": {"accept_stat": 0.833, "n_step": 28.3, "convergence_error": 0.15, "non_reversible_step": 0.0},
            "vars": {}}
