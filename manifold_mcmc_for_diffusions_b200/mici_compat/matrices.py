@@ -3,6 +3,10 @@ import numpy as np
 
 
 class IdentityMatrix:
+    # NumPy must defer `ndarray @ IdentityMatrix` to __rmatmul__ (Mici's Matrix classes do the same): the reference's
+    # h2 is `0.5 * state.mom @ self.metric.inv @ state.mom` (mici_extensions.py:1202)
+    __array_ufunc__ = None
+
     def __init__(self, size=None, scalar=1.0):
         self.size = size
         self.scalar = scalar
@@ -32,6 +36,8 @@ class IdentityMatrix:
 
 
 class DensePositiveDefiniteMatrix:
+    __array_ufunc__ = None
+
     def __init__(self, array):
         self.array = np.asarray(array)
 
@@ -49,6 +55,9 @@ class DensePositiveDefiniteMatrix:
 
     def __matmul__(self, other):
         return self.array @ other
+
+    def __rmatmul__(self, other):
+        return other @ self.array
 
 
 class PositiveDefiniteBlockDiagonalMatrix:
