@@ -10,9 +10,16 @@ reference uses ``jax.jacrev`` / ``jax.value_and_grad``, so this file is independ
 hand-derived adjoint recursions in the CUDA kernels.
 
 PARITY STATUS: the reference ships no golden vectors or tests and none of its pinned dependencies
-(mici 0.1.10, symnum 0.1.2, jax 0.2.21) can be installed in this environment, so this oracle is
-"parity unpinned" against the reference binary; it is pinned only by the self-consistency
-invariants in ``tests/test_oracle_invariants.py`` and the notebook's recorded statistics.
+(mici 0.1.10, symnum 0.1.2, jax 0.2.21) can be installed in this environment.  Since round 2 this
+restatement is pinned, at trace level, to the REFERENCE'S OWN SOURCE FILE: ``oracle/reference_runner.py``
+executes ``/root/reference/sde/mici_extensions.py`` unmodified with a torch-backed ``jax`` stand-in
+(``oracle/jax_torch_shim.py``) and ``tests/test_reference_pin_cpu.py`` compares it with this file quantity by
+quantity (constraint, log-det, its gradient, cotangent projection, Hamiltonian, whole leapfrog steps with both
+solvers; 1e-10 .. 1e-13), and the GPU tests compare the CUDA path with vectors generated from that run
+(``tests/golden/reference_pin_golden.npz``).  What is substituted in that run, and therefore NOT pinned: the array
+library (torch instead of XLA), Mici's integrator / state classes (``mici_compat`` stand-ins of Mici 0.1.10) and the
+SymNum-generated model callables (the torch functions of ``oracle/models.py``, re-derived with SymPy).  Further
+pins: the invariants of ``tests/test_oracle_invariants.py`` and the notebook's recorded posterior.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg may import this.
 """

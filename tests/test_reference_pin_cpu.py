@@ -99,3 +99,71 @@ def test_partition_switch_and_initialiser_equal_the_reference(setup):
     x_o = syso.generate_x_obs_seq(torch.tensor(q)) if hasattr(syso, "generate_x_obs_seq") else None
     if x_o is not None:
         assert _rel(st.x_obs_seq, x_o) < 1e-13
+
+
+def test_sir_system_equals_the_reference():
+    """The SIR model (Euler-Maruyama on the log-transformed SDE, non-linear observation, inferred noise scale, one block
+    of all observations) through the reference's own source against the oracle: point quantities and one leapfrog step
+    with each solver."""
+    import torch as _torch
+
+    from manifold_mcmc_for_diffusions_b200.mici_compat.integrators import ConstrainedLeapfrogIntegrator
+    from oracle.models import sir
+    from tests.test_gpu_sir import make_sir_problem
+
+    prob = make_sir_problem(6, 4, 6, n_chains=1)
+    ref, syso = R.load(), prob["system"]
+    sysr = ref.ConditionedDiffusionConstrainedSystem(
+        prob["obs_interval"], prob["S"], prob["R"], _torch.as_tensor(prob["y"]), 5, 3, 3, sir.forward_func,
+        sir.generate_x_0, sir.generate_z, sir.obs_func, sir.generate_σ_y, False, dim_v_0=1)
+    q0, xo = prob["q"][0], prob["xobs"][0]
+    rng = np.random.default_rng(3)
+    st = ref.ConditionedDiffusionHamiltonianState(pos=q0.copy(), x_obs_seq=xo, partition=0)
+    pt = syso.point(q0, xo, 0)
+    assert np.max(np.abs(np.asarray(sysr.constr(st)) - syso._constr(_torch.tensor(q0), _torch.tensor(xo), 0).numpy())) < 1e-12
+    assert abs(float(sysr.log_det_sqrt_gram(st)) - float(pt["ld"])) < 1e-11 * max(1.0, abs(float(pt["ld"])))
+    assert _rel(sysr.grad_log_det_sqrt_gram(st), pt["grad_ld"]) < 1e-10
+    p_raw = rng.standard_normal(q0.shape)
+    tol = dict(constraint_tol=1e-9, position_tol=1e-8, divergence_tol=1e10, max_iters=50)
+    for solver, wrapper in (("quasi_newton", ref.jitted_solve_projection_onto_manifold_quasi_newton),
+                            ("newton", ref.jitted_solve_projection_onto_manifold_newton)):
+        integ = ConstrainedLeapfrogIntegrator(sysr, step_size=0.01, n_inner_step=1, reverse_check_tol=2e-8,
+                                              projection_solver=wrapper, projection_solver_kwargs=tol)
+        st = ref.ConditionedDiffusionHamiltonianState(pos=q0.copy(), x_obs_seq=xo, partition=0)
+        st.mom = np.asarray(sysr.project_onto_cotangent_space(p_raw.copy(), st))
+        p = syso.project_onto_cotangent_space(_torch.tensor(p_raw), pt)
+        assert _rel(st.mom, p) < 1e-11
+        st = integ.step(st)
+        q, p, _, _ = O.leapfrog_step(syso, q0, p, xo, 0, 0.01, pt=pt, solver=solver, **tol)
+        assert _rel(st.pos, q) < 1e-11 and _rel(st.mom, p) < 1e-9
+
+
+@pytest.mark.parametrize("gaussian", [False, True])
+def test_hmc_target_and_initialiser_equal_the_reference(gaussian):
+    """The standard-HMC baseline target (conditioned_diffusion_neg_log_dens_and_grad, :82-205) and the
+    linear-interpolation initialiser (:1479-1547) of the reference source against the oracle."""
+    import torch as _torch
+
+    from oracle.models import fhn
+
+    prob = make_fhn_problem(8, 5, 4, n_chains=1, nd=100, noise=2, gaussian=gaussian)
+    ref, syso = R.load(), prob["system"]
+    y = _torch.as_tensor(prob["y"])
+    args = (0.2, 5, y, 5, 2, 2, fhn.forward_func, fhn.generate_x_0, fhn.generate_z, fhn.generate_σ_y, fhn.obs_func, gaussian)
+    nld_r, grad_r = ref.conditioned_diffusion_neg_log_dens_and_grad(*args)
+    nld_o, vg_o = O.conditioned_diffusion_neg_log_dens_and_grad(*args)
+    rng = np.random.default_rng(2)
+    q = np.concatenate([0.3 * rng.standard_normal(4), [np.log(0.1)], prob["q"][0][5:7], prob["q"][0][7:7 + 8 * 5 * 2]])
+    g_r, v_r = grad_r(q)
+    v_o, g_o = vg_o(q)
+    assert abs(v_r - float(v_o)) < 1e-12 * abs(v_r) and abs(nld_r(q) - float(nld_o(q))) < 1e-12 * abs(v_r)
+    assert _rel(g_r, g_o) < 1e-11
+    # initialiser: same u, v_0 and x_obs_seq on both sides
+    sysr = R.make_fhn_system(0.2, 5, 4, prob["y"], noise=2, use_gaussian_splitting=gaussian)
+    x_init = np.concatenate((prob["y"], 0.5 * np.random.default_rng(5).standard_normal(prob["y"].shape)), -1)
+    u, v0 = 0.4 * rng.standard_normal(5), rng.standard_normal(2)
+    st = ref.find_initial_state_by_linear_interpolation(sysr, np.random.default_rng(0), lambda r: x_init,
+                                                        u=_torch.tensor(u), v_0=_torch.tensor(v0))
+    q_o, x_o = O.find_initial_state_by_linear_interpolation(syso, np.random.default_rng(0), lambda r: x_init, u=u, v_0=v0)
+    assert _rel(st.pos, q_o) < 1e-11 and _rel(st.x_obs_seq, x_o) < 1e-14
+    assert np.max(np.abs(np.asarray(sysr.constr(st)))) < 1e-9
