@@ -97,6 +97,7 @@ def _make_numpy():
     np.where = lambda c, a, b: torch.where(_t(c), _t(a), _t(b))
     np.diag_indices = lambda n: (torch.arange(n), torch.arange(n))
     np.diag = lambda x: torch.diag(_t(x))
+    np.clip = lambda x, a_min=None, a_max=None: torch.clamp(_t(x), min=a_min, max=a_max)   # sir.py:63
     np.sum = lambda x, axis=None: torch.sum(_t(x), **_axis_kw(axis))
     np.mean = lambda x, axis=None: torch.mean(_t(x), **_axis_kw(axis))
     np.max = lambda x, axis=None: torch.max(_t(x)) if axis is None else torch.max(_t(x), dim=axis).values
@@ -200,6 +201,7 @@ def _make_lax():
 
     lax.scan, lax.while_loop, lax.map = scan, while_loop, map_
     lax.cond = lambda pred, tf, ff, *ops: tf(*ops) if bool(pred) else ff(*ops)
+    lax.select = lambda pred, a, b: torch.where(_t(pred), _t(a), _t(b))   # sir.py:66-70
     return lax
 
 

@@ -16,9 +16,10 @@ executes ``/root/reference/sde/mici_extensions.py`` unmodified with a torch-back
 (``oracle/jax_torch_shim.py``) and ``tests/test_reference_pin_cpu.py`` compares it with this file quantity by
 quantity (constraint, log-det, its gradient, cotangent projection, Hamiltonian, whole leapfrog steps with both
 solvers; 1e-10 .. 1e-13), and the GPU tests compare the CUDA path with vectors generated from that run
-(``tests/golden/reference_pin_golden.npz``).  What is substituted in that run, and therefore NOT pinned: the array
-library (torch instead of XLA), Mici's integrator / state classes (``mici_compat`` stand-ins of Mici 0.1.10) and the
-SymNum-generated model callables (the torch functions of ``oracle/models.py``, re-derived with SymPy).  Further
+(``tests/golden/reference_pin_golden.npz``).  The model callables of that run are the reference's own
+``sde/example_models/*.py`` executed through a SymPy-backed ``symnum`` stand-in (``oracle/symnum_sympy_shim.py``).
+What is substituted, and therefore NOT pinned: the array / code-generation libraries (torch and SymPy instead of XLA
+and SymNum) and Mici's integrator / state classes (``mici_compat`` stand-ins of Mici 0.1.10).  Further
 pins: the invariants of ``tests/test_oracle_invariants.py`` and the notebook's recorded posterior.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg may import this.
