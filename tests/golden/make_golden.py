@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Generate the canonical-size golden vectors (FHN noiseless, T=100, S=25, R=5) from the float64
 autodiff oracle.  The reference itself cannot run in this environment (mici / jax / symnum are not
-installable), so these are ORACLE-frozen vectors: they pin the CUDA path to the restatement, not the
-restatement to the reference binary.
+installable), so these are ORACLE-frozen vectors; since round 2 the file is cross-checked against the reference's own
+source executed through torch / SymPy stand-ins (tests/test_reference_pin_cpu.py::
+test_canonical_size_golden_equals_the_reference).
 
     python tests/golden/make_golden.py      # ~3 minutes on one core; writes fhn_T100_S25_R5_golden.npz
 """

@@ -209,3 +209,30 @@ def test_model_definitions_equal_the_reference():
         xx = _torch.tensor(rng.standard_normal((4, 3)))
         assert _rel(sir_r.obs_func(xx), sir_o.obs_func(xx)) < 1e-15 and _rel(fhn_r.obs_func(xx[:, :2]), fhn_o.obs_func(xx[:, :2])) < 1e-15
         assert _rel(sir_r.generate_x_0(zs, v0[:1]), sir_o.generate_x_0(zs, v0[:1])) < 1e-15
+
+
+def test_canonical_size_golden_equals_the_reference():
+    """The committed canonical-size vectors (tests/golden/fhn_T100_S25_R5_golden.npz: FHN noiseless T=100, S=25, R=5, the
+    shape of the bench workload; frozen from the oracle) against the reference's own source at that size: log-det,
+    its gradient, and two constrained leapfrog steps (chain 0 / partition 0 with the reference's quasi-Newton wrapper)."""
+    import os
+
+    from manifold_mcmc_for_diffusions_b200.mici_compat.integrators import ConstrainedLeapfrogIntegrator
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fhn_T100_S25_R5_golden.npz"),
+                allow_pickle=True)
+    ref = R.load()
+    sysr = R.make_fhn_system(0.2, int(g["S"]), int(g["R"]), g["y"])
+    c = 0
+    st = ref.ConditionedDiffusionHamiltonianState(pos=g["q0"][c].copy(), x_obs_seq=g["xobs"][c], partition=c % 2)
+    assert abs(float(sysr.log_det_sqrt_gram(st)) - float(g["ld"][c])) < 1e-10 * abs(float(g["ld"][c]))
+    assert _rel(sysr.grad_log_det_sqrt_gram(st), g["grad_ld"][c]) < 1e-9
+    st.mom = np.asarray(sysr.project_onto_cotangent_space(g["p_raw"][c].copy(), st))
+    integ = ConstrainedLeapfrogIntegrator(
+        sysr, step_size=float(g["dt"]), n_inner_step=1, reverse_check_tol=2e-8,
+        projection_solver=ref.jitted_solve_projection_onto_manifold_quasi_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, divergence_tol=1e10, max_iters=50))
+    for s in range(2):
+        st = integ.step(st)
+        assert _rel(st.pos, g["traj_q"][c][s]) < 1e-10 and _rel(st.mom, g["traj_p"][c][s]) < 1e-8
+        assert abs(float(sysr.h(st)) - float(g["traj_h"][c][s + 1])) < 1e-10 * abs(float(g["traj_h"][c][s + 1]))
