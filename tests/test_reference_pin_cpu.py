@@ -236,3 +236,42 @@ def test_canonical_size_golden_equals_the_reference():
         st = integ.step(st)
         assert _rel(st.pos, g["traj_q"][c][s]) < 1e-10 and _rel(st.mom, g["traj_p"][c][s]) < 1e-8
         assert abs(float(sysr.h(st)) - float(g["traj_h"][c][s + 1])) < 1e-10 * abs(float(g["traj_h"][c][s + 1]))
+
+
+@pytest.mark.parametrize("tag", ["fhn_noisy", "sir"])
+def test_bundled_data_goldens_equal_the_reference(tag):
+    """The committed vectors on the reference's bundled data sets (tests/golden/bundled_configs_golden.npz, BASELINE
+    configs 2 and 3: FHN noisy observations T=100 S=40 R=5, SIR boarding-school data) against the reference's own source:
+    constraint, log-det, its gradient and one constrained leapfrog step with the Newton solver (the scripts' default)."""
+    import os
+
+    import torch as _torch
+
+    from manifold_mcmc_for_diffusions_b200.mici_compat.integrators import ConstrainedLeapfrogIntegrator
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bundled_configs_golden.npz"))
+    ref = R.load()
+    fhn_r, sir_r = R.load_models()
+    y = _torch.as_tensor(np.asarray(g[f"{tag}_y"], dtype=np.float64))
+    if tag == "fhn_noisy":
+        sysr = ref.ConditionedDiffusionConstrainedSystem(
+            float(g[f"{tag}_obs_interval"]), int(g[f"{tag}_S"]), int(g[f"{tag}_R"]), y, 4, 2, 2, fhn_r.forward_func,
+            fhn_r.generate_x_0, fhn_r.generate_z, fhn_r.obs_func, float(g[f"{tag}_sigma"]), False, dim_v_0=2)
+    else:
+        sysr = ref.ConditionedDiffusionConstrainedSystem(
+            float(g[f"{tag}_obs_interval"]), int(g[f"{tag}_S"]), int(g[f"{tag}_T"]), y, 4, 3, 3, sir_r.forward_func,
+            sir_r.generate_x_0, sir_r.generate_z, sir_r.obs_func, float(g[f"{tag}_sigma"]), False, dim_v_0=1)
+    st = ref.ConditionedDiffusionHamiltonianState(pos=g[f"{tag}_q0"].copy(), x_obs_seq=g[f"{tag}_xobs"], partition=0)
+    assert np.max(np.abs(np.asarray(sysr.constr(st)) - g[f"{tag}_c"])) < 1e-11 * max(1.0, float(np.max(np.abs(g[f"{tag}_y"]))))
+    ld = float(g[f"{tag}_ld"])
+    assert abs(float(sysr.log_det_sqrt_gram(st)) - ld) < 1e-10 * max(1.0, abs(ld))
+    assert _rel(sysr.grad_log_det_sqrt_gram(st), g[f"{tag}_grad_ld"]) < 1e-9
+    st.mom = np.asarray(sysr.project_onto_cotangent_space(g[f"{tag}_p_raw"].copy(), st))
+    integ = ConstrainedLeapfrogIntegrator(
+        sysr, step_size=float(g[f"{tag}_dt"]), n_inner_step=1, reverse_check_tol=2e-8,
+        projection_solver=ref.jitted_solve_projection_onto_manifold_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, divergence_tol=1e10, max_iters=50))
+    st = integ.step(st)
+    assert _rel(st.pos, g[f"{tag}_newton_q"]) < 1e-10 and _rel(st.mom, g[f"{tag}_newton_p"]) < 1e-8
+    h_ref = float(g[f"{tag}_newton_h"])
+    assert abs(float(sysr.h(st)) - h_ref) < 1e-9 * max(1.0, abs(h_ref))
