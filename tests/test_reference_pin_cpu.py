@@ -275,3 +275,35 @@ def test_bundled_data_goldens_equal_the_reference(tag):
     assert _rel(st.pos, g[f"{tag}_newton_q"]) < 1e-10 and _rel(st.mom, g[f"{tag}_newton_p"]) < 1e-8
     h_ref = float(g[f"{tag}_newton_h"])
     assert abs(float(sysr.h(st)) - h_ref) < 1e-9 * max(1.0, abs(h_ref))
+
+
+def test_metric_adapter_equals_the_reference():
+    """OnlineBlockDiagonalMetricAdapter (:1804-1931): this package's class against the reference's own, fed the same
+    chains (single chain and the multi-chain combination in finalize)."""
+    from manifold_mcmc_for_diffusions_b200 import mici_extensions as me
+
+    class _State:
+        def __init__(self, pos):
+            self.pos = pos
+
+    class _Tr:
+        def __init__(self):
+            self.system = type("S", (), {"metric": None})()
+
+    def run(ad, draws):
+        st = ad.initialize(_State(draws[0]), None)
+        for d in draws:
+            ad.update(st, _State(d), None, None)
+        return st
+
+    ref = R.load()
+    rng = np.random.default_rng(4)
+    chains = [rng.standard_normal((k, 8)) @ rng.standard_normal((8, 8)) + i for i, k in enumerate((25, 40, 13))]
+    for states in (lambda ad: run(ad, chains[0]), lambda ad: [run(ad, c) for c in chains]):
+        a_r, a_o = ref.OnlineBlockDiagonalMetricAdapter(5), me.OnlineBlockDiagonalMetricAdapter(5)
+        t_r, t_o = _Tr(), _Tr()
+        a_r.finalize(states(a_r), t_r)
+        a_o.finalize(states(a_o), t_o)
+        b_r, b_o = t_r.system.metric.blocks, t_o.system.metric.blocks
+        assert _rel(b_o[0].array, b_r[0].array) < 1e-12
+        assert type(b_o[1]).__name__ == type(b_r[1]).__name__ == "IdentityMatrix"
