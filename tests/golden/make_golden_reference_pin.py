@@ -56,8 +56,14 @@ for c in CASES:
             for i in range(N_CHAINS):
                 st = ref.ConditionedDiffusionHamiltonianState(pos=prob["q"][i].copy(), x_obs_seq=prob["xobs"][i],
                                                               partition=part, mom=ps[i].copy())
-                for _ in range(N_STEPS):
+                for k_step in range(N_STEPS):
                     st = integ.step(st)
+                    if i == 0 and k_step == 0:
+                        # Mici's per-method call counts after ONE step from a fresh state (the paper's cost accounting;
+                        # the solver wrappers book their iterations on them, :1382-1387, :1451-1461)
+                        cc = {k[2]: int(v) for k, v in st._call_counts.items()}
+                        out[f"{t}_p{part}_{solver}_count_names"] = np.array(sorted(cc))
+                        out[f"{t}_p{part}_{solver}_count_values"] = np.array([cc[k] for k in sorted(cc)])
                 qs.append(np.asarray(st.pos, dtype=np.float64)); pps.append(np.asarray(st.mom, dtype=np.float64))
                 hh.append(float(sysr.h(st)))
             out.update({f"{t}_p{part}_{solver}_q": np.stack(qs), f"{t}_p{part}_{solver}_p": np.stack(pps),

@@ -79,3 +79,32 @@ def test_partition_switch_equals_the_reference_source(gold, tag):
     assert bc.partition == 1
     assert _rel(x[0], g[f"{tag}_switch_xobs"]) < 1e-12
     bc.close()
+
+
+@pytest.mark.parametrize("solver", ["quasi_newton", "newton"])
+@pytest.mark.parametrize("tag", ["noiseless", "inferred_noise"])
+def test_drop_in_surface_call_counts_equal_the_reference(gold, tag, solver):
+    """The drop-in module (mici_extensions.py of this package: same names as sde.mici_extensions) driven by the Mici
+    step order books the same per-method call counts on the state as the reference's own source does for the same
+    step -- the cost accounting the paper's cost-per-ESS figures rest on -- and lands on the same state."""
+    from manifold_mcmc_for_diffusions_b200 import example_models, mici_extensions as me
+    from manifold_mcmc_for_diffusions_b200.mici_compat.integrators import ConstrainedLeapfrogIntegrator
+
+    g, m = gold, example_models.fhn
+    noise = int(g[f"{tag}_noise"])
+    system = me.ConditionedDiffusionConstrainedSystem(
+        0.2, int(g[f"{tag}_S"]), int(g[f"{tag}_R"]), g[f"{tag}_y"], 5 if noise == 2 else 4, m.dim_x, m.dim_v, m.forward_func,
+        m.generate_x_0, m.generate_z, m.obs_func, generate_σ=(None if noise == 0 else m.generate_σ_y),
+        use_gaussian_splitting=bool(g[f"{tag}_gaussian"]), dim_v_0=m.dim_v_0)
+    wrapper = (me.jitted_solve_projection_onto_manifold_quasi_newton if solver == "quasi_newton"
+               else me.jitted_solve_projection_onto_manifold_newton)
+    integ = ConstrainedLeapfrogIntegrator(
+        system, step_size=float(g["dt"]), n_inner_step=1, reverse_check_tol=2e-8, projection_solver=wrapper,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, divergence_tol=1e10, max_iters=50))
+    part = 0
+    st = me.ConditionedDiffusionHamiltonianState(pos=g[f"{tag}_q0"][0].copy(), x_obs_seq=g[f"{tag}_xobs"][0], partition=part,
+                                                 mom=g[f"{tag}_p{part}_p0"][0].copy())
+    st = integ.step(st)
+    counts = {k[2]: int(v) for k, v in st._call_counts.items()}
+    ref_counts = dict(zip(g[f"{tag}_p{part}_{solver}_count_names"].tolist(), g[f"{tag}_p{part}_{solver}_count_values"].tolist()))
+    assert counts == ref_counts, (counts, ref_counts)
