@@ -28,7 +28,7 @@ def _rel(a, b):
     c["T"], c["S"], c["R"], c["noise"], "gauss" if c["gaussian"] else "std"))
 def setup(request):
     c = request.param
-    prob = make_fhn_problem(c["T"], c["S"], c["R"], n_chains=2, nd=200, noise=c["noise"], gaussian=c["gaussian"])
+    prob = make_fhn_problem(c["T"], c["S"], c["R"], n_chains=1, nd=200, noise=c["noise"], gaussian=c["gaussian"])
     ref = R.load()
     sysr = R.make_fhn_system(0.2, c["S"], c["R"], prob["y"], noise=c["noise"], sigma=prob["sigma"],
                              use_gaussian_splitting=c["gaussian"])
