@@ -73,6 +73,40 @@ for c in CASES:
     ref.SwitchPartitionTransition(sysr).sample(st, None)
     out[f"{t}_switch_xobs"] = np.asarray(st.x_obs_seq, dtype=np.float64)
     print(t, "done", flush=True)
+# ---- SIR (sde/example_models/sir.py through the symnum stand-in): non-linear observation, inferred noise scale,
+# one block of all observations
+import torch  # noqa: E402
+from tests.test_gpu_sir import make_sir_problem  # noqa: E402
+
+prob = make_sir_problem(6, 4, 6, n_chains=2)
+sir_r = R.load_models()[1]
+sysr = ref.ConditionedDiffusionConstrainedSystem(
+    prob["obs_interval"], prob["S"], prob["R"], torch.as_tensor(prob["y"]), 5, 3, 3, sir_r.forward_func,
+    sir_r.generate_x_0, sir_r.generate_z, sir_r.obs_func, sir_r.generate_σ_y, False, dim_v_0=1)
+rng = np.random.default_rng(23)
+p_raw = rng.standard_normal(prob["q"].shape)
+SIR_DT = 0.01
+out.update(sir_T=prob["T"], sir_S=prob["S"], sir_obs_interval=prob["obs_interval"], sir_y=prob["y"], sir_q0=prob["q"],
+           sir_xobs=prob["xobs"], sir_p_raw=p_raw, sir_dt=SIR_DT)
+cs, lds, gs, ps = [], [], [], []
+for i in range(prob["q"].shape[0]):
+    st = ref.ConditionedDiffusionHamiltonianState(pos=prob["q"][i].copy(), x_obs_seq=prob["xobs"][i], partition=0)
+    cs.append(np.asarray(sysr.constr(st), dtype=np.float64)); lds.append(float(sysr.log_det_sqrt_gram(st)))
+    gs.append(np.asarray(sysr.grad_log_det_sqrt_gram(st), dtype=np.float64))
+    ps.append(np.asarray(sysr.project_onto_cotangent_space(p_raw[i].copy(), st), dtype=np.float64))
+out.update(sir_c=np.stack(cs), sir_ld=np.array(lds), sir_grad_ld=np.stack(gs), sir_p0=np.stack(ps))
+for solver, wrapper in (("quasi_newton", ref.jitted_solve_projection_onto_manifold_quasi_newton),
+                        ("newton", ref.jitted_solve_projection_onto_manifold_newton)):
+    integ = ConstrainedLeapfrogIntegrator(sysr, step_size=SIR_DT, n_inner_step=1, reverse_check_tol=2e-8,
+                                          projection_solver=wrapper, projection_solver_kwargs=TOL)
+    qs, pps = [], []
+    for i in range(prob["q"].shape[0]):
+        st = ref.ConditionedDiffusionHamiltonianState(pos=prob["q"][i].copy(), x_obs_seq=prob["xobs"][i], partition=0,
+                                                      mom=ps[i].copy())
+        st = integ.step(st)
+        qs.append(np.asarray(st.pos, dtype=np.float64)); pps.append(np.asarray(st.mom, dtype=np.float64))
+    out.update({f"sir_{solver}_q": np.stack(qs), f"sir_{solver}_p": np.stack(pps)})
+print("sir done", flush=True)
 path = os.path.join(ROOT, "tests", "golden", "reference_pin_golden.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes")

@@ -108,3 +108,34 @@ def test_drop_in_surface_call_counts_equal_the_reference(gold, tag, solver):
     counts = {k[2]: int(v) for k, v in st._call_counts.items()}
     ref_counts = dict(zip(g[f"{tag}_p{part}_{solver}_count_names"].tolist(), g[f"{tag}_p{part}_{solver}_count_values"].tolist()))
     assert counts == ref_counts, (counts, ref_counts)
+
+
+def test_sir_cuda_path_equals_the_reference_source(gold):
+    """The SIR model (sde/example_models/sir.py executed through the symnum stand-in inside the reference system):
+    point quantities and one constrained leapfrog step with each solver."""
+    g = gold
+    q0, xo, p_raw = g["sir_q0"], g["sir_xobs"], g["sir_p_raw"]
+    n, T = q0.shape[0], int(g["sir_T"])
+    mk = lambda: BatchedChains("sir", float(g["sir_obs_interval"]), int(g["sir_S"]), T, g["sir_y"], 5, n, noise=2)  # noqa: E731
+    bc = mk()
+    bc.set_state(q0, xo, 0, p=p_raw)
+    assert np.max(np.abs(bc.constr() - g["sir_c"])) < 1e-11 * max(1.0, float(np.max(np.abs(g["sir_y"]))))
+    bc.linearize(True)
+    assert np.max(np.abs(bc.log_det_sqrt_gram() - g["sir_ld"])) < 1e-10 * max(1.0, float(np.max(np.abs(g["sir_ld"]))))
+    for i in range(n):
+        assert _rel(bc.grad_log_det_sqrt_gram()[i], g["sir_grad_ld"][i]) < 1e-9
+    bc.project_momentum()
+    assert _rel(bc.get_state()[1], g["sir_p0"]) < 1e-9
+    bc.close()
+    for solver, name in ((0, "quasi_newton"), (1, "newton")):
+        bc = mk()
+        bc.opts.solver = solver
+        bc.set_state(q0, xo, 0, p=p_raw)
+        bc.linearize(True)
+        bc.project_momentum()
+        bc.leapfrog_step(float(g["sir_dt"]))
+        assert (bc.step_info()["status"] == 0).all()
+        q, p, _ = bc.get_state()
+        for i in range(n):
+            assert _rel(q[i], g[f"sir_{name}_q"][i]) < 1e-9 and _rel(p[i], g[f"sir_{name}_p"][i]) < 1e-8
+        bc.close()
